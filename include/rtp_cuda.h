@@ -1,0 +1,236 @@
+/*
+ * rtp_cuda.h -- C ABI of the B200-native (sm_100a) CUDA backend for the RealTimeParticles hot path.
+ *
+ * This library replaces, for the hot path only, the reference's OpenCL layer:
+ *   - CL::Context (string-keyed programs/kernels/buffers)         physics/ocl/Context.hpp:21-96
+ *   - RadixSort (vendored OCLRadixSort)                            physics/utils/RadixSort.hpp:37-65
+ *   - the kernel sequences of Boids/Fluids/Clouds::update()        physics/ocl/Boids.cpp:323-384,
+ *                                                                  physics/ocl/Fluids.cpp:400-471,
+ *                                                                  physics/ocl/Clouds.cpp:503-627
+ * It is bound from C++ by Physics::CUDA::{Boids,Fluids,Clouds} (realtimeparticles_b200/cpp/CudaModels.hpp),
+ * which derive from the unmodified Physics::Model (physics/Model.hpp:81-216), and from Python by ctypes
+ * (realtimeparticles_b200/_abi.py) for the headless bench harness and the parity tests.
+ *
+ * Conventions: plain pointers and sizes, no exceptions across the boundary. Every call returns RTP_OK (0)
+ * or a negative rtp_status; rtp_last_error() gives the text. One handle owns one CUDA device + one stream
+ * and, like a reference model, is not thread-safe. There is NO CPU fallback: without a usable CUDA device
+ * rtp_create() fails with RTP_ERR_CUDA.
+ */
+#ifndef RTP_CUDA_H
+#define RTP_CUDA_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#if defined(_WIN32)
+#define RTP_API __declspec(dllexport)
+#else
+#define RTP_API __attribute__((visibility("default")))
+#endif
+
+#define RTP_ABI_VERSION 1
+
+typedef enum rtp_status
+{
+  RTP_OK = 0,
+  RTP_ERR_INVALID = -1, /* bad argument / size mismatch / unknown field */
+  RTP_ERR_CUDA = -2, /* CUDA runtime error, no device */
+  RTP_ERR_STATE = -3, /* call not valid for this model type or state */
+  RTP_ERR_COMM = -4 /* multi-GPU exchange error */
+} rtp_status;
+
+/* Physics::ModelType, physics/Model.hpp:16-21 */
+typedef enum rtp_model
+{
+  RTP_MODEL_BOIDS = 0,
+  RTP_MODEL_FLUIDS = 1,
+  RTP_MODEL_CLOUDS = 2
+} rtp_model;
+
+/* Physics::Boundary, physics/Model.hpp:38-44 (boids only, Boids.cpp:363-373) */
+typedef enum rtp_boundary
+{
+  RTP_BOUNDARY_BOUNCING_WALL = 0,
+  RTP_BOUNDARY_CYCLIC_WALL = 1
+} rtp_boundary;
+
+/* Named device buffers. Names are the reference's string keys (SURVEY Appendix A:
+ * Boids.cpp:126-136, Fluids.cpp:132-147, Clouds.cpp:166-199). f4 = float4 (xyz, w=0), f = float, u = uint32. */
+typedef enum rtp_field
+{
+  RTP_F_POS = 0, /* p_pos            f4[M] */
+  RTP_F_COL = 1, /* p_col            f4[M] */
+  RTP_F_VEL = 2, /* p_vel            f4[M] */
+  RTP_F_ACC = 3, /* p_acc            f4[M]  boids */
+  RTP_F_PRED_POS = 4, /* p_predPos        f4[M]  fluids, clouds */
+  RTP_F_CORR_POS = 5, /* p_corrPos        f4[M]  fluids, clouds (written only with RTP_STEP_DEBUG_FIELDS) */
+  RTP_F_VORT = 6, /* p_vort           f4[M] */
+  RTP_F_TOT_CORR_POS = 7, /* p_totCorrPos     f4[M]  clouds */
+  RTP_F_DENSITY = 8, /* p_density        f[M] */
+  RTP_F_CONST_FACTOR = 9, /* p_constFactor / p_constFactorFld  f[M] */
+  RTP_F_TEMP = 10, /* p_temp           f[M]   clouds */
+  RTP_F_VAPOR_DENS = 11, /* p_vaporDens      f[M] */
+  RTP_F_CLOUD_DENS = 12, /* p_cloudDens      f[M] */
+  RTP_F_BUOYANCY = 13, /* p_buoyancy       f[M] */
+  RTP_F_CLOUD_GEN = 14, /* p_cloudGen       f[M] */
+  RTP_F_PART_ID = 15, /* p_partID         f[M] */
+  RTP_F_LAPLACIAN_TEMP = 16, /* p_laplacianTemp  f[M] */
+  RTP_F_CONST_FACTOR_TEMP = 17, /* p_constFactorTemp f[M] */
+  RTP_F_CORR_TEMP = 18, /* p_corrTemp       f[M] */
+  RTP_F_CELL_ID = 19, /* p_cellID         u[M]   (sorted keys after a step) */
+  RTP_F_CAMERA_DIST = 20, /* p_cameraDist     u[M] */
+  RTP_F_START_END_CELL = 21, /* c_startEndPartID uint2[C] */
+  RTP_F_PERM = 22, /* RadixSortIndices u[M]   permutation of the last cell sort: sorted[i] = unsorted[perm[i]] */
+  RTP_F_CAMERA_PERM = 23, /* permutation of the last camera sort, u[M] */
+  RTP_F_PART_DETECTOR = 24, /* c_partDetector   float8[C] */
+  RTP_F_COUNT_
+} rtp_field;
+
+/* Kernel parameter blocks: field order and sizes are those of the reference's POD structs, which travel by
+ * value into its kernels. */
+
+/* BoidsRuleKernelInputs, physics/ocl/Boids.hpp:14-20 (16 B) */
+typedef struct rtp_boids_params
+{
+  float velocityScale; /* 0.5  */
+  float alignmentScale; /* 1.6  */
+  float separationScale; /* 1.6  */
+  float cohesionScale; /* 1.45 */
+} rtp_boids_params;
+
+/* TargetKernelInputs, physics/ocl/Boids.hpp:22-26 (8 B) */
+typedef struct rtp_target_params
+{
+  float targetRadiusEffect; /* 2.0 */
+  int32_t targetSignEffect; /* +1 attract, -1 repulse */
+} rtp_target_params;
+
+/* FluidKernelInputs, physics/ocl/Fluids.hpp:17-32 == FluidParams, kernels/define.cl:13-25 (44 B) */
+typedef struct rtp_fluid_params
+{
+  float restDensity; /* 450 */
+  float relaxCFM; /* 600 */
+  float timeStep; /* 0.010 */
+  uint32_t dim; /* 3 */
+  uint32_t isArtPressureEnabled; /* 1 */
+  float artPressureRadius; /* 0.006 */
+  float artPressureCoeff; /* 0.001 */
+  uint32_t artPressureExp; /* 4 */
+  uint32_t isVorticityConfEnabled; /* 1 */
+  float vorticityConfCoeff; /* 0.0004 */
+  float xsphViscosityCoeff; /* 0.0001 */
+} rtp_fluid_params;
+
+/* CloudKernelInputs, physics/ocl/Clouds.hpp:15-45 == CloudParams, kernels/clouds.cl:19-33 (52 B) */
+typedef struct rtp_cloud_params
+{
+  uint32_t dim; /* 3 */
+  float timeStep; /* 0.01 */
+  float restDensity; /* 450 (copied from the Fluids block, Clouds.cpp:308) */
+  float groundHeatCoeff; /* 10 */
+  float buoyancyCoeff; /* 0.10 */
+  float gravCoeff; /* 0.0005 */
+  float adiabaticLapseRate; /* 5 */
+  float phaseTransitionRate; /* 0.3485 */
+  float latentHeatCoeff; /* 0.07 */
+  uint32_t isTempSmoothingEnabled; /* 1 */
+  float relaxCFM; /* 600 */
+  float initVaporDensityCoeff; /* 0.75 */
+  float windCoeff; /* 1.0 */
+} rtp_cloud_params;
+
+/* Construction parameters == the part of Physics::ModelParams (physics/Model.hpp:60-73) the backend needs,
+ * plus the per-model cap m_maxNbPartsInCell (Boids.cpp:78 -> 3000, Fluids.cpp:79 / Clouds.cpp:107 -> 100). */
+typedef struct rtp_config
+{
+  int32_t model; /* rtp_model */
+  int32_t device; /* CUDA device ordinal */
+  uint64_t max_particles; /* m_maxNbParticles (M) */
+  uint64_t nb_particles; /* m_currNbParticles (N <= M) */
+  uint32_t box[3]; /* m_boxSize (integers in the reference, Geometry.hpp:42-47) */
+  uint32_t grid[3]; /* m_gridRes */
+  uint32_t dim; /* 2 or 3 */
+  uint32_t max_parts_in_cell; /* 0 = model default */
+} rtp_config;
+
+typedef struct rtp_handle rtp_handle;
+
+/* rtp_step() flags. A reference update() == PHYSICS | RENDER_AUX | CAMERA_SORT; on pause it is
+ * CAMERA_SORT (+ clouds colour) only (Fluids.cpp:409, :466-468). */
+#define RTP_STEP_PHYSICS 0x1u /* the solver stages */
+#define RTP_STEP_RENDER_AUX 0x2u /* grid detector + colour kernels (grid.cl:43-60, fluids.cl:458-479, utils.cl:65-78) */
+#define RTP_STEP_CAMERA_SORT 0x4u /* fillCameraDist + second sort (utils.cl:43-52, Fluids.cpp:466-468) */
+#define RTP_STEP_DEBUG_FIELDS 0x8u /* also materialise intermediates a fused kernel would not write (p_corrPos) */
+
+/* ---- life cycle (replaces CL::Context::Get()/release(), createProgram/createBuffers/createKernels) ---- */
+RTP_API int rtp_abi_version(void);
+RTP_API int rtp_device_count(void);
+RTP_API int rtp_create(const rtp_config* cfg, rtp_handle** out);
+RTP_API void rtp_destroy(rtp_handle* h);
+RTP_API const char* rtp_last_error(const rtp_handle* h); /* h may be NULL: error of the last failed rtp_create */
+
+/* ---- buffers (replaces Context::loadBufferFromHost / unloadBufferFromDevice, Context.cpp:355-400) ---- */
+RTP_API int rtp_field_bytes(const rtp_handle* h, int field, size_t* bytes);
+RTP_API int rtp_upload(rtp_handle* h, int field, const void* host, size_t bytes);
+RTP_API int rtp_download(rtp_handle* h, int field, void* host, size_t bytes);
+/* device pointer of a field for zero-copy consumers (torch, CUDA-GL interop); valid until the next rtp_step */
+RTP_API int rtp_device_ptr(rtp_handle* h, int field, void** dptr);
+
+/* ---- parameters (replaces setKernelArg(.., sizeof(struct), &struct), Fluids.cpp:253-271 etc.) ---- */
+RTP_API int rtp_set_boids_params(rtp_handle* h, const rtp_boids_params* rules, const rtp_target_params* target,
+    const float target_pos[4], int target_active);
+RTP_API int rtp_set_fluid_params(rtp_handle* h, const rtp_fluid_params* fluid, int nb_jacobi_iters);
+RTP_API int rtp_set_cloud_params(rtp_handle* h, const rtp_cloud_params* cloud);
+RTP_API int rtp_set_boundary(rtp_handle* h, int boundary);
+RTP_API int rtp_set_nb_particles(rtp_handle* h, uint64_t n);
+RTP_API int rtp_set_dimension(rtp_handle* h, int dim);
+/* clouds colouring: which float field and which [min,max] (Clouds.cpp:610-617) */
+RTP_API int rtp_set_displayed_quantity(rtp_handle* h, int field, float min_val, float max_val);
+
+/* ---- reset-time kernels ---- */
+/* resetCellIDs + resetCameraDist over M (grid.cl:65-71, utils.cl:35; Fluids.cpp:214-215) */
+RTP_API int rtp_reset_ids(rtp_handle* h);
+/* cld_initTemperature + cld_initVaporDensity over M (clouds.cl:116-135; Clouds.cpp:495-497) */
+RTP_API int rtp_init_clouds_fields(rtp_handle* h);
+
+/* ---- the step (replaces the body of {Boids,Fluids,Clouds}::update()) ---- */
+RTP_API int rtp_step(rtp_handle* h, unsigned flags, const float camera_pos[3]);
+/* n back-to-back steps replayed from one CUDA graph (bench / headless runs); same result as n rtp_step calls */
+RTP_API int rtp_step_n(rtp_handle* h, unsigned flags, const float camera_pos[3], int n);
+RTP_API int rtp_sync(rtp_handle* h);
+
+/* ---- stand-alone access to the neighbour-search primitives (parity tests, other callers) ---- */
+/* stable ascending sort of n 32-bit keys (device pointers); perm_out[i] = index of the i-th smallest key.
+ * Replaces RadixSort::sort(key, ..) (RadixSort.cpp:122-161). key_bits = number of significant low bits. */
+RTP_API int rtp_sort_keys(rtp_handle* h, const uint32_t* d_keys_in, uint32_t* d_keys_out, uint32_t* d_perm_out,
+    uint64_t n, int key_bits);
+/* host-buffer convenience wrapper around rtp_sort_keys (H2D, sort, D2H) */
+RTP_API int rtp_sort_keys_host(rtp_handle* h, const uint32_t* keys_in, uint32_t* keys_out, uint32_t* perm_out,
+    uint64_t n, int key_bits);
+
+/* ---- profiling (replaces Context::enableProfiler + per-kernel event logging, Context.cpp:692-705) ---- */
+RTP_API int rtp_enable_profiling(rtp_handle* h, int enable);
+/* fills up to cap entries with the stage names / milliseconds of the last profiled step; returns the count */
+RTP_API int rtp_get_stage_times(rtp_handle* h, const char** names, float* ms, int cap);
+/* number of kernel launches issued by the last rtp_step / per step of rtp_step_n */
+RTP_API int rtp_last_launch_count(const rtp_handle* h);
+
+/* ---- initial-condition generators (host side; semantics of utils/Geometry.cpp:198-272) ---- */
+/* out: float4[res.x*res.y*res.z]; returns number of points or negative rtp_status */
+RTP_API int64_t rtp_gen_box_grid(float* out_xyzw, const int res[3], const float start[3], const float end[3]);
+RTP_API int64_t rtp_gen_sphere_grid(float* out_xyzw, const int res[3], const float start[3], const float end[3]);
+/* glibc rand()-driven uniform fill in (x,y,z) call order; seed<0 keeps the process' current rand() state */
+RTP_API int64_t rtp_gen_random_box(float* out_xyzw, int64_t n, const float start[3], const float end[3], int seed);
+/* the float a reference kernel sees for a -D constant: parse(FloatToStr(v)) (utils/Utils.cpp:24-29) */
+RTP_API float rtp_baked_constant(float v);
+
+/* ---- multi-GPU slab decomposition (new design): see rtp_cuda_sharded.h ---- */
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* RTP_CUDA_H */
