@@ -1,0 +1,309 @@
+"""ctypes binding of the C ABI in include/rtp_cuda.h (realtimeparticles_b200/lib/librtp_cuda.so).
+
+This is the only door into the compute path: there is no CPU or PyTorch fallback. If the shared library is missing
+or no CUDA device is usable, the calls raise.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "lib", "librtp_cuda.so")
+
+RTP_OK = 0
+
+# rtp_model
+BOIDS, FLUIDS, CLOUDS = 0, 1, 2
+# rtp_boundary
+BOUNCING_WALL, CYCLIC_WALL = 0, 1
+# rtp_step flags
+STEP_PHYSICS, STEP_RENDER_AUX, STEP_CAMERA_SORT, STEP_DEBUG_FIELDS = 1, 2, 4, 8
+STEP_UPDATE = STEP_PHYSICS | STEP_RENDER_AUX | STEP_CAMERA_SORT  # a full reference update()
+
+# rtp_field
+FIELDS = dict(POS=0, COL=1, VEL=2, ACC=3, PRED_POS=4, CORR_POS=5, VORT=6, TOT_CORR_POS=7, DENSITY=8,
+              CONST_FACTOR=9, TEMP=10, VAPOR_DENS=11, CLOUD_DENS=12, BUOYANCY=13, CLOUD_GEN=14, PART_ID=15,
+              LAPLACIAN_TEMP=16, CONST_FACTOR_TEMP=17, CORR_TEMP=18, CELL_ID=19, CAMERA_DIST=20,
+              START_END_CELL=21, PERM=22, CAMERA_PERM=23, PART_DETECTOR=24)
+# the reference's buffer names -> field ids
+BUFFER_NAMES = {"p_pos": 0, "p_col": 1, "p_vel": 2, "p_acc": 3, "p_predPos": 4, "p_corrPos": 5, "p_vort": 6,
+                "p_totCorrPos": 7, "p_density": 8, "p_constFactor": 9, "p_constFactorFld": 9, "p_temp": 10,
+                "p_vaporDens": 11, "p_cloudDens": 12, "p_buoyancy": 13, "p_cloudGen": 14, "p_partID": 15,
+                "p_laplacianTemp": 16, "p_constFactorTemp": 17, "p_corrTemp": 18, "p_cellID": 19,
+                "p_cameraDist": 20, "c_startEndPartID": 21, "RadixSortIndices": 22, "c_partDetector": 24}
+_F4 = {0, 1, 2, 3, 4, 5, 6, 7}
+_U32 = {19, 20, 22, 23}
+
+
+class Config(C.Structure):
+    _fields_ = [("model", C.c_int32), ("device", C.c_int32), ("max_particles", C.c_uint64),
+                ("nb_particles", C.c_uint64), ("box", C.c_uint32 * 3), ("grid", C.c_uint32 * 3),
+                ("dim", C.c_uint32), ("max_parts_in_cell", C.c_uint32)]
+
+
+class BoidsParams(C.Structure):
+    """BoidsRuleKernelInputs, physics/ocl/Boids.hpp:14-20"""
+    _fields_ = [("velocityScale", C.c_float), ("alignmentScale", C.c_float), ("separationScale", C.c_float),
+                ("cohesionScale", C.c_float)]
+
+
+class TargetParams(C.Structure):
+    """TargetKernelInputs, physics/ocl/Boids.hpp:22-26"""
+    _fields_ = [("targetRadiusEffect", C.c_float), ("targetSignEffect", C.c_int32)]
+
+
+class FluidParams(C.Structure):
+    """FluidKernelInputs, physics/ocl/Fluids.hpp:17-32"""
+    _fields_ = [("restDensity", C.c_float), ("relaxCFM", C.c_float), ("timeStep", C.c_float), ("dim", C.c_uint32),
+                ("isArtPressureEnabled", C.c_uint32), ("artPressureRadius", C.c_float),
+                ("artPressureCoeff", C.c_float), ("artPressureExp", C.c_uint32),
+                ("isVorticityConfEnabled", C.c_uint32), ("vorticityConfCoeff", C.c_float),
+                ("xsphViscosityCoeff", C.c_float)]
+
+
+class CloudParams(C.Structure):
+    """CloudKernelInputs, physics/ocl/Clouds.hpp:15-45"""
+    _fields_ = [("dim", C.c_uint32), ("timeStep", C.c_float), ("restDensity", C.c_float),
+                ("groundHeatCoeff", C.c_float), ("buoyancyCoeff", C.c_float), ("gravCoeff", C.c_float),
+                ("adiabaticLapseRate", C.c_float), ("phaseTransitionRate", C.c_float),
+                ("latentHeatCoeff", C.c_float), ("isTempSmoothingEnabled", C.c_uint32), ("relaxCFM", C.c_float),
+                ("initVaporDensityCoeff", C.c_float), ("windCoeff", C.c_float)]
+
+
+assert C.sizeof(BoidsParams) == 16 and C.sizeof(TargetParams) == 8
+assert C.sizeof(FluidParams) == 44 and C.sizeof(CloudParams) == 52
+
+# every symbol include/rtp_cuda.h declares
+EXPORTS = ["rtp_abi_version", "rtp_device_count", "rtp_create", "rtp_destroy", "rtp_last_error", "rtp_field_bytes",
+           "rtp_upload", "rtp_download", "rtp_device_ptr", "rtp_set_boids_params", "rtp_set_fluid_params",
+           "rtp_set_cloud_params", "rtp_set_boundary", "rtp_set_nb_particles", "rtp_set_dimension",
+           "rtp_set_displayed_quantity", "rtp_reset_ids", "rtp_init_clouds_fields", "rtp_step", "rtp_step_n",
+           "rtp_sync", "rtp_sort_keys", "rtp_sort_keys_host", "rtp_enable_profiling", "rtp_get_stage_times",
+           "rtp_last_launch_count", "rtp_gen_box_grid", "rtp_gen_sphere_grid", "rtp_gen_random_box",
+           "rtp_baked_constant"]
+
+_lib = None
+
+
+def lib():
+    """Load librtp_cuda.so; fail loudly when the CUDA extension has not been built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise RuntimeError(
+            "realtimeparticles_b200: %s is missing. Build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+            "or `make -C realtimeparticles_b200/csrc`. There is no CPU fallback." % LIB_PATH)
+    L = C.CDLL(LIB_PATH)
+    vp, u32p, fp = C.c_void_p, C.POINTER(C.c_uint32), C.POINTER(C.c_float)
+    L.rtp_abi_version.restype = C.c_int
+    L.rtp_device_count.restype = C.c_int
+    L.rtp_create.argtypes = [C.POINTER(Config), C.POINTER(vp)]
+    L.rtp_destroy.argtypes = [vp]
+    L.rtp_destroy.restype = None
+    L.rtp_last_error.argtypes = [vp]
+    L.rtp_last_error.restype = C.c_char_p
+    L.rtp_field_bytes.argtypes = [vp, C.c_int, C.POINTER(C.c_size_t)]
+    L.rtp_upload.argtypes = [vp, C.c_int, vp, C.c_size_t]
+    L.rtp_download.argtypes = [vp, C.c_int, vp, C.c_size_t]
+    L.rtp_device_ptr.argtypes = [vp, C.c_int, C.POINTER(vp)]
+    L.rtp_set_boids_params.argtypes = [vp, C.POINTER(BoidsParams), C.POINTER(TargetParams), fp, C.c_int]
+    L.rtp_set_fluid_params.argtypes = [vp, C.POINTER(FluidParams), C.c_int]
+    L.rtp_set_cloud_params.argtypes = [vp, C.POINTER(CloudParams)]
+    L.rtp_set_boundary.argtypes = [vp, C.c_int]
+    L.rtp_set_nb_particles.argtypes = [vp, C.c_uint64]
+    L.rtp_set_dimension.argtypes = [vp, C.c_int]
+    L.rtp_set_displayed_quantity.argtypes = [vp, C.c_int, C.c_float, C.c_float]
+    L.rtp_reset_ids.argtypes = [vp]
+    L.rtp_init_clouds_fields.argtypes = [vp]
+    L.rtp_step.argtypes = [vp, C.c_uint, fp]
+    L.rtp_step_n.argtypes = [vp, C.c_uint, fp, C.c_int]
+    L.rtp_sync.argtypes = [vp]
+    L.rtp_sort_keys.argtypes = [vp, vp, vp, vp, C.c_uint64, C.c_int]
+    L.rtp_sort_keys_host.argtypes = [vp, vp, vp, vp, C.c_uint64, C.c_int]
+    L.rtp_enable_profiling.argtypes = [vp, C.c_int]
+    L.rtp_get_stage_times.argtypes = [vp, C.POINTER(C.c_char_p), fp, C.c_int]
+    L.rtp_last_launch_count.argtypes = [vp]
+    for g in ("rtp_gen_box_grid", "rtp_gen_sphere_grid"):
+        getattr(L, g).argtypes = [vp, C.POINTER(C.c_int), fp, fp]
+        getattr(L, g).restype = C.c_int64
+    L.rtp_gen_random_box.argtypes = [vp, C.c_int64, fp, fp, C.c_int]
+    L.rtp_gen_random_box.restype = C.c_int64
+    L.rtp_baked_constant.argtypes = [C.c_float]
+    L.rtp_baked_constant.restype = C.c_float
+    _lib = L
+    return L
+
+
+class RtpError(RuntimeError):
+    pass
+
+
+def _f3(v):
+    return (C.c_float * 3)(*[float(x) for x in v])
+
+
+def field_id(f):
+    if isinstance(f, str):
+        return BUFFER_NAMES[f] if f in BUFFER_NAMES else FIELDS[f]
+    return int(f)
+
+
+def _np_layout(fid, nbytes):
+    if fid in _F4:
+        return np.float32, (nbytes // 16, 4)
+    if fid in _U32:
+        return np.uint32, (nbytes // 4,)
+    if fid == FIELDS["START_END_CELL"]:
+        return np.uint32, (nbytes // 8, 2)
+    if fid == FIELDS["PART_DETECTOR"]:
+        return np.float32, (nbytes // 32, 8)
+    return np.float32, (nbytes // 4,)
+
+
+class Handle:
+    """Owns one rtp_handle (one CUDA device + stream + all named buffers of one model)."""
+
+    def __init__(self, model, max_particles, nb_particles, box=(10, 10, 10), grid=(30, 30, 30), dim=3,
+                 max_parts_in_cell=0, device=0):
+        self.L = lib()
+        cfg = Config(model, device, max_particles, nb_particles, (C.c_uint32 * 3)(*box), (C.c_uint32 * 3)(*grid),
+                     dim, max_parts_in_cell)
+        h = C.c_void_p()
+        rc = self.L.rtp_create(C.byref(cfg), C.byref(h))
+        if rc != RTP_OK:
+            raise RtpError("rtp_create failed (%d): %s" % (rc, (self.L.rtp_last_error(None) or b"").decode()))
+        self.h = h
+        self.model, self.M, self.N = model, max_particles, nb_particles
+        self.ncells = grid[0] * grid[1] * grid[2]
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.L.rtp_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        self.close()
+
+    def _check(self, rc, what):
+        if rc != RTP_OK:
+            raise RtpError("%s failed (%d): %s" % (what, rc, (self.L.rtp_last_error(self.h) or b"").decode()))
+
+    def field_bytes(self, f):
+        n = C.c_size_t()
+        self._check(self.L.rtp_field_bytes(self.h, field_id(f), C.byref(n)), "rtp_field_bytes")
+        return n.value
+
+    def upload(self, f, arr):
+        fid = field_id(f)
+        n = self.field_bytes(fid)
+        dt, shape = _np_layout(fid, n)
+        a = np.ascontiguousarray(np.asarray(arr, dtype=dt).reshape(shape))
+        self._check(self.L.rtp_upload(self.h, fid, a.ctypes.data, a.nbytes), "rtp_upload")
+
+    def download(self, f, out=None):
+        fid = field_id(f)
+        n = self.field_bytes(fid)
+        dt, shape = _np_layout(fid, n)
+        if out is None:
+            out = np.empty(shape, dt)
+        self._check(self.L.rtp_download(self.h, fid, out.ctypes.data, out.nbytes), "rtp_download")
+        return out
+
+    def device_ptr(self, f):
+        p = C.c_void_p()
+        self._check(self.L.rtp_device_ptr(self.h, field_id(f), C.byref(p)), "rtp_device_ptr")
+        return p.value
+
+    def set_boids_params(self, rules, target=None, target_pos=None, target_active=False):
+        tp = (C.c_float * 4)(*target_pos) if target_pos is not None else None
+        self._check(self.L.rtp_set_boids_params(self.h, C.byref(rules), C.byref(target) if target is not None else None,
+                                                tp, int(target_active)), "rtp_set_boids_params")
+
+    def set_fluid_params(self, p, jacobi):
+        self._check(self.L.rtp_set_fluid_params(self.h, C.byref(p), int(jacobi)), "rtp_set_fluid_params")
+
+    def set_cloud_params(self, p):
+        self._check(self.L.rtp_set_cloud_params(self.h, C.byref(p)), "rtp_set_cloud_params")
+
+    def set_boundary(self, b):
+        self._check(self.L.rtp_set_boundary(self.h, int(b)), "rtp_set_boundary")
+
+    def set_nb_particles(self, n):
+        self._check(self.L.rtp_set_nb_particles(self.h, int(n)), "rtp_set_nb_particles")
+        self.N = int(n)
+
+    def set_dimension(self, d):
+        self._check(self.L.rtp_set_dimension(self.h, int(d)), "rtp_set_dimension")
+
+    def set_displayed_quantity(self, f, lo, hi):
+        self._check(self.L.rtp_set_displayed_quantity(self.h, field_id(f), lo, hi), "rtp_set_displayed_quantity")
+
+    def reset_ids(self):
+        self._check(self.L.rtp_reset_ids(self.h), "rtp_reset_ids")
+
+    def init_clouds_fields(self):
+        self._check(self.L.rtp_init_clouds_fields(self.h), "rtp_init_clouds_fields")
+
+    def step(self, flags=STEP_PHYSICS, cam=(32.0, -1.2, 0.0)):
+        self._check(self.L.rtp_step(self.h, flags, _f3(cam)), "rtp_step")
+
+    def step_n(self, n, flags=STEP_PHYSICS, cam=(32.0, -1.2, 0.0)):
+        self._check(self.L.rtp_step_n(self.h, flags, _f3(cam), int(n)), "rtp_step_n")
+
+    def sync(self):
+        self._check(self.L.rtp_sync(self.h), "rtp_sync")
+
+    def sort_keys_host(self, keys, key_bits=32):
+        keys = np.ascontiguousarray(keys, dtype=np.uint32)
+        out, perm = np.empty_like(keys), np.empty_like(keys)
+        self._check(self.L.rtp_sort_keys_host(self.h, keys.ctypes.data, out.ctypes.data, perm.ctypes.data, keys.size,
+                                              key_bits), "rtp_sort_keys_host")
+        return out, perm
+
+    def enable_profiling(self, on):
+        self._check(self.L.rtp_enable_profiling(self.h, int(on)), "rtp_enable_profiling")
+
+    def stage_times(self):
+        cap = 64
+        names = (C.c_char_p * cap)()
+        ms = (C.c_float * cap)()
+        n = self.L.rtp_get_stage_times(self.h, names, ms, cap)
+        return [(names[i].decode(), float(ms[i])) for i in range(min(n, cap))]
+
+    def last_launch_count(self):
+        return int(self.L.rtp_last_launch_count(self.h))
+
+
+def gen_box_grid(res, start, end):
+    """Uniform lattice, x-major order (utils/Geometry.cpp:198-227); float4 rows."""
+    n = res[0] * res[1] * res[2]
+    out = np.empty((n, 4), np.float32)
+    r = lib().rtp_gen_box_grid(out.ctypes.data, (C.c_int * 3)(*res), _f3(start), _f3(end))
+    if r != n:
+        raise RtpError("rtp_gen_box_grid failed: %d" % r)
+    return out
+
+
+def gen_sphere_grid(res, start, end):
+    """Spherical lattice (utils/Geometry.cpp:243-272); float4 rows."""
+    n = res[0] * res[1] * res[2]
+    out = np.empty((n, 4), np.float32)
+    r = lib().rtp_gen_sphere_grid(out.ctypes.data, (C.c_int * 3)(*res), _f3(start), _f3(end))
+    if r != n:
+        raise RtpError("rtp_gen_sphere_grid failed: %d" % r)
+    return out
+
+
+def gen_random_box(n, start, end, seed=1):
+    """glibc rand() uniform fill in x,y,z call order (utils/Geometry.cpp:229-239); seed=1 == a fresh process."""
+    out = np.empty((n, 4), np.float32)
+    r = lib().rtp_gen_random_box(out.ctypes.data, n, _f3(start), _f3(end), seed)
+    if r != n:
+        raise RtpError("rtp_gen_random_box failed: %d" % r)
+    return out
+
+
+def baked_constant(v):
+    return float(lib().rtp_baked_constant(float(v)))

@@ -1,0 +1,195 @@
+// boids.cu -- Reynolds boids on the uniform grid (reference: physics/ocl/kernels/boids.cl, host sequence
+// Boids::update physics/ocl/Boids.cpp:323-384).
+//
+// Step = 3 model launches around the sort:
+//   boidsCellIdsKernel : fillCellIDs on p_pos (grid.cl:76-86) + resetStartEndCell (grid.cl:91-96)
+//   boidsGatherKernel  : payload permutation of p_pos/p_vel (radixSort.cl:179-190) into the sorted working copies,
+//                        pre-normalised neighbour velocities, fillStartCell/fillEndCell (grid.cl:101-138)
+//   boidsRulesKernel   : bd_applyBoidsRulesWithGrid3D/2D (boids.cl:46-221) fused with bd_addTargetRule (:226-241),
+//                        bd_updateVel (:246-259) and bd_updatePosAndApply{Wall,Periodic}BC (:264-315)
+// p_acc and p_col are not permuted by the cell sort: p_acc is fully rewritten every step and p_col is uniform.
+// The whole rule evaluation is bit-exact with the oracle: exact hit test, sums in the reference's order, IEEE
+// divisions.
+#include "kernels.cuh"
+
+namespace rtp
+{
+constexpr int BD_THREADS = 128;
+
+__device__ __forceinline__ void fillCellTable(const u32* __restrict__ keys, u32 i, u32 N, u32 numCells, uint2* __restrict__ table)
+{
+  const u32 id = keys[i];
+  if (id < numCells)
+  {
+    // fillStartCell grid.cl:101-117: sorted index 0 never writes its start (reset value 1 stays)
+    if (i > 0 && id != keys[i - 1])
+      table[id].x = i;
+    // fillEndCell grid.cl:122-138: cellID[N] is a tail key >= 2C (or out of bounds when N == M): never equal
+    const u32 next = (i + 1 < N) ? keys[i + 1] : 0xFFFFFFFFu;
+    if (id != next)
+      table[id].y = i;
+  }
+}
+
+__global__ void __launch_bounds__(256) boidsCellIdsKernel(const float4* __restrict__ pos, GridParams g, u32* __restrict__ keys,
+    uint2* __restrict__ table, u32 N)
+{
+  const u32 i = blockIdx.x * 256 + threadIdx.x;
+  if (i < g.numCells)
+    table[i] = make_uint2(1u, 0u);
+  if (i < N)
+  {
+    const float4 p = pos[i];
+    keys[i] = cell1D(g, p.x, p.y, p.z);
+  }
+}
+
+__global__ void __launch_bounds__(256) boidsGatherKernel(DeviceState s, GridParams g)
+{
+  const u32 i = blockIdx.x * 256 + threadIdx.x;
+  if (i >= s.N)
+    return;
+  const u32 j = s.perm[i];
+  s.posB[i] = s.posA[j];
+  const float4 v = s.velA[j];
+  s.velB[i] = v;
+  // fast_normalize(velocity[e]) (boids.cl:104) depends on e only: do it once per particle, exactly
+  const float r = fdiv(1.0f, fsqrt(dot3c(v.x, v.y, v.z, v.x, v.y, v.z)));
+  s.velC[i] = make_float4(fmul(v.x, r), fmul(v.y, r), fmul(v.z, r), fmul(v.w, r));
+  fillCellTable(s.cellID, i, s.N, g.numCells, s.table);
+}
+
+template <bool DIM2>
+__global__ void __launch_bounds__(BD_THREADS) boidsRulesKernel(DeviceState s, GridParams g, SphConsts c, BoidsStepParams p)
+{
+  const u32 i = blockIdx.x * BD_THREADS + threadIdx.x;
+  if (i >= s.N)
+    return;
+  const float4* __restrict__ P = s.posB;
+  const float4* __restrict__ NV = s.velC;
+  const float4 pi = P[i];
+  const int3 ci = cell3D(g, pi.x, pi.y, pi.z);
+
+  int count = 0;
+  float apx = 0.f, apy = 0.f, apz = 0.f; // averageBoidsPos
+  float avx = 0.f, avy = 0.f, avz = 0.f; // averageBoidsVel
+  float rpx = 0.f, rpy = 0.f, rpz = 0.f; // repulseHeading
+
+  auto visit = [&](u32 start, u32 end, float, float)
+  {
+    for (u32 e = start; e <= end; ++e)
+    {
+      const float4 pj = ld4(P, e);
+      const float dx = pi.x - pj.x, dy = pi.y - pj.y, dz = pi.z - pj.z;
+      const float sq = dot3c(dx, dy, dz, dx, dy, dz);
+      if (sq < c.effectRadiusSq && sq > RTP_FLOAT_EPS)
+      {
+        const float4 nv = ld4(NV, e);
+        apx += pj.x; apy += pj.y; apz += pj.z;
+        avx += nv.x; avy += nv.y; avz += nv.z;
+        rpx += fdiv(dx, sq); rpy += fdiv(dy, sq); rpz += fdiv(dz, sq);
+        ++count;
+      }
+    }
+  };
+
+  if (!DIM2)
+  {
+    forEachNeighbourCell<TRAV_BOIDS>(g, s.table, ci, visit);
+  }
+  else
+  {
+    // boids.cl:170-183: 9 YZ cells, every axis tested against GRID_RES_X, x cell forced to GRID_RES_X / 2
+    const int RX = g.res[0], RY = g.res[1];
+    for (int iY = -1; iY <= 1; ++iY)
+      for (int iZ = -1; iZ <= 1; ++iZ)
+      {
+        const int cx = ci.x, cy = ci.y + iY, cz = ci.z + iZ;
+        if (cx < 0 || cy < 0 || cz < 0 || cx >= RX || cy >= RX || cz >= RX)
+          continue;
+        const uint2 se = __ldg(&s.table[(RX / 2 * RX + cy) * RY + cz]);
+        visit(se.x, se.y, 0.f, 0.f);
+      }
+  }
+
+  float ax = 0.f, ay = 0.f, az = 0.f;
+  if (count != 0)
+  {
+    // boids.cl:115-131
+    const float fc = (float)count;
+    apx = fsub(fdiv(apx, fc), pi.x); apy = fsub(fdiv(apy, fc), pi.y); apz = fsub(fdiv(apz, fc), pi.z);
+    float r = fdiv(1.0f, fsqrt(dot3c(apx, apy, apz, apx, apy, apz)));
+    apx = fmul(fmul(apx, r), p.rules.velocityScale); apy = fmul(fmul(apy, r), p.rules.velocityScale); apz = fmul(fmul(apz, r), p.rules.velocityScale);
+    r = fdiv(1.0f, fsqrt(dot3c(avx, avy, avz, avx, avy, avz)));
+    avx = fmul(fmul(avx, r), p.rules.velocityScale); avy = fmul(fmul(avy, r), p.rules.velocityScale); avz = fmul(fmul(avz, r), p.rules.velocityScale);
+    r = fdiv(1.0f, fsqrt(dot3c(rpx, rpy, rpz, rpx, rpy, rpz)));
+    rpx = fmul(fmul(rpx, r), p.rules.velocityScale); rpy = fmul(fmul(rpy, r), p.rules.velocityScale); rpz = fmul(fmul(rpz, r), p.rules.velocityScale);
+    ax = fadd(fadd(fmul(avx, p.rules.alignmentScale), fmul(rpx, p.rules.separationScale)), fmul(apx, p.rules.cohesionScale));
+    ay = fadd(fadd(fmul(avy, p.rules.alignmentScale), fmul(rpy, p.rules.separationScale)), fmul(apy, p.rules.cohesionScale));
+    az = fadd(fadd(fmul(avz, p.rules.alignmentScale), fmul(rpz, p.rules.separationScale)), fmul(apz, p.rules.cohesionScale));
+  }
+
+  // bd_addTargetRule boids.cl:226-241
+  if (p.targetActive)
+  {
+    const float tx = fsub(p.targetPos[0], pi.x), ty = fsub(p.targetPos[1], pi.y), tz = fsub(p.targetPos[2], pi.z);
+    const float dist = fsqrt(dot3c(tx, ty, tz, tx, ty, tz));
+    if (dist < p.target.targetRadiusEffect)
+    {
+      const float sgn = (float)p.target.targetSignEffect;
+      const float k = fclamp(fdiv(1.3f, dist), 0.0f, 1.4f * RTP_MAX_STEERING);
+      ax = fadd(ax, fmul(fmul(tx, sgn), k));
+      ay = fadd(ay, fmul(fmul(ty, sgn), k));
+      az = fadd(az, fmul(fmul(tz, sgn), k));
+    }
+  }
+  s.acc[i] = make_float4(ax, ay, az, 0.f);
+
+  // bd_updateVel boids.cl:246-259
+  const float4 vi = s.velB[i];
+  const float maxV = p.rules.velocityScale;
+  float nvx = fadd(vi.x, fmul(ax, p.dt)), nvy = fadd(vi.y, fmul(ay, p.dt)), nvz = fadd(vi.z, fmul(az, p.dt));
+  const float len = fsqrt(dot3c(nvx, nvy, nvz, nvx, nvy, nvz));
+  const float norm = fclamp(len, fmul(0.2f, maxV), maxV);
+  const float rn = fdiv(1.0f, len);
+  float vx = fmul(fmul(nvx, rn), norm), vy = fmul(fmul(nvy, rn), norm), vz = fmul(fmul(nvz, rn), norm);
+
+  // bd_updatePosAndApplyWallBC boids.cl:264-284 / bd_updatePosAndApplyPeriodicBC :289-315
+  const float npx = fadd(pi.x, fmul(vx, p.dt)), npy = fadd(pi.y, fmul(vy, p.dt)), npz = fadd(pi.z, fmul(vz, p.dt));
+  float cpx = fclamp(npx, -g.absW[0], g.absW[0]), cpy = fclamp(npy, -g.absW[1], g.absW[1]), cpz = fclamp(npz, -g.absW[2], g.absW[2]);
+  if (p.boundary == RTP_BOUNDARY_CYCLIC_WALL)
+  {
+    if (!(cpx == npx)) cpx = fmul(cpx, -1.0f);
+    if (!(cpy == npy)) cpy = fmul(cpy, -1.0f);
+    if (!(cpz == npz)) cpz = fmul(cpz, -1.0f);
+  }
+  else if (!(cpx == npx && cpy == npy && cpz == npz))
+  {
+    vx = fmul(vx, -0.5f); vy = fmul(vy, -0.5f); vz = fmul(vz, -0.5f);
+  }
+  s.posA[i] = make_float4(cpx, cpy, cpz, 0.f);
+  s.velA[i] = make_float4(vx, vy, vz, 0.f);
+}
+
+void launchBoidsCellIds(const DeviceState& s, const GridParams& g, u32* keysOut, cudaStream_t st)
+{
+  const u32 n = max(s.N, g.numCells);
+  boidsCellIdsKernel<<<(n + 255) / 256, 256, 0, st>>>(s.posA, g, keysOut, s.table, s.N);
+}
+void launchBoidsGather(const DeviceState& s, const GridParams& g, cudaStream_t st)
+{
+  if (s.N)
+    boidsGatherKernel<<<(s.N + 255) / 256, 256, 0, st>>>(s, g);
+}
+void launchBoidsRules(const DeviceState& s, const GridParams& g, const SphConsts& c, const BoidsStepParams& p, cudaStream_t st)
+{
+  if (!s.N)
+    return;
+  const int blocks = (s.N + BD_THREADS - 1) / BD_THREADS;
+  if (p.dim == 2)
+    boidsRulesKernel<true><<<blocks, BD_THREADS, 0, st>>>(s, g, c, p);
+  else
+    boidsRulesKernel<false><<<blocks, BD_THREADS, 0, st>>>(s, g, c, p);
+}
+
+} // namespace rtp

@@ -1,0 +1,633 @@
+// fluids.cu -- Position Based Fluids solver and its clouds extension on the uniform grid.
+// Reference: physics/ocl/kernels/{sph,fluids,clouds}.cl; host sequences Fluids::update (physics/ocl/Fluids.cpp:400-471)
+// and Clouds::update (physics/ocl/Clouds.cpp:503-627).
+//
+// Launches per fluids step with I Jacobi iterations (reference: 3 + 5 I + 5 + buffer copies around two sorts):
+//   fluidPredictKernel      fld_predictPosition (fluids.cl:62-74) + fillCellIDs on p_predPos (grid.cl:76-86)
+//                           + resetStartEndCell (grid.cl:91-96)
+//   [sort]                  sort.cu
+//   fluidGatherKernel       payload permutation of p_pos, p_vel, p_predPos (radixSort.cl:179-190) + first
+//                           fld_applyBoundaryCondition (fluids.cl:435-439) + fillStartCell/fillEndCell (grid.cl:101-138)
+//   [adjustEndCell]         grid.cu
+//   I x densityLambdaKernel fld_computeDensity (:80-126) + fld_computeConstraintFactor (:131-193) in ONE sweep
+//   I x correctionKernel    fld_computeConstraintCorrection (:198-247) + fld_correctPosition (:252-258) + the next
+//                           iteration's boundary clamp; the last one also does fld_updateVel (:263-273)
+//   vorticityKernel         fld_computeVorticity (:278-324)
+//   confinementKernel       fld_applyVorticityConfinement (:329-377), writes the copy p_velInViscosity (Fluids.cpp:451)
+//   xsphKernel              fld_applyXsphViscosityCorrection (:383-430) + fld_updatePosition (:444-450)
+// The clouds variants use the same kernels with the periodic-image traversal (clouds.cl:334-347).
+//
+// Numerics: hit tests and all element-wise stages are bit-exact (rtp_common.cuh); pair terms inside the sums use
+// FMA contraction and MUFU rsqrt/rcp (tolerance class). Sums run in the reference's order (27 cells, ascending e).
+#include "kernels.cuh"
+
+namespace rtp
+{
+constexpr int NB_THREADS = 128; // neighbour kernels
+constexpr int EW_THREADS = 256; // element-wise kernels
+
+__device__ __forceinline__ float rsqrtApprox(float x)
+{
+  float r;
+  asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return r;
+}
+__device__ __forceinline__ float rcpApprox(float x)
+{
+  float r;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return r;
+}
+
+__device__ __forceinline__ void fillCellTable(const u32* __restrict__ keys, u32 i, u32 N, u32 numCells, uint2* __restrict__ table)
+{
+  const u32 id = keys[i];
+  if (id < numCells)
+  {
+    if (i > 0 && id != keys[i - 1]) // fillStartCell grid.cl:101-117
+      table[id].x = i;
+    const u32 next = (i + 1 < N) ? keys[i + 1] : 0xFFFFFFFFu; // fillEndCell grid.cl:122-138
+    if (id != next)
+      table[id].y = i;
+  }
+}
+
+// fld_applyBoundaryCondition fluids.cl:435-439
+__device__ __forceinline__ float4 fluidBoundary(const GridParams& g, float4 p)
+{
+  p.x = fclamp(p.x, fadd(-g.absW[0], 0.01f), fsub(g.absW[0], 0.1f));
+  p.y = fclamp(p.y, fadd(-g.absW[1], 0.01f), fsub(g.absW[1], 0.1f));
+  p.z = fclamp(p.z, fadd(-g.absW[2], 0.01f), fsub(g.absW[2], 0.1f));
+  p.w = 0.0f;
+  return p;
+}
+// cld_applyMixedBoundaryConditions clouds.cl:279-299
+__device__ __forceinline__ float4 cloudBoundary(const GridParams& g, float4 np)
+{
+  float4 p = np;
+  const float cx = fclamp(np.x, -g.absW[0], g.absW[0]), cy = fclamp(np.y, -g.absW[1], g.absW[1]), cz = fclamp(np.z, -g.absW[2], g.absW[2]);
+  if (fabsf(np.x) > g.absW[0]) p.x = fsub(np.x, fmul(2.0f, cx));
+  if (fabsf(np.y) > g.absW[1]) p.y = cy;
+  if (fabsf(np.z) > g.absW[2]) p.z = fsub(np.z, fmul(2.0f, cz));
+  return p;
+}
+
+// Visit every candidate j of particle i in the reference's order and call pairF for those inside the support.
+template <int TRAV, typename PairF>
+__device__ __forceinline__ void sweepNeighbours(const GridParams& g, const SphConsts& c, const uint2* __restrict__ table,
+    const float4* __restrict__ P, const float4 pi, PairF&& pairF)
+{
+  const int3 ci = cell3D(g, pi.x, pi.y, pi.z);
+  forEachNeighbourCell<TRAV>(g, table, ci,
+      [&](u32 start, u32 end, float sx, float sz)
+      {
+        for (u32 e = start; e <= end; ++e)
+        {
+          const float4 pj = ld4(P, e);
+          float dx = pi.x - pj.x, dy = pi.y - pj.y, dz = pi.z - pj.z;
+          if (TRAV == TRAV_CLOUDS)
+          {
+            dx = dx - sx; // pos - predPos[e] - absWall * signAbsWall, clouds.cl:356
+            dz = dz - sz;
+          }
+          const float sq = dot3c(dx, dy, dz, dx, dy, dz);
+          if (sq < c.supportSq)
+            pairF(e, dx, dy, dz, sq);
+        }
+      });
+}
+
+// |gradSpiky| / (-3 SPIKY_COEFF |vec|) = (h - len)^2 / len   (sph.cl:26-34; the constant is applied after the sum)
+__device__ __forceinline__ float spikyScalar(const SphConsts& c, float sq)
+{
+  const float rinv = rsqrtApprox(sq);
+  const float hl = c.h - sq * rinv;
+  return hl * hl * rinv;
+}
+
+// ------------------------------------------------------------------ element-wise kernels
+
+__global__ void __launch_bounds__(EW_THREADS) fluidPredictKernel(DeviceState s, GridParams g, float dt, u32* __restrict__ keys)
+{
+  const u32 i = blockIdx.x * EW_THREADS + threadIdx.x;
+  if (i < g.numCells)
+    s.table[i] = make_uint2(1u, 0u);
+  if (i >= s.N)
+    return;
+  const float4 p = s.posA[i], v = s.velA[i];
+  // newVel = vel + GRAVITY_ACC * dt ; predPos = pos + newVel * dt
+  const float nvx = fadd(v.x, fmul(0.0f, dt)), nvy = fadd(v.y, fmul(-RTP_ABS_GRAVITY_ACC_Y, dt)), nvz = fadd(v.z, fmul(0.0f, dt));
+  const float4 pr = make_float4(fadd(p.x, fmul(nvx, dt)), fadd(p.y, fmul(nvy, dt)), fadd(p.z, fmul(nvz, dt)), 0.0f);
+  s.pred0[i] = pr;
+  keys[i] = cell1D(g, pr.x, pr.y, pr.z);
+}
+
+__global__ void __launch_bounds__(EW_THREADS) fluidGatherKernel(DeviceState s, GridParams g)
+{
+  const u32 i = blockIdx.x * EW_THREADS + threadIdx.x;
+  if (i >= s.N)
+    return;
+  const u32 j = s.perm[i];
+  s.posB[i] = s.posA[j];
+  s.velB[i] = s.velA[j];
+  s.pred1[i] = fluidBoundary(g, s.pred0[j]);
+  fillCellTable(s.cellID, i, s.N, g.numCells, s.table);
+}
+
+// clouds.cl:72-99
+__device__ __forceinline__ float environmentTemp(const GridParams& g, float alt) { return fadd(fmul(-3.5f, fadd(alt, g.absW[1])), 293.0f); }
+__device__ __forceinline__ float externalHeatSource(const GridParams& g, float alt)
+{
+  return fclamp(expf(fdiv(-fadd(alt, g.absW[1]), 3.0f)), 0.0f, 1.0f);
+}
+__device__ __forceinline__ float saturationVaporDensity(float T)
+{
+  return (float)(217 * exp(19.5 - 4303.4 / ((double)T - 29.5)) / (double)T);
+}
+
+// cld_initTemperature clouds.cl:116-122 + cld_initVaporDensity :127-135 over M
+__global__ void __launch_bounds__(EW_THREADS) cloudsInitFieldsKernel(DeviceState s, GridParams g, float coeff)
+{
+  const u32 i = blockIdx.x * EW_THREADS + threadIdx.x;
+  if (i >= s.M)
+    return;
+  const float T = environmentTemp(g, s.posA[i].y);
+  s.tempA[i] = T;
+  s.vaporA[i] = fmul(coeff, saturationVaporDensity(T));
+}
+
+// Clouds.cpp:514-541 in one pass: 6 thermodynamics kernels + 3 buffer copies (clouds.cl:159-252), cld_predictPosition
+// (:257-273), cld_applyMixedBoundaryConditions (:279-299), fillCellIDs, resetStartEndCell.
+__global__ void __launch_bounds__(EW_THREADS) cloudsThermoPredictKernel(DeviceState s, GridParams g, rtp_cloud_params c,
+    u32* __restrict__ keys)
+{
+  const u32 i = blockIdx.x * EW_THREADS + threadIdx.x;
+  if (i < g.numCells)
+    s.table[i] = make_uint2(1u, 0u);
+  if (i >= s.N)
+    return;
+  const float4 p = s.posA[i], v = s.velA[i];
+  const float dt = c.timeStep;
+  // cld_heatFromGround
+  float temp = fminf(fadd(s.tempA[i], fmul(fmul(externalHeatSource(g, p.y), c.groundHeatCoeff), dt)), 313.0f);
+  // cld_computeBuoyancy (cloud density before the phase transition)
+  const float envTemp = environmentTemp(g, p.y);
+  const float cloudIn = s.cloudA[i], vaporIn = s.vaporA[i];
+  const float buoy = fsub(fdiv(fmul(c.buoyancyCoeff, fsub(temp, envTemp)), envTemp), fmul(fmul(c.gravCoeff, RTP_ABS_GRAVITY_ACC_Y), cloudIn));
+  // cld_applyAdiabaticCooling
+  const float tempIn = fmaxf(fsub(temp, fmul(fmul(c.adiabaticLapseRate, v.y), dt)), 223.0f);
+  // cld_generateCloud
+  const float gen = fmul(c.phaseTransitionRate, fsub(vaporIn, saturationVaporDensity(tempIn)));
+  // cld_applyPhaseTransition
+  s.cloudA[i] = fmaxf(fadd(cloudIn, fmul(gen, dt)), 0.0f);
+  s.vaporA[i] = fmaxf(fsub(vaporIn, fmul(gen, dt)), 0.0f);
+  // cld_applyLatentHeat
+  temp = fadd(tempIn, fmaxf(fmul(fmul(c.latentHeatCoeff, gen), dt), 0.0f));
+  s.tempA[i] = temp;
+  s.buoyA[i] = buoy;
+  s.cloudGen[i] = gen;
+  // cld_predictPosition
+  const float pvx = fadd(v.x, fmul(0.0f, dt)), pvy = fadd(v.y, fmul(buoy, dt)), pvz = fadd(v.z, fmul(0.0f, dt));
+  const float4 tot = make_float4(fmul(pvx, dt), fmul(pvy, dt), fmul(pvz, dt), 0.0f);
+  s.totCorrA[i] = tot;
+  float4 pr = make_float4(fadd(p.x, tot.x), fadd(p.y, tot.y), fadd(p.z, tot.z), 0.0f);
+  pr = cloudBoundary(g, pr);
+  s.pred0[i] = pr;
+  keys[i] = cell1D(g, pr.x, pr.y, pr.z);
+}
+
+__global__ void __launch_bounds__(EW_THREADS) cloudsGatherKernel(DeviceState s, GridParams g)
+{
+  const u32 i = blockIdx.x * EW_THREADS + threadIdx.x;
+  if (i >= s.N)
+    return;
+  const u32 j = s.perm[i];
+  s.posB[i] = s.posA[j];
+  s.velB[i] = s.velA[j];
+  s.pred1[i] = s.pred0[j];
+  s.totCorrB[i] = s.totCorrA[j];
+  s.tempB[i] = s.tempA[j];
+  s.buoyB[i] = s.buoyA[j];
+  s.vaporB[i] = s.vaporA[j];
+  s.cloudB[i] = s.cloudA[j];
+  s.partIdB[i] = s.partIdA[j];
+  fillCellTable(s.cellID, i, s.N, g.numCells, s.table);
+}
+
+// cld_updatePosition clouds.cl:942-953 + write the sorted state back to the canonical buffers
+__global__ void __launch_bounds__(EW_THREADS) cloudsFinishKernel(DeviceState s, GridParams g, rtp_cloud_params c,
+    const float4* __restrict__ pred, int copyVel)
+{
+  const u32 i = blockIdx.x * EW_THREADS + threadIdx.x;
+  if (i >= s.N)
+    return;
+  const float4 pp = pred[i];
+  float4 p = pp;
+  const float a = fadd(pp.y, g.absW[1]);
+  p.x = fadd(p.x, fmul(fmul(fmul(fsub(1.0f, expf(fmul(-a, 0.2f))), c.windCoeff), c.timeStep), (float)(c.dim - 2)));
+  p.z = fadd(p.z, fmul(fmul(fmul(fsub(1.0f, expf(fmul(-a, 0.3f))), 0.7f), c.windCoeff), c.timeStep));
+  s.posA[i] = p;
+  if (copyVel)
+    s.velA[i] = s.velB[i];
+  s.tempA[i] = s.tempB[i];
+  s.buoyA[i] = s.buoyB[i];
+  s.vaporA[i] = s.vaporB[i];
+  s.cloudA[i] = s.cloudB[i];
+  s.partIdA[i] = s.partIdB[i];
+  s.totCorrA[i] = s.totCorrB[i];
+}
+
+// ------------------------------------------------------------------ neighbour kernels
+
+template <int TRAV>
+__global__ void __launch_bounds__(NB_THREADS) densityLambdaKernel(DeviceState s, GridParams g, SphConsts c, float rho0, float cfm,
+    const float4* __restrict__ pred)
+{
+  const u32 i = blockIdx.x * NB_THREADS + threadIdx.x;
+  if (i >= s.N)
+    return;
+  const float4 pi = pred[i];
+  float sumT3 = 0.f, gx = 0.f, gy = 0.f, gz = 0.f, sumG2 = 0.f;
+  sweepNeighbours<TRAV>(g, c, s.table, pred, pi,
+      [&](u32, float dx, float dy, float dz, float sq)
+      {
+        const float t = c.h2 - sq;
+        sumT3 += t * t * t;
+        if (sq > c.epsSq)
+        {
+          const float G = spikyScalar(c, sq);
+          gx += dx * G;
+          gy += dy * G;
+          gz += dz * G;
+          sumG2 += G * G * sq;
+        }
+      });
+  const float k = -3.0f * c.spiky;
+  const float density = c.poly6 * sumT3;
+  gx *= k; gy *= k; gz *= k;
+  sumG2 *= k * k;
+  s.density[i] = density;
+  // fluids.cl:189-192
+  const float densityC = fsub(fdiv(density, rho0), 1.0f);
+  float ssg = fadd(sumG2, dot3c(gx, gy, gz, gx, gy, gz));
+  ssg = fdiv(ssg, fmul(rho0, rho0));
+  s.lambda[i] = fdiv(-densityC, fadd(ssg, cfm));
+}
+
+template <int TRAV, bool LAST>
+__global__ void __launch_bounds__(NB_THREADS) correctionKernel(DeviceState s, GridParams g, SphConsts c, FluidStepParams fp,
+    const float4* __restrict__ pred, float4* __restrict__ predOut, int writeCorr)
+{
+  const u32 i = blockIdx.x * NB_THREADS + threadIdx.x;
+  if (i >= s.N)
+    return;
+  const float4 pi = pred[i];
+  const float* __restrict__ lambda = s.lambda;
+  const float li = lambda[i];
+  const bool art = fp.f.isArtPressureEnabled != 0;
+  const u32 artExp = fp.f.artPressureExp;
+  const float artCoeff = fp.f.artPressureCoeff, invDen = fp.invArtDenom;
+  float cx = 0.f, cy = 0.f, cz = 0.f;
+  sweepNeighbours<TRAV>(g, c, s.table, pred, pi,
+      [&](u32 e, float dx, float dy, float dz, float sq)
+      {
+        if (sq > c.epsSq)
+        {
+          const float G = spikyScalar(c, sq);
+          float sc = li + __ldg(lambda + e);
+          if (art)
+          {
+            // artPressure fluids.cl:51-57: -k * (W(vec) / W(dq h))^n ; POLY6_COEFF cancels in the ratio
+            const float t = c.h2 - sq;
+            const float ratio = t * t * t * invDen;
+            float pw = ratio;
+            for (u32 q = 1; q < artExp; ++q)
+              pw *= ratio;
+            sc -= artCoeff * pw;
+          }
+          const float w = sc * G;
+          cx += w * dx;
+          cy += w * dy;
+          cz += w * dz;
+        }
+      });
+  const float k = -3.0f * c.spiky;
+  const float rho0 = fp.f.restDensity;
+  const float4 corr = make_float4(fdiv(cx * k, rho0), fdiv(cy * k, rho0), fdiv(cz * k, rho0), 0.0f);
+  if (writeCorr)
+    s.corrPos[i] = corr;
+  // fld_correctPosition / cld_correctPosition
+  float4 np = make_float4(fadd(pi.x, corr.x), fadd(pi.y, corr.y), fadd(pi.z, corr.z), 0.0f);
+  const float idt = fadd(fp.f.timeStep, RTP_FLOAT_EPS);
+  if (TRAV == TRAV_FLUIDS)
+  {
+    if (!LAST)
+    {
+      predOut[i] = fluidBoundary(g, np); // next iteration's fld_applyBoundaryCondition (Fluids.cpp:430)
+    }
+    else
+    {
+      predOut[i] = np;
+      // fld_updateVel fluids.cl:263-273
+      const float4 p0 = s.posB[i];
+      const float4 v = make_float4(fclamp(fdiv(fsub(np.x, p0.x), idt), -c.maxVel, c.maxVel),
+          fclamp(fdiv(fsub(np.y, p0.y), idt), -c.maxVel, c.maxVel), fclamp(fdiv(fsub(np.z, p0.z), idt), -c.maxVel, c.maxVel), 0.0f);
+      if (fp.f.isVorticityConfEnabled)
+      {
+        s.velB[i] = v;
+      }
+      else
+      {
+        s.velA[i] = v;
+        s.posA[i] = np; // fld_updatePosition fluids.cl:444-450
+      }
+    }
+  }
+  else
+  {
+    // clouds: second cld_correctPosition on p_totCorrPos, then the boundary kernel (Clouds.cpp:579-586)
+    const float4 t0 = s.totCorrB[i];
+    const float4 tot = make_float4(fadd(t0.x, corr.x), fadd(t0.y, corr.y), fadd(t0.z, corr.z), 0.0f);
+    s.totCorrB[i] = tot;
+    predOut[i] = cloudBoundary(g, np);
+    if (LAST)
+    {
+      // cld_updateVel clouds.cl:958-967
+      s.velB[i] = make_float4(fclamp(fdiv(tot.x, idt), -c.maxVel, c.maxVel), fclamp(fdiv(tot.y, idt), -c.maxVel, c.maxVel),
+          fclamp(fdiv(tot.z, idt), -c.maxVel, c.maxVel), 0.0f);
+    }
+  }
+}
+
+template <int TRAV>
+__global__ void __launch_bounds__(NB_THREADS) vorticityKernel(DeviceState s, GridParams g, SphConsts c, const float4* __restrict__ pred)
+{
+  const u32 i = blockIdx.x * NB_THREADS + threadIdx.x;
+  if (i >= s.N)
+    return;
+  const float4 pi = pred[i];
+  const float4* __restrict__ V = s.velB;
+  const float4 vi = V[i];
+  float wx = 0.f, wy = 0.f, wz = 0.f;
+  sweepNeighbours<TRAV>(g, c, s.table, pred, pi,
+      [&](u32 e, float dx, float dy, float dz, float sq)
+      {
+        if (sq > c.epsSq)
+        {
+          const float G = spikyScalar(c, sq);
+          const float4 vj = ld4(V, e);
+          const float ax = vj.x - vi.x, ay = vj.y - vi.y, az = vj.z - vi.z;
+          wx += (ay * dz - az * dy) * G;
+          wy += (az * dx - ax * dz) * G;
+          wz += (ax * dy - ay * dx) * G;
+        }
+      });
+  const float k = -3.0f * c.spiky;
+  wx *= k; wy *= k; wz *= k;
+  s.vort[i] = make_float4(wx, wy, wz, 0.0f);
+  s.vortNorm[i] = fsqrt(dot3c(wx, wy, wz, wx, wy, wz)); // fast_length(vort[e]) of the next sweep
+}
+
+template <int TRAV>
+__global__ void __launch_bounds__(NB_THREADS) confinementKernel(DeviceState s, GridParams g, SphConsts c, float coeff, float dt,
+    const float4* __restrict__ pred)
+{
+  const u32 i = blockIdx.x * NB_THREADS + threadIdx.x;
+  if (i >= s.N)
+    return;
+  const float4 pi = pred[i];
+  const float* __restrict__ wn = s.vortNorm;
+  float nx = 0.f, ny = 0.f, nz = 0.f;
+  sweepNeighbours<TRAV>(g, c, s.table, pred, pi,
+      [&](u32 e, float dx, float dy, float dz, float sq)
+      {
+        if (sq > c.epsSq)
+        {
+          const float w = __ldg(wn + e) * spikyScalar(c, sq);
+          nx += w * dx;
+          ny += w * dy;
+          nz += w * dz;
+        }
+      });
+  const float k = -3.0f * c.spiky;
+  nx *= k; ny *= k; nz *= k;
+  // normalize(n) with normalize(0) = 0, then vel += coeff * cross(n, vorticity) * dt   (fluids.cl:376)
+  const float l = fsqrt(dot3c(nx, ny, nz, nx, ny, nz));
+  if (l == 0.0f)
+  {
+    nx = ny = nz = 0.0f;
+  }
+  else
+  {
+    nx = fdiv(nx, l); ny = fdiv(ny, l); nz = fdiv(nz, l);
+  }
+  const float4 w = s.vort[i];
+  const float crx = fsub(fmul(ny, w.z), fmul(nz, w.y)), cry = fsub(fmul(nz, w.x), fmul(nx, w.z)), crz = fsub(fmul(nx, w.y), fmul(ny, w.x));
+  const float4 v = s.velB[i];
+  s.velC[i] = make_float4(fadd(v.x, fmul(fmul(crx, coeff), dt)), fadd(v.y, fmul(fmul(cry, coeff), dt)), fadd(v.z, fmul(fmul(crz, coeff), dt)), 0.0f);
+}
+
+template <int TRAV>
+__global__ void __launch_bounds__(NB_THREADS) xsphKernel(DeviceState s, GridParams g, SphConsts c, float coeff, const float4* __restrict__ pred)
+{
+  const u32 i = blockIdx.x * NB_THREADS + threadIdx.x;
+  if (i >= s.N)
+    return;
+  const float4 pi = pred[i];
+  const float4* __restrict__ V = s.velC;
+  const float4 vi = V[i];
+  float sx = 0.f, sy = 0.f, sz = 0.f;
+  sweepNeighbours<TRAV>(g, c, s.table, pred, pi,
+      [&](u32 e, float, float, float, float sq)
+      {
+        const float t = c.h2 - sq;
+        const float W = t * t * t;
+        const float4 vj = ld4(V, e);
+        sx += (vj.x - vi.x) * W;
+        sy += (vj.y - vi.y) * W;
+        sz += (vj.z - vi.z) * W;
+      });
+  sx *= c.poly6; sy *= c.poly6; sz *= c.poly6;
+  s.velA[i] = make_float4(fadd(vi.x, fmul(sx, coeff)), fadd(vi.y, fmul(sy, coeff)), fadd(vi.z, fmul(sz, coeff)), 0.0f);
+  if (TRAV == TRAV_FLUIDS)
+    s.posA[i] = pi; // fld_updatePosition fluids.cl:444-450 (clouds: cloudsFinishKernel)
+}
+
+// cld_computeLaplacianTemp clouds.cl:508-569 -- on the SORTED p_pos with the table built from p_predPos (Clouds.cpp:253)
+__global__ void __launch_bounds__(NB_THREADS) laplacianTempKernel(DeviceState s, GridParams g, SphConsts c, float rho0)
+{
+  const u32 i = blockIdx.x * NB_THREADS + threadIdx.x;
+  if (i >= s.N)
+    return;
+  const float4 pi = s.posB[i];
+  const float* __restrict__ T = s.tempB;
+  const float Ti = T[i];
+  float lap = 0.f;
+  sweepNeighbours<TRAV_CLOUDS>(g, c, s.table, s.posB, pi,
+      [&](u32 e, float, float, float, float sq)
+      {
+        if (sq > c.epsSq)
+          lap += (Ti - __ldg(T + e)) * (spikyScalar(c, sq) * sq) * rcpApprox(sq + RTP_FLOAT_EPS);
+      });
+  lap *= -3.0f * c.spiky;
+  s.lapTemp[i] = fdiv(lap, rho0);
+}
+
+// cld_computeConstraintFactorTemp clouds.cl:575-648
+__global__ void __launch_bounds__(NB_THREADS) lambdaTempKernel(DeviceState s, GridParams g, SphConsts c, float rho0, float cfm)
+{
+  const u32 i = blockIdx.x * NB_THREADS + threadIdx.x;
+  if (i >= s.N)
+    return;
+  const float4 pi = s.posB[i];
+  float sumD = 0.f, sumD2 = 0.f;
+  sweepNeighbours<TRAV_CLOUDS>(g, c, s.table, s.posB, pi,
+      [&](u32, float, float, float, float sq)
+      {
+        if (sq > c.epsSq)
+        {
+          const float d = (spikyScalar(c, sq) * sq) * rcpApprox(sq * rho0 + RTP_FLOAT_EPS);
+          sumD += d;
+          sumD2 += d * d;
+        }
+      });
+  const float k = -3.0f * c.spiky;
+  sumD *= k;
+  sumD2 *= k * k;
+  const float ssg = fadd(sumD2, fmul(sumD, sumD));
+  s.lambdaTemp[i] = fdiv(-s.lapTemp[i], fadd(ssg, cfm));
+}
+
+// cld_computeConstraintCorrectionTemp clouds.cl:654-722 + cld_correctTemperature :931-937
+__global__ void __launch_bounds__(NB_THREADS) correctTempKernel(DeviceState s, GridParams g, SphConsts c, float rho0)
+{
+  const u32 i = blockIdx.x * NB_THREADS + threadIdx.x;
+  if (i >= s.N)
+    return;
+  const float4 pi = s.posB[i];
+  const float* __restrict__ L = s.lambdaTemp;
+  const float li = L[i];
+  float corr = 0.f;
+  sweepNeighbours<TRAV_CLOUDS>(g, c, s.table, s.posB, pi,
+      [&](u32 e, float, float, float, float sq)
+      {
+        if (sq > c.epsSq)
+        {
+          const float d = (spikyScalar(c, sq) * sq) * rcpApprox(sq * rho0 + RTP_FLOAT_EPS);
+          corr += (li + __ldg(L + e)) * d;
+        }
+      });
+  corr *= -3.0f * c.spiky;
+  s.corrTemp[i] = corr;
+  s.tempB[i] = fadd(s.tempB[i], fmul(0.3f, corr));
+}
+
+// ------------------------------------------------------------------ launch wrappers
+
+static inline int ewBlocks(size_t n) { return (int)((n + EW_THREADS - 1) / EW_THREADS); }
+static inline int nbBlocks(size_t n) { return (int)((n + NB_THREADS - 1) / NB_THREADS); }
+
+void launchFluidPredict(const DeviceState& s, const GridParams& g, const FluidStepParams& p, u32* keysOut, cudaStream_t st)
+{
+  fluidPredictKernel<<<ewBlocks(max(s.N, g.numCells)), EW_THREADS, 0, st>>>(s, g, p.f.timeStep, keysOut);
+}
+void launchFluidGather(const DeviceState& s, const GridParams& g, cudaStream_t st)
+{
+  if (s.N)
+    fluidGatherKernel<<<ewBlocks(s.N), EW_THREADS, 0, st>>>(s, g);
+}
+void launchDensityLambda(const DeviceState& s, int model, const GridParams& g, const SphConsts& c, const FluidStepParams& p,
+    const float4* pred, cudaStream_t st)
+{
+  if (!s.N)
+    return;
+  if (model == RTP_MODEL_CLOUDS)
+    densityLambdaKernel<TRAV_CLOUDS><<<nbBlocks(s.N), NB_THREADS, 0, st>>>(s, g, c, p.f.restDensity, p.f.relaxCFM, pred);
+  else
+    densityLambdaKernel<TRAV_FLUIDS><<<nbBlocks(s.N), NB_THREADS, 0, st>>>(s, g, c, p.f.restDensity, p.f.relaxCFM, pred);
+}
+void launchCorrection(const DeviceState& s, int model, const GridParams& g, const SphConsts& c, const FluidStepParams& p,
+    const rtp_cloud_params&, const float4* pred, float4* predOut, bool last, bool writeCorr, cudaStream_t st)
+{
+  if (!s.N)
+    return;
+  const int nb = nbBlocks(s.N), wc = writeCorr ? 1 : 0;
+  if (model == RTP_MODEL_CLOUDS)
+  {
+    if (last)
+      correctionKernel<TRAV_CLOUDS, true><<<nb, NB_THREADS, 0, st>>>(s, g, c, p, pred, predOut, wc);
+    else
+      correctionKernel<TRAV_CLOUDS, false><<<nb, NB_THREADS, 0, st>>>(s, g, c, p, pred, predOut, wc);
+  }
+  else
+  {
+    if (last)
+      correctionKernel<TRAV_FLUIDS, true><<<nb, NB_THREADS, 0, st>>>(s, g, c, p, pred, predOut, wc);
+    else
+      correctionKernel<TRAV_FLUIDS, false><<<nb, NB_THREADS, 0, st>>>(s, g, c, p, pred, predOut, wc);
+  }
+}
+void launchVorticity(const DeviceState& s, int model, const GridParams& g, const SphConsts& c, const float4* pred, cudaStream_t st)
+{
+  if (!s.N)
+    return;
+  if (model == RTP_MODEL_CLOUDS)
+    vorticityKernel<TRAV_CLOUDS><<<nbBlocks(s.N), NB_THREADS, 0, st>>>(s, g, c, pred);
+  else
+    vorticityKernel<TRAV_FLUIDS><<<nbBlocks(s.N), NB_THREADS, 0, st>>>(s, g, c, pred);
+}
+void launchConfinement(const DeviceState& s, int model, const GridParams& g, const SphConsts& c, const FluidStepParams& p,
+    const float4* pred, cudaStream_t st)
+{
+  if (!s.N)
+    return;
+  if (model == RTP_MODEL_CLOUDS)
+    confinementKernel<TRAV_CLOUDS><<<nbBlocks(s.N), NB_THREADS, 0, st>>>(s, g, c, p.f.vorticityConfCoeff, p.f.timeStep, pred);
+  else
+    confinementKernel<TRAV_FLUIDS><<<nbBlocks(s.N), NB_THREADS, 0, st>>>(s, g, c, p.f.vorticityConfCoeff, p.f.timeStep, pred);
+}
+void launchXsph(const DeviceState& s, int model, const GridParams& g, const SphConsts& c, const FluidStepParams& p,
+    const rtp_cloud_params&, const float4* pred, cudaStream_t st)
+{
+  if (!s.N)
+    return;
+  if (model == RTP_MODEL_CLOUDS)
+    xsphKernel<TRAV_CLOUDS><<<nbBlocks(s.N), NB_THREADS, 0, st>>>(s, g, c, p.f.xsphViscosityCoeff, pred);
+  else
+    xsphKernel<TRAV_FLUIDS><<<nbBlocks(s.N), NB_THREADS, 0, st>>>(s, g, c, p.f.xsphViscosityCoeff, pred);
+}
+void launchCloudsInitFields(const DeviceState& s, const GridParams& g, const rtp_cloud_params& cloud, cudaStream_t st)
+{
+  cloudsInitFieldsKernel<<<ewBlocks(s.M), EW_THREADS, 0, st>>>(s, g, cloud.initVaporDensityCoeff);
+}
+void launchCloudsThermoPredict(const DeviceState& s, const GridParams& g, const rtp_cloud_params& cloud, u32* keysOut, cudaStream_t st)
+{
+  cloudsThermoPredictKernel<<<ewBlocks(max(s.N, g.numCells)), EW_THREADS, 0, st>>>(s, g, cloud, keysOut);
+}
+void launchCloudsGather(const DeviceState& s, const GridParams& g, cudaStream_t st)
+{
+  if (s.N)
+    cloudsGatherKernel<<<ewBlocks(s.N), EW_THREADS, 0, st>>>(s, g);
+}
+void launchCloudsLaplacianTemp(const DeviceState& s, const GridParams& g, const SphConsts& c, const rtp_cloud_params& cloud, cudaStream_t st)
+{
+  if (s.N)
+    laplacianTempKernel<<<nbBlocks(s.N), NB_THREADS, 0, st>>>(s, g, c, cloud.restDensity);
+}
+void launchCloudsLambdaTemp(const DeviceState& s, const GridParams& g, const SphConsts& c, const rtp_cloud_params& cloud, cudaStream_t st)
+{
+  if (s.N)
+    lambdaTempKernel<<<nbBlocks(s.N), NB_THREADS, 0, st>>>(s, g, c, cloud.restDensity, cloud.relaxCFM);
+}
+void launchCloudsCorrectTemp(const DeviceState& s, const GridParams& g, const SphConsts& c, const rtp_cloud_params& cloud, cudaStream_t st)
+{
+  if (s.N)
+    correctTempKernel<<<nbBlocks(s.N), NB_THREADS, 0, st>>>(s, g, c, cloud.restDensity);
+}
+void launchCloudsFinish(const DeviceState& s, const GridParams& g, const rtp_cloud_params& cloud, const float4* pred, bool copyVel, cudaStream_t st)
+{
+  if (s.N)
+    cloudsFinishKernel<<<ewBlocks(s.N), EW_THREADS, 0, st>>>(s, g, cloud, pred, copyVel ? 1 : 0);
+}
+
+} // namespace rtp

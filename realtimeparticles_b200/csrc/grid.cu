@@ -1,0 +1,174 @@
+// grid.cu -- reset / cell-table / camera / render-side kernels shared by the three models.
+#include "kernels.cuh"
+
+namespace rtp
+{
+constexpr int EW_THREADS = 256;
+static inline int ewBlocks(size_t n) { return (int)((n + EW_THREADS - 1) / EW_THREADS); }
+
+// resetCellIDs grid.cl:65-71 + resetCameraDist utils.cl:35-38 (+ identity permutations for the never-moving tail)
+__global__ void __launch_bounds__(EW_THREADS) resetIdsKernel(u32* __restrict__ cellID, u32* __restrict__ cameraDist,
+    u32* __restrict__ perm, u32* __restrict__ cameraPerm, u32 M, u32 numCells)
+{
+  const u32 i = blockIdx.x * EW_THREADS + threadIdx.x;
+  if (i >= M)
+    return;
+  cellID[i] = numCells * 2u + i;
+  cameraDist[i] = (u32)(RTP_FAR_DIST);
+  perm[i] = i;
+  cameraPerm[i] = i;
+}
+
+// adjustEndCell grid.cl:143-152
+__global__ void __launch_bounds__(EW_THREADS) adjustEndCellKernel(uint2* __restrict__ table, u32 numCells, u32 cap)
+{
+  const u32 c = blockIdx.x * EW_THREADS + threadIdx.x;
+  if (c >= numCells)
+    return;
+  const uint2 se = table[c];
+  if (se.y > se.x)
+    table[c] = make_uint2(se.x, se.x + min(se.y - se.x, cap));
+}
+
+// fillCameraDist utils.cl:43-52: key = (uint) max(FAR_DIST - length(pos - cam) * 100, 0)
+__global__ void __launch_bounds__(EW_THREADS) fillCameraDistKernel(const float4* __restrict__ pos, float cx, float cy, float cz,
+    u32* __restrict__ keys, u32 N)
+{
+  const u32 i = blockIdx.x * EW_THREADS + threadIdx.x;
+  if (i >= N)
+    return;
+  const float4 p = pos[i];
+  const float dx = fsub(p.x, cx), dy = fsub(p.y, cy), dz = fsub(p.z, cz);
+  const float len = fsqrt(dot3c(dx, dy, dz, dx, dy, dz));
+  keys[i] = (u32)(fmaxf(fsub(RTP_FAR_DIST, fmul(len, 100.0f)), 0.0f));
+}
+
+// payload gather of the camera sort: {p_pos,p_col,p_vel,p_predPos} (+ 5 float arrays for clouds)
+// Boids.cpp:381, Fluids.cpp:468, Clouds.cpp:624. Output goes to the B buffers; the caller copies back.
+__global__ void __launch_bounds__(EW_THREADS) cameraGatherKernel(DeviceState s, int model, const float4* __restrict__ pred,
+    float4* __restrict__ predOut)
+{
+  const u32 i = blockIdx.x * EW_THREADS + threadIdx.x;
+  if (i >= s.N)
+    return;
+  const u32 j = s.cameraPerm[i];
+  s.posB[i] = s.posA[j];
+  s.colB[i] = s.col[j];
+  s.velB[i] = s.velA[j];
+  if (model == RTP_MODEL_BOIDS)
+  {
+    s.velC[i] = s.acc[j]; // p_acc travels too (Boids.cpp:381); velC is free scratch here
+  }
+  else
+  {
+    predOut[i] = pred[j];
+    if (model == RTP_MODEL_CLOUDS)
+    {
+      s.tempB[i] = s.tempA[j];
+      s.buoyB[i] = s.buoyA[j];
+      s.vaporB[i] = s.vaporA[j];
+      s.cloudB[i] = s.cloudA[j];
+      s.partIdB[i] = s.partIdA[j];
+    }
+  }
+}
+
+// resetGridDetector / fillGridDetector grid.cl:43-60 (float8 per cell)
+__global__ void __launch_bounds__(EW_THREADS) resetGridDetectorKernel(float4* __restrict__ det, u32 n4)
+{
+  const u32 i = blockIdx.x * EW_THREADS + threadIdx.x;
+  if (i < n4)
+    det[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+}
+__global__ void __launch_bounds__(EW_THREADS) fillGridDetectorKernel(const float4* __restrict__ pos, GridParams g,
+    float4* __restrict__ det, u32 N)
+{
+  const u32 i = blockIdx.x * EW_THREADS + threadIdx.x;
+  if (i >= N)
+    return;
+  const float4 p = pos[i];
+  const u32 c = cell1D(g, p.x, p.y, p.z);
+  if (c < g.numCells)
+  {
+    det[2 * c] = make_float4(1.f, 1.f, 1.f, 1.f);
+    det[2 * c + 1] = make_float4(1.f, 1.f, 1.f, 1.f);
+  }
+}
+
+// fld_fillFluidColor fluids.cl:458-479
+__global__ void __launch_bounds__(EW_THREADS) fillFluidColorKernel(const float* __restrict__ density, float restDensity,
+    float4* __restrict__ col, u32 N)
+{
+  const u32 i = blockIdx.x * EW_THREADS + threadIdx.x;
+  if (i >= N)
+    return;
+  const float constraint = fsub(1.0f, fdiv(density[i], restDensity));
+  float4 color = make_float4(0.0f, 0.1f, 1.0f, 0.5f);
+  if (constraint > 0.0f)
+  {
+    // (lightBlue - blue) = (0.7, 0.6, 0, 0)
+    color.x = fadd(color.x, fdiv(fmul(fsub(0.7f, 0.0f), constraint), 0.35f));
+    color.y = fadd(color.y, fdiv(fmul(fsub(0.7f, 0.1f), constraint), 0.35f));
+    color.z = fadd(color.z, fdiv(fmul(fsub(1.0f, 1.0f), constraint), 0.35f));
+    color.w = fadd(color.w, fdiv(fmul(fsub(0.5f, 0.5f), constraint), 0.35f));
+  }
+  else if (constraint < 0.0f)
+  {
+    // (blue - darkBlue) = (0, 0.1, 0.2, 0)
+    color.x = fadd(color.x, fdiv(fmul(fsub(0.0f, 0.0f), constraint), 0.35f));
+    color.y = fadd(color.y, fdiv(fmul(fsub(0.1f, 0.0f), constraint), 0.35f));
+    color.z = fadd(color.z, fdiv(fmul(fsub(1.0f, 0.8f), constraint), 0.35f));
+    color.w = fadd(color.w, fdiv(fmul(fsub(0.5f, 0.5f), constraint), 0.35f));
+  }
+  col[i] = color;
+}
+
+// fillColorFloat utils.cl:65-78
+__global__ void __launch_bounds__(EW_THREADS) fillColorFloatKernel(const float* __restrict__ q, float minVal, float maxVal,
+    float4* __restrict__ col, u32 N)
+{
+  const u32 i = blockIdx.x * EW_THREADS + threadIdx.x;
+  if (i >= N)
+    return;
+  float val = fdiv(fsub(q[i], minVal), fsub(maxVal, minVal));
+  val = fmul(val, (val < 0.0f) ? 0.0f : 1.0f);
+  val = fmul(val, (1.0f < val) ? 0.0f : 1.0f);
+  col[i] = make_float4(val, val, val, val);
+}
+
+void launchResetIds(const DeviceState& s, u32 numCells, cudaStream_t st)
+{
+  resetIdsKernel<<<ewBlocks(s.M), EW_THREADS, 0, st>>>(s.cellID, s.cameraDist, s.perm, s.cameraPerm, s.M, numCells);
+}
+void launchAdjustEndCell(const DeviceState& s, const GridParams& g, cudaStream_t st)
+{
+  adjustEndCellKernel<<<ewBlocks(g.numCells), EW_THREADS, 0, st>>>(s.table, g.numCells, g.maxPartsInCell);
+}
+void launchFillCameraDist(const DeviceState& s, const float cam[3], u32* keysOut, cudaStream_t st)
+{
+  if (s.N)
+    fillCameraDistKernel<<<ewBlocks(s.N), EW_THREADS, 0, st>>>(s.posA, cam[0], cam[1], cam[2], keysOut, s.N);
+}
+void launchCameraGather(const DeviceState& s, int model, const float4* pred, float4* predOut, cudaStream_t st)
+{
+  if (s.N)
+    cameraGatherKernel<<<ewBlocks(s.N), EW_THREADS, 0, st>>>(s, model, pred, predOut);
+}
+void launchGridDetector(const DeviceState& s, const GridParams& g, cudaStream_t st)
+{
+  resetGridDetectorKernel<<<ewBlocks((size_t)g.numCells * 2), EW_THREADS, 0, st>>>((float4*)s.partDetector, g.numCells * 2);
+  if (s.N)
+    fillGridDetectorKernel<<<ewBlocks(s.N), EW_THREADS, 0, st>>>(s.posA, g, (float4*)s.partDetector, s.N);
+}
+void launchFillFluidColor(const DeviceState& s, float restDensity, cudaStream_t st)
+{
+  if (s.N)
+    fillFluidColorKernel<<<ewBlocks(s.N), EW_THREADS, 0, st>>>(s.density, restDensity, s.col, s.N);
+}
+void launchFillColorFloat(const DeviceState& s, const float* quantity, float minVal, float maxVal, cudaStream_t st)
+{
+  if (s.N)
+    fillColorFloatKernel<<<ewBlocks(s.N), EW_THREADS, 0, st>>>(quantity, minVal, maxVal, s.col, s.N);
+}
+
+} // namespace rtp

@@ -1,0 +1,86 @@
+// kernels.cuh -- host-side launch wrappers of the model kernels (definitions in grid.cu, boids.cu, fluids.cu).
+// Every wrapper enqueues exactly one kernel on the given stream and returns nothing; errors are collected by the
+// caller with cudaGetLastError().
+#pragma once
+
+#include "rtp_common.cuh"
+
+namespace rtp
+{
+// Buffers of one model instance. "A" buffers hold the canonical state seen by rtp_upload/rtp_download (the
+// reference's named buffers); "B" buffers are the cell-sorted working copies the neighbour kernels read. Every
+// step ends with the state back in the A buffers, so one captured CUDA graph replays for every step.
+struct DeviceState
+{
+  u32 M = 0, N = 0;
+  // float4[M]
+  float4 *posA = nullptr, *posB = nullptr, *velA = nullptr, *velB = nullptr, *velC = nullptr;
+  float4 *col = nullptr, *colB = nullptr, *acc = nullptr;
+  float4 *pred0 = nullptr, *pred1 = nullptr; // ping-pong predicted positions; predCur points at the official one
+  float4 *corrPos = nullptr, *vort = nullptr, *totCorrA = nullptr, *totCorrB = nullptr;
+  // float[M]
+  float *density = nullptr, *lambda = nullptr, *vortNorm = nullptr;
+  float *tempA = nullptr, *tempB = nullptr, *vaporA = nullptr, *vaporB = nullptr, *cloudA = nullptr, *cloudB = nullptr;
+  float *buoyA = nullptr, *buoyB = nullptr, *partIdA = nullptr, *partIdB = nullptr, *cloudGen = nullptr;
+  float *lapTemp = nullptr, *lambdaTemp = nullptr, *corrTemp = nullptr;
+  float* partDetector = nullptr; // float8[C]
+  // u32
+  u32 *cellID = nullptr, *keysTmp = nullptr, *perm = nullptr, *permTmp = nullptr;
+  u32 *cameraDist = nullptr, *cameraPerm = nullptr;
+  uint2* table = nullptr; // c_startEndPartID
+  u32 *sortCtrl = nullptr, *sortStatus = nullptr;
+};
+
+struct BoidsStepParams
+{
+  rtp_boids_params rules;
+  rtp_target_params target;
+  float targetPos[4];
+  int targetActive;
+  int boundary;
+  int dim;
+  float dt; // 0.1, Boids.cpp:334
+};
+
+struct FluidStepParams
+{
+  rtp_fluid_params f;
+  float invArtDenom; // 1 / (h^2 - (artPressureRadius*h)^2)^3  (poly6 coefficient cancels in the ratio)
+};
+
+// ---- grid.cu
+void launchResetIds(const DeviceState& s, u32 numCells, cudaStream_t st);
+void launchAdjustEndCell(const DeviceState& s, const GridParams& g, cudaStream_t st);
+void launchFillCameraDist(const DeviceState& s, const float cam[3], u32* keysOut, cudaStream_t st);
+void launchCameraGather(const DeviceState& s, int model, const float4* pred, float4* predOut, cudaStream_t st);
+void launchGridDetector(const DeviceState& s, const GridParams& g, cudaStream_t st); // reset + fill (2 launches)
+void launchFillFluidColor(const DeviceState& s, float restDensity, cudaStream_t st);
+void launchFillColorFloat(const DeviceState& s, const float* quantity, float minVal, float maxVal, cudaStream_t st);
+
+// ---- boids.cu
+void launchBoidsCellIds(const DeviceState& s, const GridParams& g, u32* keysOut, cudaStream_t st);
+void launchBoidsGather(const DeviceState& s, const GridParams& g, cudaStream_t st);
+void launchBoidsRules(const DeviceState& s, const GridParams& g, const SphConsts& c, const BoidsStepParams& p, cudaStream_t st);
+
+// ---- fluids.cu (fluids + clouds)
+void launchFluidPredict(const DeviceState& s, const GridParams& g, const FluidStepParams& p, u32* keysOut, cudaStream_t st);
+void launchFluidGather(const DeviceState& s, const GridParams& g, cudaStream_t st);
+void launchDensityLambda(const DeviceState& s, int model, const GridParams& g, const SphConsts& c, const FluidStepParams& p,
+    const float4* pred, cudaStream_t st);
+// last: also integrates velocity (updateVel) and, without vorticity, copies the position (updatePosition)
+void launchCorrection(const DeviceState& s, int model, const GridParams& g, const SphConsts& c, const FluidStepParams& p,
+    const rtp_cloud_params& cloud, const float4* pred, float4* predOut, bool last, bool writeCorr, cudaStream_t st);
+void launchVorticity(const DeviceState& s, int model, const GridParams& g, const SphConsts& c, const float4* pred, cudaStream_t st);
+void launchConfinement(const DeviceState& s, int model, const GridParams& g, const SphConsts& c, const FluidStepParams& p,
+    const float4* pred, cudaStream_t st);
+void launchXsph(const DeviceState& s, int model, const GridParams& g, const SphConsts& c, const FluidStepParams& p,
+    const rtp_cloud_params& cloud, const float4* pred, cudaStream_t st);
+void launchCloudsInitFields(const DeviceState& s, const GridParams& g, const rtp_cloud_params& cloud, cudaStream_t st);
+void launchCloudsThermoPredict(const DeviceState& s, const GridParams& g, const rtp_cloud_params& cloud, u32* keysOut, cudaStream_t st);
+void launchCloudsGather(const DeviceState& s, const GridParams& g, cudaStream_t st);
+void launchCloudsLaplacianTemp(const DeviceState& s, const GridParams& g, const SphConsts& c, const rtp_cloud_params& cloud, cudaStream_t st);
+void launchCloudsLambdaTemp(const DeviceState& s, const GridParams& g, const SphConsts& c, const rtp_cloud_params& cloud, cudaStream_t st);
+void launchCloudsCorrectTemp(const DeviceState& s, const GridParams& g, const SphConsts& c, const rtp_cloud_params& cloud, cudaStream_t st);
+void launchCloudsFinish(const DeviceState& s, const GridParams& g, const rtp_cloud_params& cloud, const float4* pred, bool smoothing, cudaStream_t st);
+
+} // namespace rtp

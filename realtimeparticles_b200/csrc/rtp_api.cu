@@ -1,0 +1,934 @@
+// rtp_api.cu -- the C ABI (include/rtp_cuda.h): handle, named buffers, parameter blocks, step orchestration.
+// Replaces CL::Context (physics/ocl/Context.cpp), RadixSort (physics/utils/RadixSort.cpp) and the bodies of
+// Boids/Fluids/Clouds::update() (physics/ocl/{Boids,Fluids,Clouds}.cpp). No CPU fallback anywhere.
+#include "kernels.cuh"
+#include "sort.cuh"
+
+#include <math.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include <string>
+#include <vector>
+
+using namespace rtp;
+
+static thread_local std::string g_createError;
+
+struct StageMark
+{
+  const char* name;
+  cudaEvent_t ev;
+};
+
+struct rtp_handle
+{
+  rtp_config cfg;
+  cudaStream_t stream = nullptr;
+  DeviceState s;
+  GridParams g;
+  SphConsts c;
+  BoidsStepParams bp;
+  FluidStepParams fp;
+  rtp_cloud_params cp;
+  int jacobi = 2;
+  int dispField = RTP_F_CLOUD_DENS;
+  float dispMin = 1.0f, dispMax = 15.0f;
+  SortPlan cellPlan, camPlan;
+  float4* predFinal = nullptr;
+  std::vector<void*> allocs;
+  std::string err;
+  // graph cache for rtp_step_n
+  cudaGraphExec_t graphExec = nullptr;
+  unsigned graphFlags = 0;
+  float graphCam[3] = { 0, 0, 0 };
+  bool graphValid = false;
+  int lastLaunches = 0;
+  // profiling
+  bool profiling = false;
+  std::vector<StageMark> marks;
+  std::vector<std::string> stageNames;
+  std::vector<float> stageMs;
+};
+
+#define CUDA_TRY(h, expr)                                                                      \
+  do                                                                                           \
+  {                                                                                            \
+    cudaError_t e_ = (expr);                                                                   \
+    if (e_ != cudaSuccess)                                                                     \
+    {                                                                                          \
+      (h)->err = std::string(#expr) + ": " + cudaGetErrorString(e_);                           \
+      return RTP_ERR_CUDA;                                                                     \
+    }                                                                                          \
+  } while (0)
+
+static int fail(rtp_handle* h, int code, const char* msg)
+{
+  if (h)
+    h->err = msg;
+  return code;
+}
+
+// utils/Utils.cpp:24-29 FloatToStr(val, 10) + the OpenCL compiler parsing the -D literal
+extern "C" float rtp_baked_constant(float v)
+{
+  char buf[128];
+  snprintf(buf, sizeof buf, "%.10f", (double)v);
+  return strtof(buf, nullptr);
+}
+
+static void computeConstants(rtp_handle* h)
+{
+  const rtp_config& cfg = h->cfg;
+  GridParams& g = h->g;
+  SphConsts& c = h->c;
+  for (int k = 0; k < 3; ++k)
+  {
+    g.absW[k] = rtp_baked_constant((float)cfg.box[k] / 2.0f);
+    g.res[k] = (int)cfg.grid[k];
+  }
+  g.cellSize = rtp_baked_constant((float)cfg.box[0] / (float)cfg.grid[0]);
+  g.numCells = cfg.grid[0] * cfg.grid[1] * cfg.grid[2];
+  g.maxPartsInCell = cfg.max_parts_in_cell ? cfg.max_parts_in_cell : (cfg.model == RTP_MODEL_BOIDS ? 3000u : 100u);
+
+  // Fluids.cpp:104-119
+  const float effectRadius = (float)cfg.box[0] / (float)cfg.grid[0];
+  const float PI_F = 3.1415927f;
+  c.h = rtp_baked_constant(effectRadius);
+  c.h2 = c.h * c.h;
+  c.poly6 = rtp_baked_constant(315.0f / (64.0f * PI_F * powf(effectRadius, 9.f)));
+  c.spiky = rtp_baked_constant(15.0f / (PI_F * powf(effectRadius, 6.f)));
+  c.maxVel = rtp_baked_constant(30.0f);
+  c.effectRadiusSq = rtp_baked_constant(1.0f * (float)cfg.box[0] * (float)cfg.box[0] / (float)((size_t)cfg.grid[0] * cfg.grid[0]));
+  // (sqrtf(sq) < h) <=> (sq < supportSq): sqrtf is correctly rounded and monotonic
+  float x = c.h * c.h;
+  while (sqrtf(x) >= c.h)
+    x = nextafterf(x, 0.0f);
+  while (sqrtf(x) < c.h)
+    x = nextafterf(x, INFINITY);
+  c.supportSq = x;
+  // (sqrtf(sq) <= FLOAT_EPS) <=> (sq <= epsSq)
+  x = RTP_FLOAT_EPS * RTP_FLOAT_EPS;
+  while (sqrtf(x) > RTP_FLOAT_EPS)
+    x = nextafterf(x, 0.0f);
+  while (sqrtf(nextafterf(x, INFINITY)) <= RTP_FLOAT_EPS)
+    x = nextafterf(x, INFINITY);
+  c.epsSq = x;
+}
+
+static void updateDerivedFluidParams(rtp_handle* h)
+{
+  // poly6L(artPressureRadius * EFFECT_RADIUS) without its coefficient (fluids.cl:56)
+  const float len = h->fp.f.artPressureRadius * h->c.h;
+  const float t = h->c.h * h->c.h - len * len;
+  const float den = (len < h->c.h) ? t * t * t : 0.0f;
+  h->fp.invArtDenom = 1.0f / den;
+}
+
+template <typename T>
+static cudaError_t devAlloc(rtp_handle* h, T** p, size_t count)
+{
+  void* q = nullptr;
+  const size_t bytes = (count ? count : 1) * sizeof(T);
+  cudaError_t e = cudaMalloc(&q, bytes);
+  if (e != cudaSuccess)
+    return e;
+  e = cudaMemsetAsync(q, 0, bytes, h->stream);
+  h->allocs.push_back(q);
+  *p = (T*)q;
+  return e;
+}
+
+static int cellKeyBits(const rtp_config& cfg)
+{
+  // largest key of an active particle: index RES is reachable on every axis (position exactly on the +wall)
+  const uint64_t rx = cfg.grid[0], ry = cfg.grid[1], rz = cfg.grid[2];
+  uint64_t maxKey = rx * ry * rz + ry * rz + rz;
+  int bits = 0;
+  while (maxKey)
+  {
+    ++bits;
+    maxKey >>= 1;
+  }
+  return bits < 1 ? 1 : bits;
+}
+
+static void invalidateGraph(rtp_handle* h)
+{
+  h->graphValid = false;
+}
+
+static void makePlans(rtp_handle* h)
+{
+  h->cellPlan = makeSortPlan(h->s.N, cellKeyBits(h->cfg));
+  h->camPlan = makeSortPlan(h->s.N, 20); // keys <= FAR_DIST = 1e6 < 2^20
+}
+
+extern "C" int rtp_abi_version(void) { return RTP_ABI_VERSION; }
+
+extern "C" int rtp_device_count(void)
+{
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess)
+    return 0;
+  return n;
+}
+
+extern "C" const char* rtp_last_error(const rtp_handle* h) { return h ? h->err.c_str() : g_createError.c_str(); }
+
+extern "C" void rtp_destroy(rtp_handle* h)
+{
+  if (!h)
+    return;
+  cudaSetDevice(h->cfg.device);
+  if (h->stream)
+    cudaStreamSynchronize(h->stream);
+  if (h->graphExec)
+    cudaGraphExecDestroy(h->graphExec);
+  for (auto& m : h->marks)
+    cudaEventDestroy(m.ev);
+  for (void* p : h->allocs)
+    cudaFree(p);
+  if (h->stream)
+    cudaStreamDestroy(h->stream);
+  delete h;
+}
+
+extern "C" int rtp_create(const rtp_config* cfg, rtp_handle** out)
+{
+  if (!cfg || !out)
+  {
+    g_createError = "rtp_create: null argument";
+    return RTP_ERR_INVALID;
+  }
+  *out = nullptr;
+  if (cfg->model < RTP_MODEL_BOIDS || cfg->model > RTP_MODEL_CLOUDS || cfg->max_particles == 0
+      || cfg->nb_particles > cfg->max_particles || cfg->max_particles >= (1ull << 30))
+  {
+    g_createError = "rtp_create: invalid model or particle counts";
+    return RTP_ERR_INVALID;
+  }
+  for (int k = 0; k < 3; ++k)
+    if (cfg->box[k] == 0 || cfg->grid[k] == 0)
+    {
+      g_createError = "rtp_create: box and grid must be non-zero";
+      return RTP_ERR_INVALID;
+    }
+  if ((uint64_t)cfg->grid[0] * cfg->grid[1] * cfg->grid[2] >= (1ull << 30))
+  {
+    g_createError = "rtp_create: grid too large";
+    return RTP_ERR_INVALID;
+  }
+  int ndev = 0;
+  cudaError_t e = cudaGetDeviceCount(&ndev);
+  if (e != cudaSuccess || ndev == 0 || cfg->device < 0 || cfg->device >= ndev)
+  {
+    g_createError = std::string("rtp_create: no usable CUDA device (") + (e != cudaSuccess ? cudaGetErrorString(e) : "bad ordinal")
+        + "); this backend has no CPU fallback";
+    return RTP_ERR_CUDA;
+  }
+  rtp_handle* h = new rtp_handle();
+  h->cfg = *cfg;
+  h->cfg.dim = cfg->dim == 2 ? 2 : 3;
+#define CREATE_TRY(expr)                                                                 \
+  do                                                                                     \
+  {                                                                                      \
+    cudaError_t e2_ = (expr);                                                            \
+    if (e2_ != cudaSuccess)                                                              \
+    {                                                                                    \
+      g_createError = std::string(#expr) + ": " + cudaGetErrorString(e2_);               \
+      rtp_destroy(h);                                                                    \
+      return RTP_ERR_CUDA;                                                               \
+    }                                                                                    \
+  } while (0)
+  CREATE_TRY(cudaSetDevice(cfg->device));
+  CREATE_TRY(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
+  computeConstants(h);
+
+  // defaults: Boids.hpp:14-26, Fluids.hpp:17-32, Clouds.hpp:15-45 (+ Clouds.cpp:308-311)
+  h->bp.rules = rtp_boids_params { 0.5f, 1.6f, 1.6f, 1.45f };
+  h->bp.target = rtp_target_params { 2.0f, 1 };
+  h->bp.targetPos[0] = h->bp.targetPos[1] = h->bp.targetPos[2] = h->bp.targetPos[3] = 0.0f;
+  h->bp.targetActive = 0;
+  h->bp.boundary = RTP_BOUNDARY_BOUNCING_WALL;
+  h->bp.dim = (int)h->cfg.dim;
+  h->bp.dt = 0.1f;
+  h->fp.f = rtp_fluid_params { 450.0f, 600.0f, 0.010f, h->cfg.dim, 1, 0.006f, 0.001f, 4, 1, 0.0004f, 0.0001f };
+  updateDerivedFluidParams(h);
+  h->cp = rtp_cloud_params { h->cfg.dim, 0.01f, 450.0f, 10.0f, 0.10f, 0.0005f, 5.0f, 0.3485f, 0.07f, 1, 600.0f, 0.75f, 1.0f };
+
+  DeviceState& s = h->s;
+  const size_t M = cfg->max_particles;
+  const size_t C = h->g.numCells;
+  s.M = (u32)M;
+  s.N = (u32)cfg->nb_particles;
+  const int model = cfg->model;
+  const bool fluidLike = model != RTP_MODEL_BOIDS;
+  CREATE_TRY(devAlloc(h, &s.posA, M));
+  CREATE_TRY(devAlloc(h, &s.posB, M));
+  CREATE_TRY(devAlloc(h, &s.velA, M));
+  CREATE_TRY(devAlloc(h, &s.velB, M));
+  CREATE_TRY(devAlloc(h, &s.velC, M));
+  CREATE_TRY(devAlloc(h, &s.col, M));
+  CREATE_TRY(devAlloc(h, &s.colB, M));
+  if (!fluidLike)
+    CREATE_TRY(devAlloc(h, &s.acc, M));
+  if (fluidLike)
+  {
+    CREATE_TRY(devAlloc(h, &s.pred0, M));
+    CREATE_TRY(devAlloc(h, &s.pred1, M));
+    CREATE_TRY(devAlloc(h, &s.corrPos, M));
+    CREATE_TRY(devAlloc(h, &s.vort, M));
+    CREATE_TRY(devAlloc(h, &s.density, M));
+    CREATE_TRY(devAlloc(h, &s.lambda, M));
+    CREATE_TRY(devAlloc(h, &s.vortNorm, M));
+    h->predFinal = s.pred0;
+  }
+  if (model == RTP_MODEL_CLOUDS)
+  {
+    CREATE_TRY(devAlloc(h, &s.totCorrA, M));
+    CREATE_TRY(devAlloc(h, &s.totCorrB, M));
+    float** fl[] = { &s.tempA, &s.tempB, &s.vaporA, &s.vaporB, &s.cloudA, &s.cloudB, &s.buoyA, &s.buoyB, &s.partIdA, &s.partIdB,
+      &s.cloudGen, &s.lapTemp, &s.lambdaTemp, &s.corrTemp };
+    for (float** p : fl)
+      CREATE_TRY(devAlloc(h, p, M));
+  }
+  CREATE_TRY(devAlloc(h, &s.partDetector, C * 8));
+  CREATE_TRY(devAlloc(h, &s.cellID, M));
+  CREATE_TRY(devAlloc(h, &s.keysTmp, M));
+  CREATE_TRY(devAlloc(h, &s.perm, M));
+  CREATE_TRY(devAlloc(h, &s.permTmp, M));
+  CREATE_TRY(devAlloc(h, &s.cameraDist, M));
+  CREATE_TRY(devAlloc(h, &s.cameraPerm, M));
+  CREATE_TRY(devAlloc(h, &s.table, C));
+  CREATE_TRY(devAlloc(h, &s.sortCtrl, SORT_CTRL_WORDS));
+  // status words sized for the worst plan over any N <= M
+  {
+    const SortPlan worstA = makeSortPlan((u32)M, 32);
+    size_t words = (size_t)SORT_MAX_PASSES * ((M + SORT_THREADS * 4 - 1) / (SORT_THREADS * 4)) * SORT_RADIX;
+    (void)worstA;
+    CREATE_TRY(devAlloc(h, &s.sortStatus, words));
+  }
+  makePlans(h);
+  launchResetIds(s, h->g.numCells, h->stream);
+  CREATE_TRY(cudaGetLastError());
+  CREATE_TRY(cudaStreamSynchronize(h->stream));
+#undef CREATE_TRY
+  *out = h;
+  return RTP_OK;
+}
+
+// ------------------------------------------------------------------ buffers
+
+static int fieldInfo(rtp_handle* h, int field, void** ptr, size_t* bytes)
+{
+  DeviceState& s = h->s;
+  const size_t M = s.M, C = h->g.numCells;
+  void* p = nullptr;
+  size_t b = 0;
+  switch (field)
+  {
+  case RTP_F_POS: p = s.posA; b = 16 * M; break;
+  case RTP_F_COL: p = s.col; b = 16 * M; break;
+  case RTP_F_VEL: p = s.velA; b = 16 * M; break;
+  case RTP_F_ACC: p = s.acc; b = 16 * M; break;
+  case RTP_F_PRED_POS: p = h->predFinal; b = 16 * M; break;
+  case RTP_F_CORR_POS: p = s.corrPos; b = 16 * M; break;
+  case RTP_F_VORT: p = s.vort; b = 16 * M; break;
+  case RTP_F_TOT_CORR_POS: p = s.totCorrA; b = 16 * M; break;
+  case RTP_F_DENSITY: p = s.density; b = 4 * M; break;
+  case RTP_F_CONST_FACTOR: p = s.lambda; b = 4 * M; break;
+  case RTP_F_TEMP: p = s.tempA; b = 4 * M; break;
+  case RTP_F_VAPOR_DENS: p = s.vaporA; b = 4 * M; break;
+  case RTP_F_CLOUD_DENS: p = s.cloudA; b = 4 * M; break;
+  case RTP_F_BUOYANCY: p = s.buoyA; b = 4 * M; break;
+  case RTP_F_CLOUD_GEN: p = s.cloudGen; b = 4 * M; break;
+  case RTP_F_PART_ID: p = s.partIdA; b = 4 * M; break;
+  case RTP_F_LAPLACIAN_TEMP: p = s.lapTemp; b = 4 * M; break;
+  case RTP_F_CONST_FACTOR_TEMP: p = s.lambdaTemp; b = 4 * M; break;
+  case RTP_F_CORR_TEMP: p = s.corrTemp; b = 4 * M; break;
+  case RTP_F_CELL_ID: p = s.cellID; b = 4 * M; break;
+  case RTP_F_CAMERA_DIST: p = s.cameraDist; b = 4 * M; break;
+  case RTP_F_START_END_CELL: p = s.table; b = 8 * C; break;
+  case RTP_F_PERM: p = s.perm; b = 4 * M; break;
+  case RTP_F_CAMERA_PERM: p = s.cameraPerm; b = 4 * M; break;
+  case RTP_F_PART_DETECTOR: p = s.partDetector; b = 32 * C; break;
+  default: return fail(h, RTP_ERR_INVALID, "unknown field id");
+  }
+  if (!p)
+    return fail(h, RTP_ERR_STATE, "field does not exist for this model");
+  *ptr = p;
+  *bytes = b;
+  return RTP_OK;
+}
+
+extern "C" int rtp_field_bytes(const rtp_handle* h, int field, size_t* bytes)
+{
+  if (!h || !bytes)
+    return RTP_ERR_INVALID;
+  void* p;
+  return fieldInfo(const_cast<rtp_handle*>(h), field, &p, bytes);
+}
+
+extern "C" int rtp_upload(rtp_handle* h, int field, const void* host, size_t bytes)
+{
+  if (!h || !host)
+    return RTP_ERR_INVALID;
+  void* p;
+  size_t b;
+  const int rc = fieldInfo(h, field, &p, &b);
+  if (rc != RTP_OK)
+    return rc;
+  if (bytes != b)
+    return fail(h, RTP_ERR_INVALID, "rtp_upload: size mismatch");
+  CUDA_TRY(h, cudaSetDevice(h->cfg.device));
+  CUDA_TRY(h, cudaMemcpyAsync(p, host, bytes, cudaMemcpyHostToDevice, h->stream));
+  CUDA_TRY(h, cudaStreamSynchronize(h->stream)); // blocking, like the reference's CL_TRUE writes (Context.cpp:368)
+  return RTP_OK;
+}
+
+extern "C" int rtp_download(rtp_handle* h, int field, void* host, size_t bytes)
+{
+  if (!h || !host)
+    return RTP_ERR_INVALID;
+  void* p;
+  size_t b;
+  const int rc = fieldInfo(h, field, &p, &b);
+  if (rc != RTP_OK)
+    return rc;
+  if (bytes != b)
+    return fail(h, RTP_ERR_INVALID, "rtp_download: size mismatch");
+  CUDA_TRY(h, cudaSetDevice(h->cfg.device));
+  CUDA_TRY(h, cudaMemcpyAsync(host, p, bytes, cudaMemcpyDeviceToHost, h->stream));
+  CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+  return RTP_OK;
+}
+
+extern "C" int rtp_device_ptr(rtp_handle* h, int field, void** dptr)
+{
+  if (!h || !dptr)
+    return RTP_ERR_INVALID;
+  size_t b;
+  return fieldInfo(h, field, dptr, &b);
+}
+
+// ------------------------------------------------------------------ parameters
+
+extern "C" int rtp_set_boids_params(rtp_handle* h, const rtp_boids_params* rules, const rtp_target_params* target,
+    const float target_pos[4], int target_active)
+{
+  if (!h)
+    return RTP_ERR_INVALID;
+  if (h->cfg.model != RTP_MODEL_BOIDS)
+    return fail(h, RTP_ERR_STATE, "not a boids model");
+  if (rules)
+    h->bp.rules = *rules;
+  if (target)
+    h->bp.target = *target;
+  if (target_pos)
+    memcpy(h->bp.targetPos, target_pos, sizeof h->bp.targetPos);
+  h->bp.targetActive = target_active ? 1 : 0;
+  invalidateGraph(h);
+  return RTP_OK;
+}
+
+extern "C" int rtp_set_fluid_params(rtp_handle* h, const rtp_fluid_params* fluid, int nb_jacobi_iters)
+{
+  if (!h)
+    return RTP_ERR_INVALID;
+  if (h->cfg.model == RTP_MODEL_BOIDS)
+    return fail(h, RTP_ERR_STATE, "not a fluids/clouds model");
+  if (fluid)
+    h->fp.f = *fluid;
+  if (nb_jacobi_iters > 0)
+    h->jacobi = nb_jacobi_iters;
+  updateDerivedFluidParams(h);
+  invalidateGraph(h);
+  return RTP_OK;
+}
+
+extern "C" int rtp_set_cloud_params(rtp_handle* h, const rtp_cloud_params* cloud)
+{
+  if (!h)
+    return RTP_ERR_INVALID;
+  if (h->cfg.model != RTP_MODEL_CLOUDS)
+    return fail(h, RTP_ERR_STATE, "not a clouds model");
+  if (cloud)
+    h->cp = *cloud;
+  invalidateGraph(h);
+  return RTP_OK;
+}
+
+extern "C" int rtp_set_boundary(rtp_handle* h, int boundary)
+{
+  if (!h)
+    return RTP_ERR_INVALID;
+  if (boundary != RTP_BOUNDARY_BOUNCING_WALL && boundary != RTP_BOUNDARY_CYCLIC_WALL)
+    return fail(h, RTP_ERR_INVALID, "unknown boundary");
+  h->bp.boundary = boundary;
+  invalidateGraph(h);
+  return RTP_OK;
+}
+
+extern "C" int rtp_set_nb_particles(rtp_handle* h, uint64_t n)
+{
+  if (!h)
+    return RTP_ERR_INVALID;
+  if (n > h->s.M)
+    return fail(h, RTP_ERR_INVALID, "nb_particles > max_particles");
+  h->s.N = (u32)n;
+  h->cfg.nb_particles = n;
+  makePlans(h);
+  invalidateGraph(h);
+  return RTP_OK;
+}
+
+extern "C" int rtp_set_dimension(rtp_handle* h, int dim)
+{
+  if (!h)
+    return RTP_ERR_INVALID;
+  h->cfg.dim = dim == 2 ? 2 : 3;
+  h->bp.dim = (int)h->cfg.dim;
+  h->fp.f.dim = h->cfg.dim;
+  h->cp.dim = h->cfg.dim;
+  invalidateGraph(h);
+  return RTP_OK;
+}
+
+extern "C" int rtp_set_displayed_quantity(rtp_handle* h, int field, float min_val, float max_val)
+{
+  if (!h)
+    return RTP_ERR_INVALID;
+  void* p;
+  size_t b;
+  const int rc = fieldInfo(h, field, &p, &b);
+  if (rc != RTP_OK)
+    return rc;
+  if (b != 4 * (size_t)h->s.M)
+    return fail(h, RTP_ERR_INVALID, "displayed quantity must be a float[M] field");
+  h->dispField = field;
+  h->dispMin = min_val;
+  h->dispMax = max_val;
+  invalidateGraph(h);
+  return RTP_OK;
+}
+
+extern "C" int rtp_reset_ids(rtp_handle* h)
+{
+  if (!h)
+    return RTP_ERR_INVALID;
+  CUDA_TRY(h, cudaSetDevice(h->cfg.device));
+  launchResetIds(h->s, h->g.numCells, h->stream);
+  CUDA_TRY(h, cudaGetLastError());
+  return RTP_OK;
+}
+
+extern "C" int rtp_init_clouds_fields(rtp_handle* h)
+{
+  if (!h)
+    return RTP_ERR_INVALID;
+  if (h->cfg.model != RTP_MODEL_CLOUDS)
+    return fail(h, RTP_ERR_STATE, "not a clouds model");
+  CUDA_TRY(h, cudaSetDevice(h->cfg.device));
+  launchCloudsInitFields(h->s, h->g, h->cp, h->stream);
+  CUDA_TRY(h, cudaGetLastError());
+  return RTP_OK;
+}
+
+// ------------------------------------------------------------------ the step
+
+struct StepRecorder
+{
+  rtp_handle* h;
+  bool on;
+  size_t used = 0;
+  void mark(const char* name)
+  {
+    if (!on)
+      return;
+    if (used == h->marks.size())
+    {
+      StageMark m { name, nullptr };
+      cudaEventCreate(&m.ev);
+      h->marks.push_back(m);
+    }
+    h->marks[used].name = name;
+    cudaEventRecord(h->marks[used].ev, h->stream);
+    ++used;
+  }
+};
+
+static int enqueueCameraSort(rtp_handle* h, const float cam[3])
+{
+  DeviceState& s = h->s;
+  cudaStream_t st = h->stream;
+  const int model = h->cfg.model;
+  int launches = 0;
+  if (!s.N)
+    return 0;
+  u32* keysIn = (h->camPlan.passes % 2 == 0) ? s.cameraDist : s.keysTmp;
+  launchFillCameraDist(s, cam, keysIn, st);
+  ++launches;
+  launches += enqueueSort(h->camPlan, s.cameraDist, s.cameraPerm, s.keysTmp, s.permTmp, s.sortCtrl, s.sortStatus, st);
+  float4* predScratch = (h->predFinal == s.pred0) ? s.pred1 : s.pred0;
+  launchCameraGather(s, model, h->predFinal, predScratch, st);
+  ++launches;
+  const size_t n4 = (size_t)s.N * sizeof(float4), n1 = (size_t)s.N * sizeof(float);
+  cudaMemcpyAsync(s.posA, s.posB, n4, cudaMemcpyDeviceToDevice, st);
+  cudaMemcpyAsync(s.col, s.colB, n4, cudaMemcpyDeviceToDevice, st);
+  cudaMemcpyAsync(s.velA, s.velB, n4, cudaMemcpyDeviceToDevice, st);
+  launches += 3;
+  if (model == RTP_MODEL_BOIDS)
+  {
+    cudaMemcpyAsync(s.acc, s.velC, n4, cudaMemcpyDeviceToDevice, st);
+    ++launches;
+  }
+  else
+  {
+    cudaMemcpyAsync(h->predFinal, predScratch, n4, cudaMemcpyDeviceToDevice, st);
+    ++launches;
+    if (model == RTP_MODEL_CLOUDS)
+    {
+      cudaMemcpyAsync(s.tempA, s.tempB, n1, cudaMemcpyDeviceToDevice, st);
+      cudaMemcpyAsync(s.buoyA, s.buoyB, n1, cudaMemcpyDeviceToDevice, st);
+      cudaMemcpyAsync(s.vaporA, s.vaporB, n1, cudaMemcpyDeviceToDevice, st);
+      cudaMemcpyAsync(s.cloudA, s.cloudB, n1, cudaMemcpyDeviceToDevice, st);
+      cudaMemcpyAsync(s.partIdA, s.partIdB, n1, cudaMemcpyDeviceToDevice, st);
+      launches += 5;
+    }
+  }
+  return launches;
+}
+
+// Enqueue one update() on the handle's stream; returns the number of launches (kernels + memset/memcpy nodes).
+static int enqueueStep(rtp_handle* h, unsigned flags, const float cam[3], bool profile)
+{
+  DeviceState& s = h->s;
+  const GridParams& g = h->g;
+  const SphConsts& c = h->c;
+  cudaStream_t st = h->stream;
+  const int model = h->cfg.model;
+  const bool debug = (flags & RTP_STEP_DEBUG_FIELDS) != 0;
+  int launches = 0;
+  StepRecorder rec { h, profile };
+  rec.mark("begin");
+
+  if ((flags & RTP_STEP_PHYSICS) && s.N)
+  {
+    u32* keysIn = (h->cellPlan.passes % 2 == 0) ? s.cellID : s.keysTmp;
+    if (model == RTP_MODEL_BOIDS)
+    {
+      launchBoidsCellIds(s, g, keysIn, st);
+      ++launches;
+      rec.mark("fillCellIDs+resetStartEndCell");
+      launches += enqueueSort(h->cellPlan, s.cellID, s.perm, s.keysTmp, s.permTmp, s.sortCtrl, s.sortStatus, st);
+      rec.mark("radixSort(onesweep)");
+      launchBoidsGather(s, g, st);
+      launchAdjustEndCell(s, g, st);
+      launches += 2;
+      rec.mark("permutate+cellTable");
+      launchBoidsRules(s, g, c, h->bp, st);
+      ++launches;
+      rec.mark("boidsRules+updateVel+updatePos");
+    }
+    else
+    {
+      const bool clouds = model == RTP_MODEL_CLOUDS;
+      if (clouds)
+        launchCloudsThermoPredict(s, g, h->cp, keysIn, st);
+      else
+        launchFluidPredict(s, g, h->fp, keysIn, st);
+      ++launches;
+      rec.mark(clouds ? "thermo+predict+boundary+fillCellIDs" : "predictPosition+fillCellIDs");
+      launches += enqueueSort(h->cellPlan, s.cellID, s.perm, s.keysTmp, s.permTmp, s.sortCtrl, s.sortStatus, st);
+      rec.mark("radixSort(onesweep)");
+      if (clouds)
+        launchCloudsGather(s, g, st);
+      else
+        launchFluidGather(s, g, st);
+      launchAdjustEndCell(s, g, st);
+      launches += 2;
+      rec.mark("permutate+cellTable");
+      if (clouds && h->cp.isTempSmoothingEnabled)
+      {
+        launchCloudsLaplacianTemp(s, g, c, h->cp, st);
+        launchCloudsLambdaTemp(s, g, c, h->cp, st);
+        launchCloudsCorrectTemp(s, g, c, h->cp, st);
+        launches += 3;
+        rec.mark("temperatureConstraint(3 sweeps)");
+      }
+      float4* cur = s.pred1;
+      float4* nxt = s.pred0;
+      for (int it = 0; it < h->jacobi; ++it)
+      {
+        const bool last = it == h->jacobi - 1;
+        launchDensityLambda(s, model, g, c, h->fp, cur, st);
+        launchCorrection(s, model, g, c, h->fp, h->cp, cur, nxt, last, debug, st);
+        launches += 2;
+        float4* t = cur;
+        cur = nxt;
+        nxt = t;
+      }
+      rec.mark("jacobi(density+lambda, correction)");
+      h->predFinal = cur;
+      if (h->fp.f.isVorticityConfEnabled)
+      {
+        launchVorticity(s, model, g, c, cur, st);
+        launchConfinement(s, model, g, c, h->fp, cur, st);
+        launchXsph(s, model, g, c, h->fp, h->cp, cur, st);
+        launches += 3;
+        rec.mark("vorticity+confinement+xsph");
+      }
+      if (clouds)
+      {
+        launchCloudsFinish(s, g, h->cp, cur, !h->fp.f.isVorticityConfEnabled, st);
+        ++launches;
+        rec.mark("updatePosition");
+      }
+    }
+    if (flags & RTP_STEP_RENDER_AUX)
+    {
+      launchGridDetector(s, g, st);
+      launches += 2;
+      if (model == RTP_MODEL_FLUIDS)
+      {
+        launchFillFluidColor(s, h->fp.f.restDensity, st);
+        ++launches;
+      }
+    }
+  }
+  if ((flags & RTP_STEP_RENDER_AUX) && model == RTP_MODEL_CLOUDS && s.N)
+  {
+    void* q;
+    size_t b;
+    if (fieldInfo(h, h->dispField, &q, &b) == RTP_OK)
+    {
+      launchFillColorFloat(s, (const float*)q, h->dispMin, h->dispMax, st);
+      ++launches;
+    }
+  }
+  if (flags & RTP_STEP_RENDER_AUX)
+    rec.mark("renderAux");
+  if (flags & RTP_STEP_CAMERA_SORT)
+  {
+    launches += enqueueCameraSort(h, cam);
+    rec.mark("cameraSort");
+  }
+  if (profile)
+  {
+    h->stageNames.clear();
+    h->stageMs.clear();
+    cudaStreamSynchronize(st);
+    for (size_t i = 1; i < rec.used; ++i)
+    {
+      float ms = 0.f;
+      cudaEventElapsedTime(&ms, h->marks[i - 1].ev, h->marks[i].ev);
+      h->stageNames.push_back(h->marks[i].name);
+      h->stageMs.push_back(ms);
+    }
+  }
+  return launches;
+}
+
+static const float kDefaultCam[3] = { 32.0f, -1.2f, 0.0f }; // render/Camera.cpp:11
+
+extern "C" int rtp_step(rtp_handle* h, unsigned flags, const float camera_pos[3])
+{
+  if (!h)
+    return RTP_ERR_INVALID;
+  CUDA_TRY(h, cudaSetDevice(h->cfg.device));
+  h->lastLaunches = enqueueStep(h, flags, camera_pos ? camera_pos : kDefaultCam, h->profiling);
+  CUDA_TRY(h, cudaGetLastError());
+  return RTP_OK;
+}
+
+extern "C" int rtp_step_n(rtp_handle* h, unsigned flags, const float camera_pos[3], int n)
+{
+  if (!h || n < 0)
+    return RTP_ERR_INVALID;
+  if (n == 0)
+    return RTP_OK;
+  const float* cam = camera_pos ? camera_pos : kDefaultCam;
+  CUDA_TRY(h, cudaSetDevice(h->cfg.device));
+  if (!h->graphValid || h->graphFlags != flags || memcmp(h->graphCam, cam, sizeof h->graphCam) != 0)
+  {
+    if (h->graphExec)
+    {
+      cudaGraphExecDestroy(h->graphExec);
+      h->graphExec = nullptr;
+    }
+    cudaGraph_t graph = nullptr;
+    CUDA_TRY(h, cudaStreamBeginCapture(h->stream, cudaStreamCaptureModeThreadLocal));
+    h->lastLaunches = enqueueStep(h, flags, cam, false);
+    CUDA_TRY(h, cudaStreamEndCapture(h->stream, &graph));
+    CUDA_TRY(h, cudaGraphInstantiate(&h->graphExec, graph, 0));
+    cudaGraphDestroy(graph);
+    h->graphFlags = flags;
+    memcpy(h->graphCam, cam, sizeof h->graphCam);
+    h->graphValid = true;
+  }
+  for (int i = 0; i < n; ++i)
+    CUDA_TRY(h, cudaGraphLaunch(h->graphExec, h->stream));
+  return RTP_OK;
+}
+
+extern "C" int rtp_sync(rtp_handle* h)
+{
+  if (!h)
+    return RTP_ERR_INVALID;
+  CUDA_TRY(h, cudaSetDevice(h->cfg.device));
+  CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+  CUDA_TRY(h, cudaGetLastError());
+  return RTP_OK;
+}
+
+// ------------------------------------------------------------------ stand-alone sort
+
+extern "C" int rtp_sort_keys(rtp_handle* h, const uint32_t* d_keys_in, uint32_t* d_keys_out, uint32_t* d_perm_out, uint64_t n,
+    int key_bits)
+{
+  if (!h || !d_keys_in || !d_keys_out || !d_perm_out || n >= (1ull << 30))
+    return RTP_ERR_INVALID;
+  if (n == 0)
+    return RTP_OK;
+  CUDA_TRY(h, cudaSetDevice(h->cfg.device));
+  const SortPlan plan = makeSortPlan((u32)n, key_bits);
+  u32 *k1 = nullptr, *v1 = nullptr, *ctrl = nullptr, *status = nullptr;
+  CUDA_TRY(h, cudaMalloc(&k1, n * 4));
+  CUDA_TRY(h, cudaMalloc(&v1, n * 4));
+  CUDA_TRY(h, cudaMalloc(&ctrl, SORT_CTRL_WORDS * 4));
+  CUDA_TRY(h, cudaMalloc(&status, sortStatusWords(plan) * 4));
+  u32* start = (plan.passes % 2 == 0) ? d_keys_out : k1;
+  cudaMemcpyAsync(start, d_keys_in, n * 4, cudaMemcpyDeviceToDevice, h->stream);
+  enqueueSort(plan, d_keys_out, d_perm_out, k1, v1, ctrl, status, h->stream);
+  cudaError_t e = cudaStreamSynchronize(h->stream);
+  if (e == cudaSuccess)
+    e = cudaGetLastError();
+  cudaFree(k1);
+  cudaFree(v1);
+  cudaFree(ctrl);
+  cudaFree(status);
+  CUDA_TRY(h, e);
+  return RTP_OK;
+}
+
+extern "C" int rtp_sort_keys_host(rtp_handle* h, const uint32_t* keys_in, uint32_t* keys_out, uint32_t* perm_out, uint64_t n,
+    int key_bits)
+{
+  if (!h || !keys_in || !keys_out || !perm_out || n >= (1ull << 30))
+    return RTP_ERR_INVALID;
+  if (n == 0)
+    return RTP_OK;
+  CUDA_TRY(h, cudaSetDevice(h->cfg.device));
+  u32 *din = nullptr, *dk = nullptr, *dp = nullptr;
+  CUDA_TRY(h, cudaMalloc(&din, n * 4));
+  CUDA_TRY(h, cudaMalloc(&dk, n * 4));
+  CUDA_TRY(h, cudaMalloc(&dp, n * 4));
+  cudaMemcpyAsync(din, keys_in, n * 4, cudaMemcpyHostToDevice, h->stream);
+  int rc = rtp_sort_keys(h, din, dk, dp, n, key_bits);
+  if (rc == RTP_OK)
+  {
+    cudaMemcpyAsync(keys_out, dk, n * 4, cudaMemcpyDeviceToHost, h->stream);
+    cudaMemcpyAsync(perm_out, dp, n * 4, cudaMemcpyDeviceToHost, h->stream);
+    if (cudaStreamSynchronize(h->stream) != cudaSuccess)
+      rc = fail(h, RTP_ERR_CUDA, "rtp_sort_keys_host: copy back failed");
+  }
+  cudaFree(din);
+  cudaFree(dk);
+  cudaFree(dp);
+  return rc;
+}
+
+// ------------------------------------------------------------------ profiling
+
+extern "C" int rtp_enable_profiling(rtp_handle* h, int enable)
+{
+  if (!h)
+    return RTP_ERR_INVALID;
+  h->profiling = enable != 0;
+  return RTP_OK;
+}
+
+extern "C" int rtp_get_stage_times(rtp_handle* h, const char** names, float* ms, int cap)
+{
+  if (!h)
+    return RTP_ERR_INVALID;
+  const int n = (int)h->stageMs.size();
+  for (int i = 0; i < n && i < cap; ++i)
+  {
+    if (names)
+      names[i] = h->stageNames[i].c_str();
+    if (ms)
+      ms[i] = h->stageMs[i];
+  }
+  return n;
+}
+
+extern "C" int rtp_last_launch_count(const rtp_handle* h) { return h ? h->lastLaunches : 0; }
+
+// ------------------------------------------------------------------ initial conditions (host)
+
+// uniform lattice: point (ix,iy,iz) = start + i * (end - start) / res, x-major order  (utils/Geometry.cpp:198-227)
+extern "C" int64_t rtp_gen_box_grid(float* out, const int res[3], const float start[3], const float end[3])
+{
+  if (!out || !res || !start || !end || res[0] <= 0 || res[1] <= 0 || res[2] <= 0)
+    return RTP_ERR_INVALID;
+  float sp[3];
+  for (int k = 0; k < 3; ++k)
+    sp[k] = (end[k] - start[k]) / res[k];
+  int64_t n = 0;
+  for (int ix = 0; ix < res[0]; ++ix)
+    for (int iy = 0; iy < res[1]; ++iy)
+      for (int iz = 0; iz < res[2]; ++iz, ++n)
+      {
+        float* o = out + 4 * n;
+        o[0] = start[0] + ix * sp[0];
+        o[1] = start[1] + iy * sp[1];
+        o[2] = start[2] + iz * sp[2];
+        o[3] = 0.0f;
+      }
+  return n;
+}
+
+// spherical lattice (phi, theta, r) around the box centre, radius = half diagonal  (utils/Geometry.cpp:243-272)
+extern "C" int64_t rtp_gen_sphere_grid(float* out, const int res[3], const float start[3], const float end[3])
+{
+  if (!out || !res || !start || !end || res[0] <= 0 || res[1] <= 0 || res[2] <= 0)
+    return RTP_ERR_INVALID;
+  const float PI_F = 3.1415927f;
+  float v[3], ctr[3];
+  for (int k = 0; k < 3; ++k)
+  {
+    v[k] = end[k] - start[k];
+    ctr[k] = start[k] + v[k] / 2.0f;
+  }
+  const float radius = sqrtf(v[0] * v[0] + v[1] * v[1] + v[2] * v[2]) / 2.0f;
+  const float dphi = PI_F / res[0], dtheta = 2.0f * PI_F / res[1], dr = radius / res[2];
+  int64_t n = 0;
+  for (int ip = 0; ip < res[0]; ++ip)
+    for (int it = 0; it < res[1]; ++it)
+      for (int ir = 0; ir < res[2]; ++ir, ++n)
+      {
+        float* o = out + 4 * n;
+        const float r = (ir + 1) * dr;
+        o[0] = ctr[0] + r * cosf(it * dtheta) * sinf(ip * dphi);
+        o[1] = ctr[1] + r * sinf(it * dtheta) * sinf(ip * dphi);
+        o[2] = ctr[2] + r * cosf(ip * dphi);
+        o[3] = 0.0f;
+      }
+  return n;
+}
+
+// uniform random fill driven by glibc rand(), x, y, z call order  (utils/Geometry.cpp:229-239)
+extern "C" int64_t rtp_gen_random_box(float* out, int64_t n, const float start[3], const float end[3], int seed)
+{
+  if (!out || !start || !end || n < 0)
+    return RTP_ERR_INVALID;
+  if (seed >= 0)
+    srand((unsigned)seed);
+  for (int64_t i = 0; i < n; ++i)
+    for (int k = 0; k < 4; ++k)
+      out[4 * i + k] = (k < 3) ? (float)rand() / (float)RAND_MAX * (end[k] - start[k]) + start[k] : 0.0f;
+  return n;
+}

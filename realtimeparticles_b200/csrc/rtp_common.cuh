@@ -1,0 +1,145 @@
+// rtp_common.cuh -- shared device types and helpers of the sm_100a backend.
+//
+// Arithmetic policy (DESIGN.md "Numerics"):
+//  * everything that feeds a DISCRETE decision or an element-wise stage is computed with explicitly rounded,
+//    never-contracted IEEE fp32 operations (__fadd_rn / __fmul_rn / __fdiv_rn / __fsqrt_rn / __fmaf_rn) in the
+//    reference's expression order, so cell ids, hit tests, predict/boundary/integrate stages are bit-exact with
+//    the oracle;
+//  * only the per-pair force/kernel terms inside neighbour sums use contracted FMAs and MUFU approximations
+//    (tolerance class, 1e-5 relative).
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/rtp_cuda.h"
+
+namespace rtp
+{
+typedef uint32_t u32;
+
+#define RTP_FLOAT_EPS 0.00000001f // define.cl:6
+#define RTP_ABS_GRAVITY_ACC_Y 9.81f // define.cl:8
+#define RTP_FAR_DIST 1000000.0f // define.cl:10
+#define RTP_MAX_STEERING 0.5f // boids.cl:10
+
+// exactly rounded, never contracted
+__device__ __forceinline__ float fadd(float a, float b) { return __fadd_rn(a, b); }
+__device__ __forceinline__ float fsub(float a, float b) { return __fsub_rn(a, b); }
+__device__ __forceinline__ float fmul(float a, float b) { return __fmul_rn(a, b); }
+__device__ __forceinline__ float fdiv(float a, float b) { return __fdiv_rn(a, b); }
+__device__ __forceinline__ float fsqrt(float a) { return __fsqrt_rn(a); }
+__device__ __forceinline__ float ffma(float a, float b, float c) { return __fmaf_rn(a, b, c); }
+// OpenCL clamp(x, lo, hi) = fmin(fmax(x, lo), hi)
+__device__ __forceinline__ float fclamp(float x, float lo, float hi) { return fminf(fmaxf(x, lo), hi); }
+
+// canonical dot product of the path: fma(z,z, fma(y,y, x*x)) (w is always 0) -- same as oracle dotc()
+__device__ __forceinline__ float dot3c(float ax, float ay, float az, float bx, float by, float bz)
+{
+  return ffma(az, bz, ffma(ay, by, fmul(ax, bx)));
+}
+
+// The grid and the baked -D constants of a model (Boids.cpp:103-113, Fluids.cpp:104-119, Clouds.cpp:132-147).
+struct GridParams
+{
+  float absW[3]; // ABS_WALL_X/Y/Z
+  float cellSize; // GRID_CELL_SIZE_XYZ
+  int res[3]; // GRID_RES_X/Y/Z
+  u32 numCells; // GRID_NUM_CELLS
+  u32 maxPartsInCell; // NUM_MAX_PARTS_IN_CELL
+};
+
+struct SphConsts
+{
+  float h; // EFFECT_RADIUS
+  float h2; // h*h (rounded)
+  float supportSq; // smallest float x with sqrtf(x) >= h : (sqrtf(sq) < h) <=> (sq < supportSq)
+  float epsSq; // largest float x with sqrtf(x) <= FLOAT_EPS : (len <= FLOAT_EPS) <=> (sq <= epsSq)
+  float poly6; // POLY6_COEFF
+  float spiky; // SPIKY_COEFF
+  float maxVel; // MAX_VEL
+  float effectRadiusSq; // EFFECT_RADIUS_SQUARED (boids)
+};
+
+// grid.cl:14-24 getCell3DIndexFromPos -- bit-exact: clamp, add, IEEE divide, floor, truncate
+__device__ __forceinline__ int3 cell3D(const GridParams& g, float x, float y, float z)
+{
+  const float px = fadd(fclamp(x, -g.absW[0], g.absW[0]), g.absW[0]);
+  const float py = fadd(fclamp(y, -g.absW[1], g.absW[1]), g.absW[1]);
+  const float pz = fadd(fclamp(z, -g.absW[2], g.absW[2]), g.absW[2]);
+  int3 c;
+  c.x = (int)(u32)floorf(fdiv(px, g.cellSize));
+  c.y = (int)(u32)floorf(fdiv(py, g.cellSize));
+  c.z = (int)(u32)floorf(fdiv(pz, g.cellSize));
+  return c;
+}
+// grid.cl:29-38 getCell1DIndexFromPos
+__device__ __forceinline__ u32 cell1D(const GridParams& g, float x, float y, float z)
+{
+  const int3 c = cell3D(g, x, y, z);
+  return (u32)c.x * (u32)g.res[2] * (u32)g.res[1] + (u32)c.y * (u32)g.res[2] + (u32)c.z;
+}
+
+enum Traversal
+{
+  TRAV_BOIDS = 0, // out-of-range cells skipped (boids.cl:84-88)
+  TRAV_FLUIDS = 1, // modulo wrap (fluids.cl:107)
+  TRAV_CLOUDS = 2 // modulo wrap + image shift in x/z, y skipped (clouds.cl:334-347)
+};
+
+// Visit the 27 neighbour cells of ci in the reference's order (iX, iY, iZ ascending) and call
+// f(start, end, shiftX, shiftZ) with the inclusive particle range of each visited cell (end capped by the table).
+template <int TRAV, typename F>
+__device__ __forceinline__ void forEachNeighbourCell(const GridParams& g, const uint2* __restrict__ table, int3 ci, F&& f)
+{
+  const int RX = g.res[0], RY = g.res[1], RZ = g.res[2];
+#pragma unroll 1
+  for (int iX = -1; iX <= 1; ++iX)
+  {
+    int cx = ci.x + iX;
+    float sx = 0.0f;
+    if (TRAV == TRAV_BOIDS)
+    {
+      if (cx < 0 || cx >= RX)
+        continue;
+    }
+    else
+    {
+      if (TRAV == TRAV_CLOUDS)
+        sx = (cx >= RX) ? 2.0f * g.absW[0] : ((cx < 0) ? -2.0f * g.absW[0] : 0.0f);
+      cx = (cx + RX) % RX;
+    }
+#pragma unroll 1
+    for (int iY = -1; iY <= 1; ++iY)
+    {
+      int cy = ci.y + iY;
+      if (TRAV == TRAV_FLUIDS)
+        cy = (cy + RY) % RY;
+      else if (cy < 0 || cy >= RY)
+        continue;
+#pragma unroll
+      for (int iZ = -1; iZ <= 1; ++iZ)
+      {
+        int cz = ci.z + iZ;
+        float sz = 0.0f;
+        if (TRAV == TRAV_BOIDS)
+        {
+          if (cz < 0 || cz >= RZ)
+            continue;
+        }
+        else
+        {
+          if (TRAV == TRAV_CLOUDS)
+            sz = (cz >= RZ) ? 2.0f * g.absW[2] : ((cz < 0) ? -2.0f * g.absW[2] : 0.0f);
+          cz = (cz + RZ) % RZ;
+        }
+        const uint2 se = __ldg(&table[(cx * RY + cy) * RZ + cz]);
+        f(se.x, se.y, sx, sz);
+      }
+    }
+  }
+}
+
+__device__ __forceinline__ float4 ld4(const float4* __restrict__ p, u32 i) { return __ldg(p + i); }
+
+} // namespace rtp

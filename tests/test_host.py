@@ -1,0 +1,113 @@
+"""CPU-side tests (-m "not gpu"): oracle self-checks against golden vectors, host logic, C-ABI exports."""
+import ctypes
+import os
+import re
+
+import numpy as np
+
+from oracle import oracle_py as O
+from realtimeparticles_b200 import _abi
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_abi_exports_every_declared_symbol():
+    hdr = open(os.path.join(ROOT, "include", "rtp_cuda.h")).read()
+    declared = set(re.findall(r"RTP_API\s+[\w\s\*]+?\b(rtp_\w+)\s*\(", hdr))
+    assert declared == set(_abi.EXPORTS), declared ^ set(_abi.EXPORTS)
+    L = ctypes.CDLL(_abi.LIB_PATH)
+    for name in declared:
+        assert hasattr(L, name), name
+    assert L.rtp_abi_version() == 1
+
+
+def test_param_struct_layouts_match_reference_sizes():
+    # BoidsRuleKernelInputs 16 B, TargetKernelInputs 8 B, FluidKernelInputs 44 B, CloudKernelInputs 52 B
+    assert ctypes.sizeof(_abi.BoidsParams) == 16 and ctypes.sizeof(_abi.TargetParams) == 8
+    assert ctypes.sizeof(_abi.FluidParams) == 44 and ctypes.sizeof(_abi.CloudParams) == 52
+    assert _abi.FluidParams.xsphViscosityCoeff.offset == 40 and _abi.CloudParams.windCoeff.offset == 48
+
+
+def test_baked_constants_match_survey():
+    # constants computed with the reference's own Utils::FloatToStr for the 30^3 grid
+    w = O.World(O.FLUIDS, 1024, 0)
+    assert w.constant("EFFECT_RADIUS") == np.float32(0.3333333433)
+    assert w.constant("EFFECT_RADIUS_SQUARED") == np.float32(0.1111111119)
+    assert w.constant("POLY6_COEFF") == np.float32(30836.984375)
+    assert w.constant("SPIKY_COEFF") == np.float32(3480.7177734375)
+    assert _abi.baked_constant(10.0 / 30.0) == np.float32(0.3333333433)
+    assert O.lib().orc_baked_constant(ctypes.c_float(1.0 / 3.0)) == _abi.baked_constant(1.0 / 3.0)
+
+
+def test_generators_product_equals_oracle():
+    a = _abi.gen_box_grid((64, 64, 32), (-5, -5, -5), (5, 0, 0))
+    b = O.gen_box_grid((64, 64, 32), (-5, -5, -5), (5, 0, 0))
+    assert np.array_equal(a, b) and a.shape == (131072, 4)
+    assert a[1, 2] == np.float32(-5 + 0.15625) and a[32, 1] == np.float32(-5 + 0.078125)
+    a = _abi.gen_sphere_grid((8, 8, 8), (-10 / 6,) * 3, (10 / 6,) * 3)
+    b = O.gen_sphere_grid((8, 8, 8), (-10 / 6,) * 3, (10 / 6,) * 3)
+    assert np.array_equal(a, b)
+    a = _abi.gen_random_box(1000, (-5, -10, -5), (5, -5, 5), 1)
+    b = O.gen_random_box(1000, (-5, -10, -5), (5, -5, 5), 1)
+    assert np.array_equal(a, b)
+
+
+def test_oracle_sort_is_stable():
+    rng = np.random.default_rng(0)
+    k = rng.integers(0, 500, size=10000).astype(np.uint32)
+    ks, perm = O.sort_keys(k)
+    assert np.array_equal(ks, np.sort(k, kind="stable"))
+    assert np.array_equal(perm, np.argsort(k, kind="stable").astype(np.uint32))
+
+
+def test_oracle_dam_initial_state_statistics():
+    # 6750 of 27000 cells occupied, 19.4 / occupied cell, max 45, cap never binds
+    from scenarios import make_fluids
+    p = make_fluids(gpu=False, jacobi=1)
+    p.w.run_stage("PREDICT_POS")
+    p.w.run_stage("FILL_CELL_IDS")
+    p.w.run_stage("SORT_BY_CELL")
+    p.w.run_stage("BUILD_CELL_TABLE")
+    se = p.w.download("START_END_CELL").astype(np.int64)
+    cnt = np.where(se[:, 1] >= se[:, 0], se[:, 1] - se[:, 0] + 1, 0)
+    assert (cnt > 0).sum() == 6750 and cnt.max() == 45
+    keys = p.w.download("CELL_ID")
+    assert (np.diff(keys.astype(np.int64)) >= 0).all()
+    # quirk 1: the cell holding sorted index 0 keeps start = 1
+    assert se[keys[0], 0] == 1
+
+
+def test_oracle_quirks_table():
+    from scenarios import make_fluids
+    verts = np.array([[5.0, 0.0, 0.0, 0], [0.0, 5.0, 0.0, 0], [0.0, 0.0, 5.0, 0], [-4.99, -4.99, -4.99, 0]], np.float32)
+    p = make_fluids(M=1024, verts=verts, gpu=False, jacobi=1)
+    p.w.upload("PRED_POS", p.w.download("POS"))
+    p.w.run_stage("FILL_CELL_IDS")
+    ids = p.w.download("CELL_ID")[:4]
+    # x = +W -> index RES -> id >= C (ignored); y/z = +W alias into the next row/column (quirk 5)
+    assert ids[0] == 30 * 900 + 15 * 30 + 15 and ids[0] >= 27000
+    assert ids[1] == 15 * 900 + 30 * 30 + 15
+    assert ids[2] == 15 * 900 + 15 * 30 + 30
+    assert ids[3] == 0
+    # tail keys 2C + i
+    assert p.w.download("CELL_ID")[4] == 54000 + 4
+
+
+def test_model_json_round_trip_and_errors():
+    from realtimeparticles_b200 import models
+    js = models.initFluidsJson
+    assert js["Fluids"]["Nb Jacobi Iterations"] == [2, 1, 6]
+    merged = models._merge_patch({"a": {"b": 1, "c": 2}}, {"a": {"b": None, "d": 3}})
+    assert merged == {"a": {"c": 2, "d": 3}}
+    assert list(models.initCloudsJson["Clouds"].keys())[0] == "Enable Temperature Smoothing"
+
+
+def test_no_gpu_means_loud_failure_not_fallback():
+    if _abi.lib().rtp_device_count() > 0:
+        return
+    try:
+        _abi.Handle(_abi.FLUIDS, 1024, 1024)
+    except _abi.RtpError as e:
+        assert "no CPU fallback" in str(e)
+    else:
+        raise AssertionError("rtp_create must fail without a CUDA device")
