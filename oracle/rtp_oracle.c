@@ -6,15 +6,25 @@
  * == one reference kernel; expression order follows the OpenCL C source left to right so that the result is
  * comparable bit for bit with oracle/_ref (the reference's .cl sources compiled through the shim).
  *
- * Canonical built-in semantics (OpenCL leaves them to the driver; see DESIGN.md "Oracle"):
- *   all arithmetic IEEE-754 binary32, round-to-nearest, no contraction (build with -ffp-contract=off), except
+ * Canonical arithmetic (OpenCL leaves built-in precision to the driver and the reference builds with
+ * -cl-fast-relaxed-math, i.e. mad contraction allowed; DESIGN.md "Canonical arithmetic" lists every choice):
+ *   all arithmetic IEEE-754 binary32, round-to-nearest; the ONLY fused operations are the explicit fmaf() below
+ *   (build with -ffp-contract=off). Element-wise stages follow the .cl expression order literally.
  *   dot(a,b)      = fma(a.z,b.z, fma(a.y,b.y, a.x*b.x))   (w is always 0 on this path)
  *   fast_length   = length = sqrtf(dot(v,v))
  *   fast_normalize(v) = v * (1.0f / sqrtf(dot(v,v)))        (0 -> NaN, as a native rsqrt would give)
  *   normalize(v)  = v / sqrtf(dot(v,v)), normalize(0) = 0
- *   pow(x,2) = x*x ; pow(x,3) = x*x*x ; pow(x,n) = powf(x,(float)n) otherwise
- *   exp           = expf (float) / exp (double, in saturationVaporDensity whose literals are double)
  *   step(e,x)     = x < e ? 0 : 1 ; clamp(x,lo,hi) = fmin(fmax(x,lo),hi) ; convert_uint = truncation
+ *   exp           = canon_expf / canon_exp below: Cody-Waite reduction by ln2 (hi+lo) and a Taylor-Horner polynomial
+ *                   (degree 7 in float, 13 in double: < 1.5 ulp), every step an explicit fma; double is used in
+ *                   saturationVaporDensity whose literals are double (clouds.cl:98)
+ *  Pair terms inside the 27-cell sums (sph.cl kernels), with sq = dot(vec,vec), len = sqrtf(sq):
+ *   poly6(vec)    = (len < h) ? POLY6_COEFF * ((t*t)*t) : 0,  t = h*h - sq          (len^2 taken as sq)
+ *   gradSpiky(vec)= vec * c,  c = (len <= FLOAT_EPS || !(len < h)) ? 0 : ((K * (hl*hl)) * (1.0f/len)),
+ *                   hl = h - len, K = SPIKY_COEFF * -3.0f
+ *   x / d inside a pair term = x * (1.0f/d) with one IEEE reciprocal
+ *   sum += a*b    = fmaf(a, b, sum) where noted at each kernel; pow(r, n) = r*r*...*r (n-1 sequential products)
+ *  Sums run in the reference's order: 27 cells (iX, iY, iZ ascending), e ascending, one fp32 accumulator.
  */
 #include "rtp_oracle.h"
 
@@ -91,6 +101,8 @@ static inline f4 add4(f4 a, f4 b) { return mk4(a.x + b.x, a.y + b.y, a.z + b.z, 
 static inline f4 sub4(f4 a, f4 b) { return mk4(a.x - b.x, a.y - b.y, a.z - b.z, a.w - b.w); }
 static inline f4 mul4s(f4 a, float s) { return mk4(a.x * s, a.y * s, a.z * s, a.w * s); }
 static inline f4 div4s(f4 a, float s) { return mk4(a.x / s, a.y / s, a.z / s, a.w / s); }
+/* a * s + c with one rounding per component */
+static inline f4 fma4s(f4 a, float s, f4 c) { return mk4(fmaf(a.x, s, c.x), fmaf(a.y, s, c.y), fmaf(a.z, s, c.z), fmaf(a.w, s, c.w)); }
 static inline float dotc(f4 a, f4 b) { return fmaf(a.z, b.z, fmaf(a.y, b.y, a.x * b.x)); }
 static inline float lengthc(f4 v) { return sqrtf(dotc(v, v)); }
 static inline f4 fast_normalizec(f4 v)
@@ -109,14 +121,55 @@ static inline f4 crossc(f4 a, f4 b)
 {
   return mk4(a.y * b.z - a.z * b.y, a.z * b.x - a.x * b.z, a.x * b.y - a.y * b.x, 0.0f);
 }
-static inline float clampf(float x, float lo, float hi) { return fminf(fmaxf(x, lo), hi); }
-static inline float powc(float x, unsigned n)
+/* cross product with one fused multiply-add per component (pair terms) */
+static inline f4 crossf(f4 a, f4 b)
 {
-  if (n == 2)
-    return x * x;
-  if (n == 3)
-    return x * x * x;
-  return powf(x, (float)n);
+  return mk4(fmaf(a.y, b.z, -(a.z * b.y)), fmaf(a.z, b.x, -(a.x * b.z)), fmaf(a.x, b.y, -(a.y * b.x)), 0.0f);
+}
+static inline float clampf(float x, float lo, float hi) { return fminf(fmaxf(x, lo), hi); }
+
+/* canonical exp (see header): exp(x) = 2^n * P(r), n = rint(x log2 e), r = x - n ln2 (two-step), P = Taylor-Horner */
+static inline float canon_expf(float x)
+{
+  x = fminf(fmaxf(x, -87.0f), 88.0f);
+  const float n = rintf(x * 1.44269504f);
+  float r = fmaf(n, -0.693145751953125f, x);
+  r = fmaf(n, -1.428606765330187e-06f, r);
+  float p = 1.98412698e-4f;
+  p = fmaf(p, r, 1.38888889e-3f);
+  p = fmaf(p, r, 8.33333333e-3f);
+  p = fmaf(p, r, 4.16666667e-2f);
+  p = fmaf(p, r, 1.66666667e-1f);
+  p = fmaf(p, r, 0.5f);
+  p = fmaf(p, r, 1.0f);
+  p = fmaf(p, r, 1.0f);
+  union { uint32_t u; float f; } s;
+  s.u = (uint32_t)((int)n + 127) << 23;
+  return p * s.f;
+}
+static inline double canon_exp(double x)
+{
+  x = fmin(fmax(x, -700.0), 700.0);
+  const double n = rint(x * 1.4426950408889634);
+  double r = fma(n, -6.93147180369123816490e-01, x);
+  r = fma(n, -1.90821492927058770002e-10, r);
+  double p = 1.0 / 6227020800.0;
+  p = fma(p, r, 1.0 / 479001600.0);
+  p = fma(p, r, 1.0 / 39916800.0);
+  p = fma(p, r, 1.0 / 3628800.0);
+  p = fma(p, r, 1.0 / 362880.0);
+  p = fma(p, r, 1.0 / 40320.0);
+  p = fma(p, r, 1.0 / 5040.0);
+  p = fma(p, r, 1.0 / 720.0);
+  p = fma(p, r, 1.0 / 120.0);
+  p = fma(p, r, 1.0 / 24.0);
+  p = fma(p, r, 1.0 / 6.0);
+  p = fma(p, r, 0.5);
+  p = fma(p, r, 1.0);
+  p = fma(p, r, 1.0);
+  union { uint64_t u; double f; } s;
+  s.u = (uint64_t)((int64_t)n + 1023) << 52;
+  return p * s.f;
 }
 
 /* grid.cl:14-24 getCell3DIndexFromPos */
@@ -138,45 +191,48 @@ static inline uint32_t cell1D(const orc_world* w, f4 p)
   return (uint32_t)c.x * (uint32_t)w->res[2] * (uint32_t)w->res[1] + (uint32_t)c.y * (uint32_t)w->res[2] + (uint32_t)c.z;
 }
 
-/* sph.cl:10-14 poly6 */
-static inline float poly6(const orc_world* w, f4 vec)
+/* sph.cl:10-14 poly6 on the squared distance (canonical: len^2 == sq); coefficient applied by the caller */
+static inline float poly6nc(const orc_world* w, float sq)
 {
   const float h = w->effectRadius;
-  const float len = lengthc(vec);
-  const float m = 1.0f - ((len < h) ? 0.0f : 1.0f);
-  return m * w->poly6Coeff * powc(h * h - len * len, 3);
+  const float len = sqrtf(sq);
+  if (!(len < h))
+    return 0.0f;
+  const float t = h * h - sq;
+  return (t * t) * t;
 }
-/* sph.cl:16-19 poly6L */
-static inline float poly6L(const orc_world* w, float len)
+static inline float poly6(const orc_world* w, float sq) { return w->poly6Coeff * poly6nc(w, sq); }
+/* sph.cl:26-34 gradSpiky = vec * spikyCoef(sq) */
+static inline float spikyCoef(const orc_world* w, float sq)
 {
   const float h = w->effectRadius;
-  const float m = 1.0f - ((len < h) ? 0.0f : 1.0f);
-  return m * w->poly6Coeff * powc(h * h - len * len, 3);
+  const float len = sqrtf(sq);
+  if (len <= FLOAT_EPS || !(len < h))
+    return 0.0f;
+  const float hl = h - len;
+  const float K = w->spikyCoeff * -3.0f;
+  return (K * (hl * hl)) * (1.0f / len);
 }
-/* sph.cl:26-34 gradSpiky:  vec * mask * SPIKY_COEFF * -3 * pow(h - len, 2) / len, evaluated left to right */
-static inline f4 gradSpiky(const orc_world* w, f4 vec)
+/* 1 / (poly6L(artPressureRadius * EFFECT_RADIUS) / POLY6_COEFF), fluids.cl:56 (the coefficient cancels in the ratio) */
+static inline float artInvDenominator(const orc_world* w)
 {
   const float h = w->effectRadius;
-  const float len = lengthc(vec);
-  if (len <= FLOAT_EPS)
-    return mk4(0.0f, 0.0f, 0.0f, 0.0f);
-  const float m = 1.0f - ((len < h) ? 0.0f : 1.0f);
-  const float p = powc(h - len, 2);
-  f4 r = mul4s(vec, m);
-  r = mul4s(r, w->spikyCoeff);
-  r = mul4s(r, -3.0f);
-  r = mul4s(r, p);
-  r = div4s(r, len);
-  return r;
+  const float len = w->fluid.artPressureRadius * h;
+  const float t = h * h - len * len;
+  const float den = (len < h) ? (t * t) * t : 0.0f;
+  return 1.0f / den;
 }
-/* fluids.cl:51-57 / clouds.cl:105-111 artPressure */
-static inline float artPressure(const orc_world* w, f4 vec)
+/* fluids.cl:51-57 / clouds.cl:105-111 artPressure = -k * (W(vec)/W(dq h))^n */
+static inline float artPressure(const orc_world* w, float sq, float invDen)
 {
   const rtp_fluid_params* f = &w->fluid;
   if (f->isArtPressureEnabled == 0)
     return 0.0f;
-  const float ratio = poly6(w, vec) / poly6L(w, f->artPressureRadius * w->effectRadius);
-  return -f->artPressureCoeff * powc(ratio, f->artPressureExp);
+  const float ratio = poly6nc(w, sq) * invDen;
+  float pw = ratio;
+  for (uint32_t q = 1; q < f->artPressureExp; ++q)
+    pw = pw * ratio;
+  return -(f->artPressureCoeff * pw);
 }
 
 /* Neighbour-cell resolution for the three traversal flavours.
@@ -676,7 +732,7 @@ static void k_bd_rules3D(orc_world* w)
       {
         avgPos = add4(avgPos, posN);
         avgVel = add4(avgVel, fast_normalizec(w->vel[e]));
-        repulse = add4(repulse, div4s(vec, sq));
+        repulse = fma4s(vec, 1.0f / sq, repulse); /* vec / squaredDist, boids.cl:105 */
         ++count;
       }
     })
@@ -722,7 +778,7 @@ static void k_bd_rules2D(orc_world* w)
           {
             avgPos = add4(avgPos, posN);
             avgVel = add4(avgVel, fast_normalizec(w->vel[e]));
-            repulse = add4(repulse, div4s(vec, sq));
+            repulse = fma4s(vec, 1.0f / sq, repulse);
             ++count;
           }
         }
@@ -868,7 +924,10 @@ static void k_density(orc_world* w)
     const f4 pos = w->predPos[i];
     const i3 ci = cell3D(w, pos);
     float d = 0.0f;
-    FOR_EACH_NEIGHBOUR(w, ci, e, shift, { d += poly6(w, pair_vec(w, pos, w->predPos[e], shift)); })
+    FOR_EACH_NEIGHBOUR(w, ci, e, shift, {
+      const f4 vec = pair_vec(w, pos, w->predPos[e], shift);
+      d += poly6(w, dotc(vec, vec));
+    })
     w->density[i] = d;
   }
 }
@@ -886,9 +945,11 @@ static void k_constraintFactor(orc_world* w)
     f4 sumGradCi = mk4(0, 0, 0, 0);
     float sumSqGradC = 0.0f;
     FOR_EACH_NEIGHBOUR(w, ci, e, shift, {
-      const f4 grad = gradSpiky(w, pair_vec(w, pos, w->predPos[e], shift));
-      sumGradCi = add4(sumGradCi, grad);
-      sumSqGradC += dotc(grad, grad);
+      const f4 vec = pair_vec(w, pos, w->predPos[e], shift);
+      const float sq = dotc(vec, vec);
+      const float c = spikyCoef(w, sq);
+      sumGradCi = fma4s(vec, c, sumGradCi); /* sumGradCi += grad */
+      sumSqGradC += (c * c) * sq; /* dot(grad, grad) */
     })
     sumSqGradC += dotc(sumGradCi, sumGradCi);
     sumSqGradC /= rho0 * rho0;
@@ -906,10 +967,12 @@ static void k_constraintCorrection(orc_world* w)
     const float lambdaI = w->constFactor[i];
     const i3 ci = cell3D(w, pos);
     f4 corr = mk4(0, 0, 0, 0);
+    const float invDen = artInvDenominator(w);
     FOR_EACH_NEIGHBOUR(w, ci, e, shift, {
       const f4 vec = pair_vec(w, pos, w->predPos[e], shift);
-      const float s = lambdaI + w->constFactor[e] + artPressure(w, vec);
-      corr = add4(corr, mul4s(gradSpiky(w, vec), s));
+      const float sq = dotc(vec, vec);
+      const float s = lambdaI + w->constFactor[e] + artPressure(w, sq, invDen);
+      corr = fma4s(vec, s * spikyCoef(w, sq), corr);
     })
     w->corrPos[i] = div4s(corr, w->fluid.restDensity);
   }
@@ -951,7 +1014,10 @@ static void k_vorticity(orc_world* w)
     const i3 ci = cell3D(w, pos);
     f4 vort = mk4(0, 0, 0, 0);
     FOR_EACH_NEIGHBOUR(w, ci, e, shift, {
-      vort = add4(vort, crossc(sub4(w->vel[e], velocity), gradSpiky(w, pair_vec(w, pos, w->predPos[e], shift))));
+      const f4 vec = pair_vec(w, pos, w->predPos[e], shift);
+      const float c = spikyCoef(w, dotc(vec, vec));
+      /* cross(dv, vec * c) = cross(dv, vec) * c with cross(a,b).x = fma(a.y, b.z, -(a.z * b.y)) */
+      vort = fma4s(crossf(sub4(w->vel[e], velocity), vec), c, vort);
     })
     w->vort[i] = vort;
   }
@@ -968,7 +1034,8 @@ static void k_vorticityConfinement(orc_world* w)
     const i3 ci = cell3D(w, pos);
     f4 n = mk4(0, 0, 0, 0);
     FOR_EACH_NEIGHBOUR(w, ci, e, shift, {
-      n = add4(n, mul4s(gradSpiky(w, pair_vec(w, pos, w->predPos[e], shift)), lengthc(w->vort[e])));
+      const f4 vec = pair_vec(w, pos, w->predPos[e], shift);
+      n = fma4s(vec, lengthc(w->vort[e]) * spikyCoef(w, dotc(vec, vec)), n);
     })
     const f4 c = crossc(normalizec(n), vorticity);
     w->vel[i] = add4(w->vel[i], mul4s(mul4s(c, w->fluid.vorticityConfCoeff), w->fluid.timeStep));
@@ -988,7 +1055,8 @@ static void k_xsph(orc_world* w)
     const i3 ci = cell3D(w, pos);
     f4 visc = mk4(0, 0, 0, 0);
     FOR_EACH_NEIGHBOUR(w, ci, e, shift, {
-      visc = add4(visc, mul4s(sub4(w->velInVisc[e], velocity), poly6(w, pair_vec(w, pos, w->predPos[e], shift))));
+      const f4 vec = pair_vec(w, pos, w->predPos[e], shift);
+      visc = fma4s(sub4(w->velInVisc[e], velocity), poly6(w, dotc(vec, vec)), visc);
     })
     w->vel[i] = add4(velocity, mul4s(visc, w->fluid.xsphViscosityCoeff));
   }
@@ -1009,8 +1077,8 @@ static void k_updatePosition(orc_world* w)
   {
     const f4 pp = w->predPos[i];
     f4 p = pp;
-    p.x += (1 - expf(-(pp.y + WY) * 0.2f)) * c->windCoeff * c->timeStep * (float)(c->dim - 2);
-    p.z += (1 - expf(-(pp.y + WY) * 0.3f)) * 0.7f * c->windCoeff * c->timeStep;
+    p.x += (1 - canon_expf(-(pp.y + WY) * 0.2f)) * c->windCoeff * c->timeStep * (float)(c->dim - 2);
+    p.z += (1 - canon_expf(-(pp.y + WY) * 0.3f)) * 0.7f * c->windCoeff * c->timeStep;
     w->pos[i] = p;
   }
 }
@@ -1050,9 +1118,9 @@ static void k_fillColorFloat(orc_world* w)
 }
 
 /* clouds.cl:72-99 */
-static inline float externalHeatSource(const orc_world* w, float alt) { return clampf(expf(-(alt + w->absW[1]) / 3.0f), 0.0f, 1.0f); }
+static inline float externalHeatSource(const orc_world* w, float alt) { return clampf(canon_expf(-(alt + w->absW[1]) / 3.0f), 0.0f, 1.0f); }
 static inline float environmentTemp(const orc_world* w, float alt) { return -3.5f * (alt + w->absW[1]) + 293.0f; }
-static inline float saturationVaporDensity(float T) { return (float)(217 * exp(19.5 - 4303.4 / ((double)T - 29.5)) / (double)T); }
+static inline float saturationVaporDensity(float T) { return (float)(217 * canon_exp(19.5 - 4303.4 / ((double)T - 29.5)) / (double)T); }
 
 /* cld_initTemperature clouds.cl:116-122 + cld_initVaporDensity :127-135, both over M (Clouds.cpp:495-497) */
 int orc_init_clouds_fields(orc_world* w)
@@ -1112,7 +1180,9 @@ static void k_laplacianTemp(orc_world* w)
     float lap = 0.0f;
     FOR_EACH_NEIGHBOUR(w, ci, e, shift, {
       const f4 vec = pair_vec(w, pos, w->pos[e], shift);
-      lap += (temp - w->temp[e]) * dotc(vec, gradSpiky(w, vec)) / (dotc(vec, vec) + FLOAT_EPS);
+      const float sq = dotc(vec, vec);
+      /* dot(vec, grad) = c * sq ; x / d = x * (1/d) */
+      lap = fmaf((temp - w->temp[e]) * (spikyCoef(w, sq) * sq), 1.0f / (sq + FLOAT_EPS), lap);
     })
     w->lapTemp[i] = lap / w->cloud.restDensity;
   }
@@ -1130,10 +1200,10 @@ static void k_constraintFactorTemp(orc_world* w)
     float sumGradCi = 0.0f, sumSqGradC = 0.0f;
     FOR_EACH_NEIGHBOUR(w, ci, e, shift, {
       const f4 vec = pair_vec(w, pos, w->pos[e], shift);
-      const f4 grad = gradSpiky(w, vec);
-      const float dT = dotc(vec, grad) / (dotc(vec, vec) * w->cloud.restDensity + FLOAT_EPS);
+      const float sq = dotc(vec, vec);
+      const float dT = (spikyCoef(w, sq) * sq) * (1.0f / fmaf(sq, w->cloud.restDensity, FLOAT_EPS));
       sumGradCi += dT;
-      sumSqGradC += dT * dT;
+      sumSqGradC = fmaf(dT, dT, sumSqGradC);
     })
     sumSqGradC += sumGradCi * sumGradCi;
     w->constFactorTemp[i] = -lap / (sumSqGradC + w->cloud.relaxCFM);
@@ -1152,9 +1222,9 @@ static void k_constraintCorrectionTemp(orc_world* w)
     float corr = 0.0f;
     FOR_EACH_NEIGHBOUR(w, ci, e, shift, {
       const f4 vec = pair_vec(w, pos, w->pos[e], shift);
-      const f4 grad = gradSpiky(w, vec);
-      const float dT = dotc(vec, grad) / (dotc(vec, vec) * w->cloud.restDensity + FLOAT_EPS);
-      corr += (lambdaI + w->constFactorTemp[e]) * dT;
+      const float sq = dotc(vec, vec);
+      const float dT = (spikyCoef(w, sq) * sq) * (1.0f / fmaf(sq, w->cloud.restDensity, FLOAT_EPS));
+      corr = fmaf(lambdaI + w->constFactorTemp[e], dT, corr);
     })
     w->corrTemp[i] = corr;
   }

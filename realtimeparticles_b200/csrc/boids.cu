@@ -8,8 +8,8 @@
 //   boidsRulesKernel   : bd_applyBoidsRulesWithGrid3D/2D (boids.cl:46-221) fused with bd_addTargetRule (:226-241),
 //                        bd_updateVel (:246-259) and bd_updatePosAndApply{Wall,Periodic}BC (:264-315)
 // p_acc and p_col are not permuted by the cell sort: p_acc is fully rewritten every step and p_col is uniform.
-// The whole rule evaluation is bit-exact with the oracle: exact hit test, sums in the reference's order, IEEE
-// divisions.
+// The whole rule evaluation is bit-exact with the oracle: exact hit test, sums in the reference's order, the
+// canonical operation sequence of DESIGN.md "Canonical arithmetic".
 #include "kernels.cuh"
 
 namespace rtp
@@ -87,7 +87,8 @@ __global__ void __launch_bounds__(BD_THREADS) boidsRulesKernel(DeviceState s, Gr
         const float4 nv = ld4(NV, e);
         apx += pj.x; apy += pj.y; apz += pj.z;
         avx += nv.x; avy += nv.y; avz += nv.z;
-        rpx += fdiv(dx, sq); rpy += fdiv(dy, sq); rpz += fdiv(dz, sq);
+        const float r = frcp(sq); // vec / squaredDist == vec * (1 / squaredDist), one fused op per component
+        rpx = ffma(dx, r, rpx); rpy = ffma(dy, r, rpy); rpz = ffma(dz, r, rpz);
         ++count;
       }
     }

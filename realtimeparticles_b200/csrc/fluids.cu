@@ -17,27 +17,15 @@
 //   xsphKernel              fld_applyXsphViscosityCorrection (:383-430) + fld_updatePosition (:444-450)
 // The clouds variants use the same kernels with the periodic-image traversal (clouds.cl:334-347).
 //
-// Numerics: hit tests and all element-wise stages are bit-exact (rtp_common.cuh); pair terms inside the sums use
-// FMA contraction and MUFU rsqrt/rcp (tolerance class). Sums run in the reference's order (27 cells, ascending e).
+// Numerics: bit-exact with the oracle everywhere. Hit tests, element-wise stages and the per-pair terms use the
+// canonical operation sequence (rtp_common.cuh, DESIGN.md "Canonical arithmetic"); sums run in the reference's
+// order (27 cells, ascending e, one fp32 accumulator per component).
 #include "kernels.cuh"
 
 namespace rtp
 {
 constexpr int NB_THREADS = 128; // neighbour kernels
 constexpr int EW_THREADS = 256; // element-wise kernels
-
-__device__ __forceinline__ float rsqrtApprox(float x)
-{
-  float r;
-  asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
-  return r;
-}
-__device__ __forceinline__ float rcpApprox(float x)
-{
-  float r;
-  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
-  return r;
-}
 
 __device__ __forceinline__ void fillCellTable(const u32* __restrict__ keys, u32 i, u32 N, u32 numCells, uint2* __restrict__ table)
 {
@@ -97,12 +85,18 @@ __device__ __forceinline__ void sweepNeighbours(const GridParams& g, const SphCo
       });
 }
 
-// |gradSpiky| / (-3 SPIKY_COEFF |vec|) = (h - len)^2 / len   (sph.cl:26-34; the constant is applied after the sum)
-__device__ __forceinline__ float spikyScalar(const SphConsts& c, float sq)
+// gradSpiky(vec) = vec * spikyCoef(sq) for FLOAT_EPS < len < h (sph.cl:26-34): ((K * (h-len)^2) * (1/len)), K = -3 SPIKY_COEFF
+__device__ __forceinline__ float spikyCoef(const SphConsts& c, float sq)
 {
-  const float rinv = rsqrtApprox(sq);
-  const float hl = c.h - sq * rinv;
-  return hl * hl * rinv;
+  const float len = fsqrt(sq);
+  const float hl = fsub(c.h, len);
+  return fmul(fmul(c.spikyK, fmul(hl, hl)), frcp(len));
+}
+// poly6(vec) / POLY6_COEFF = (h^2 - sq)^3 inside the support (sph.cl:10-14)
+__device__ __forceinline__ float poly6nc(const SphConsts& c, float sq)
+{
+  const float t = fsub(c.h2, sq);
+  return fmul(fmul(t, t), t);
 }
 
 // ------------------------------------------------------------------ element-wise kernels
@@ -134,15 +128,56 @@ __global__ void __launch_bounds__(EW_THREADS) fluidGatherKernel(DeviceState s, G
   fillCellTable(s.cellID, i, s.N, g.numCells, s.table);
 }
 
+// canonical exp of the path (DESIGN.md "Canonical arithmetic"): 2^n * P(r), n = rint(x log2 e), r = x - n ln2 in two
+// fused steps, P = Taylor-Horner (degree 7 float / 13 double), every step an explicit fma -- identical to the oracle's.
+__device__ __forceinline__ float canonExpf(float x)
+{
+  x = fminf(fmaxf(x, -87.0f), 88.0f);
+  const float n = rintf(fmul(x, 1.44269504f));
+  float r = ffma(n, -0.693145751953125f, x);
+  r = ffma(n, -1.428606765330187e-06f, r);
+  float p = 1.98412698e-4f;
+  p = ffma(p, r, 1.38888889e-3f);
+  p = ffma(p, r, 8.33333333e-3f);
+  p = ffma(p, r, 4.16666667e-2f);
+  p = ffma(p, r, 1.66666667e-1f);
+  p = ffma(p, r, 0.5f);
+  p = ffma(p, r, 1.0f);
+  p = ffma(p, r, 1.0f);
+  return fmul(p, __int_as_float(((int)n + 127) << 23));
+}
+__device__ __forceinline__ double canonExp(double x)
+{
+  x = fmin(fmax(x, -700.0), 700.0);
+  const double n = rint(__dmul_rn(x, 1.4426950408889634));
+  double r = __fma_rn(n, -6.93147180369123816490e-01, x);
+  r = __fma_rn(n, -1.90821492927058770002e-10, r);
+  double p = 1.0 / 6227020800.0;
+  p = __fma_rn(p, r, 1.0 / 479001600.0);
+  p = __fma_rn(p, r, 1.0 / 39916800.0);
+  p = __fma_rn(p, r, 1.0 / 3628800.0);
+  p = __fma_rn(p, r, 1.0 / 362880.0);
+  p = __fma_rn(p, r, 1.0 / 40320.0);
+  p = __fma_rn(p, r, 1.0 / 5040.0);
+  p = __fma_rn(p, r, 1.0 / 720.0);
+  p = __fma_rn(p, r, 1.0 / 120.0);
+  p = __fma_rn(p, r, 1.0 / 24.0);
+  p = __fma_rn(p, r, 1.0 / 6.0);
+  p = __fma_rn(p, r, 0.5);
+  p = __fma_rn(p, r, 1.0);
+  p = __fma_rn(p, r, 1.0);
+  return __dmul_rn(p, __longlong_as_double(((long long)n + 1023) << 52));
+}
+
 // clouds.cl:72-99
 __device__ __forceinline__ float environmentTemp(const GridParams& g, float alt) { return fadd(fmul(-3.5f, fadd(alt, g.absW[1])), 293.0f); }
 __device__ __forceinline__ float externalHeatSource(const GridParams& g, float alt)
 {
-  return fclamp(expf(fdiv(-fadd(alt, g.absW[1]), 3.0f)), 0.0f, 1.0f);
+  return fclamp(canonExpf(fdiv(-fadd(alt, g.absW[1]), 3.0f)), 0.0f, 1.0f);
 }
 __device__ __forceinline__ float saturationVaporDensity(float T)
 {
-  return (float)(217 * exp(19.5 - 4303.4 / ((double)T - 29.5)) / (double)T);
+  return (float)__ddiv_rn(__dmul_rn(217.0, canonExp(__dsub_rn(19.5, __ddiv_rn(4303.4, __dsub_rn((double)T, 29.5))))), (double)T);
 }
 
 // cld_initTemperature clouds.cl:116-122 + cld_initVaporDensity :127-135 over M
@@ -224,8 +259,8 @@ __global__ void __launch_bounds__(EW_THREADS) cloudsFinishKernel(DeviceState s, 
   const float4 pp = pred[i];
   float4 p = pp;
   const float a = fadd(pp.y, g.absW[1]);
-  p.x = fadd(p.x, fmul(fmul(fmul(fsub(1.0f, expf(fmul(-a, 0.2f))), c.windCoeff), c.timeStep), (float)(c.dim - 2)));
-  p.z = fadd(p.z, fmul(fmul(fmul(fsub(1.0f, expf(fmul(-a, 0.3f))), 0.7f), c.windCoeff), c.timeStep));
+  p.x = fadd(p.x, fmul(fmul(fmul(fsub(1.0f, canonExpf(fmul(-a, 0.2f))), c.windCoeff), c.timeStep), (float)(c.dim - 2)));
+  p.z = fadd(p.z, fmul(fmul(fmul(fsub(1.0f, canonExpf(fmul(-a, 0.3f))), 0.7f), c.windCoeff), c.timeStep));
   s.posA[i] = p;
   if (copyVel)
     s.velA[i] = s.velB[i];
@@ -247,25 +282,20 @@ __global__ void __launch_bounds__(NB_THREADS) densityLambdaKernel(DeviceState s,
   if (i >= s.N)
     return;
   const float4 pi = pred[i];
-  float sumT3 = 0.f, gx = 0.f, gy = 0.f, gz = 0.f, sumG2 = 0.f;
+  float density = 0.f, gx = 0.f, gy = 0.f, gz = 0.f, sumG2 = 0.f;
   sweepNeighbours<TRAV>(g, c, s.table, pred, pi,
       [&](u32, float dx, float dy, float dz, float sq)
       {
-        const float t = c.h2 - sq;
-        sumT3 += t * t * t;
+        density = fadd(density, fmul(c.poly6, poly6nc(c, sq)));
         if (sq > c.epsSq)
         {
-          const float G = spikyScalar(c, sq);
-          gx += dx * G;
-          gy += dy * G;
-          gz += dz * G;
-          sumG2 += G * G * sq;
+          const float cs = spikyCoef(c, sq);
+          gx = ffma(dx, cs, gx);
+          gy = ffma(dy, cs, gy);
+          gz = ffma(dz, cs, gz);
+          sumG2 = fadd(sumG2, fmul(fmul(cs, cs), sq));
         }
       });
-  const float k = -3.0f * c.spiky;
-  const float density = c.poly6 * sumT3;
-  gx *= k; gy *= k; gz *= k;
-  sumG2 *= k * k;
   s.density[i] = density;
   // fluids.cl:189-192
   const float densityC = fsub(fdiv(density, rho0), 1.0f);
@@ -293,27 +323,24 @@ __global__ void __launch_bounds__(NB_THREADS) correctionKernel(DeviceState s, Gr
       {
         if (sq > c.epsSq)
         {
-          const float G = spikyScalar(c, sq);
-          float sc = li + __ldg(lambda + e);
+          float sc = fadd(li, __ldg(lambda + e));
           if (art)
           {
             // artPressure fluids.cl:51-57: -k * (W(vec) / W(dq h))^n ; POLY6_COEFF cancels in the ratio
-            const float t = c.h2 - sq;
-            const float ratio = t * t * t * invDen;
+            const float ratio = fmul(poly6nc(c, sq), invDen);
             float pw = ratio;
             for (u32 q = 1; q < artExp; ++q)
-              pw *= ratio;
-            sc -= artCoeff * pw;
+              pw = fmul(pw, ratio);
+            sc = fadd(sc, -fmul(artCoeff, pw));
           }
-          const float w = sc * G;
-          cx += w * dx;
-          cy += w * dy;
-          cz += w * dz;
+          const float w = fmul(sc, spikyCoef(c, sq));
+          cx = ffma(dx, w, cx);
+          cy = ffma(dy, w, cy);
+          cz = ffma(dz, w, cz);
         }
       });
-  const float k = -3.0f * c.spiky;
   const float rho0 = fp.f.restDensity;
-  const float4 corr = make_float4(fdiv(cx * k, rho0), fdiv(cy * k, rho0), fdiv(cz * k, rho0), 0.0f);
+  const float4 corr = make_float4(fdiv(cx, rho0), fdiv(cy, rho0), fdiv(cz, rho0), 0.0f);
   if (writeCorr)
     s.corrPos[i] = corr;
   // fld_correctPosition / cld_correctPosition
@@ -374,16 +401,15 @@ __global__ void __launch_bounds__(NB_THREADS) vorticityKernel(DeviceState s, Gri
       {
         if (sq > c.epsSq)
         {
-          const float G = spikyScalar(c, sq);
+          const float cs = spikyCoef(c, sq);
           const float4 vj = ld4(V, e);
-          const float ax = vj.x - vi.x, ay = vj.y - vi.y, az = vj.z - vi.z;
-          wx += (ay * dz - az * dy) * G;
-          wy += (az * dx - ax * dz) * G;
-          wz += (ax * dy - ay * dx) * G;
+          const float ax = fsub(vj.x, vi.x), ay = fsub(vj.y, vi.y), az = fsub(vj.z, vi.z);
+          // cross(dv, vec * c) = cross(dv, vec) * c, cross(a,b).x = fma(a.y, b.z, -(a.z * b.y))
+          wx = ffma(ffma(ay, dz, -fmul(az, dy)), cs, wx);
+          wy = ffma(ffma(az, dx, -fmul(ax, dz)), cs, wy);
+          wz = ffma(ffma(ax, dy, -fmul(ay, dx)), cs, wz);
         }
       });
-  const float k = -3.0f * c.spiky;
-  wx *= k; wy *= k; wz *= k;
   s.vort[i] = make_float4(wx, wy, wz, 0.0f);
   s.vortNorm[i] = fsqrt(dot3c(wx, wy, wz, wx, wy, wz)); // fast_length(vort[e]) of the next sweep
 }
@@ -403,14 +429,12 @@ __global__ void __launch_bounds__(NB_THREADS) confinementKernel(DeviceState s, G
       {
         if (sq > c.epsSq)
         {
-          const float w = __ldg(wn + e) * spikyScalar(c, sq);
-          nx += w * dx;
-          ny += w * dy;
-          nz += w * dz;
+          const float w = fmul(__ldg(wn + e), spikyCoef(c, sq));
+          nx = ffma(dx, w, nx);
+          ny = ffma(dy, w, ny);
+          nz = ffma(dz, w, nz);
         }
       });
-  const float k = -3.0f * c.spiky;
-  nx *= k; ny *= k; nz *= k;
   // normalize(n) with normalize(0) = 0, then vel += coeff * cross(n, vorticity) * dt   (fluids.cl:376)
   const float l = fsqrt(dot3c(nx, ny, nz, nx, ny, nz));
   if (l == 0.0f)
@@ -440,14 +464,12 @@ __global__ void __launch_bounds__(NB_THREADS) xsphKernel(DeviceState s, GridPara
   sweepNeighbours<TRAV>(g, c, s.table, pred, pi,
       [&](u32 e, float, float, float, float sq)
       {
-        const float t = c.h2 - sq;
-        const float W = t * t * t;
+        const float W = fmul(c.poly6, poly6nc(c, sq));
         const float4 vj = ld4(V, e);
-        sx += (vj.x - vi.x) * W;
-        sy += (vj.y - vi.y) * W;
-        sz += (vj.z - vi.z) * W;
+        sx = ffma(fsub(vj.x, vi.x), W, sx);
+        sy = ffma(fsub(vj.y, vi.y), W, sy);
+        sz = ffma(fsub(vj.z, vi.z), W, sz);
       });
-  sx *= c.poly6; sy *= c.poly6; sz *= c.poly6;
   s.velA[i] = make_float4(fadd(vi.x, fmul(sx, coeff)), fadd(vi.y, fmul(sy, coeff)), fadd(vi.z, fmul(sz, coeff)), 0.0f);
   if (TRAV == TRAV_FLUIDS)
     s.posA[i] = pi; // fld_updatePosition fluids.cl:444-450 (clouds: cloudsFinishKernel)
@@ -467,9 +489,8 @@ __global__ void __launch_bounds__(NB_THREADS) laplacianTempKernel(DeviceState s,
       [&](u32 e, float, float, float, float sq)
       {
         if (sq > c.epsSq)
-          lap += (Ti - __ldg(T + e)) * (spikyScalar(c, sq) * sq) * rcpApprox(sq + RTP_FLOAT_EPS);
+          lap = ffma(fmul(fsub(Ti, __ldg(T + e)), fmul(spikyCoef(c, sq), sq)), frcp(fadd(sq, RTP_FLOAT_EPS)), lap);
       });
-  lap *= -3.0f * c.spiky;
   s.lapTemp[i] = fdiv(lap, rho0);
 }
 
@@ -486,14 +507,11 @@ __global__ void __launch_bounds__(NB_THREADS) lambdaTempKernel(DeviceState s, Gr
       {
         if (sq > c.epsSq)
         {
-          const float d = (spikyScalar(c, sq) * sq) * rcpApprox(sq * rho0 + RTP_FLOAT_EPS);
-          sumD += d;
-          sumD2 += d * d;
+          const float d = fmul(fmul(spikyCoef(c, sq), sq), frcp(ffma(sq, rho0, RTP_FLOAT_EPS)));
+          sumD = fadd(sumD, d);
+          sumD2 = ffma(d, d, sumD2);
         }
       });
-  const float k = -3.0f * c.spiky;
-  sumD *= k;
-  sumD2 *= k * k;
   const float ssg = fadd(sumD2, fmul(sumD, sumD));
   s.lambdaTemp[i] = fdiv(-s.lapTemp[i], fadd(ssg, cfm));
 }
@@ -513,11 +531,10 @@ __global__ void __launch_bounds__(NB_THREADS) correctTempKernel(DeviceState s, G
       {
         if (sq > c.epsSq)
         {
-          const float d = (spikyScalar(c, sq) * sq) * rcpApprox(sq * rho0 + RTP_FLOAT_EPS);
-          corr += (li + __ldg(L + e)) * d;
+          const float d = fmul(fmul(spikyCoef(c, sq), sq), frcp(ffma(sq, rho0, RTP_FLOAT_EPS)));
+          corr = ffma(fadd(li, __ldg(L + e)), d, corr);
         }
       });
-  corr *= -3.0f * c.spiky;
   s.corrTemp[i] = corr;
   s.tempB[i] = fadd(s.tempB[i], fmul(0.3f, corr));
 }

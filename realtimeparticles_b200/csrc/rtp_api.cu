@@ -99,6 +99,7 @@ static void computeConstants(rtp_handle* h)
   c.h2 = c.h * c.h;
   c.poly6 = rtp_baked_constant(315.0f / (64.0f * PI_F * powf(effectRadius, 9.f)));
   c.spiky = rtp_baked_constant(15.0f / (PI_F * powf(effectRadius, 6.f)));
+  c.spikyK = c.spiky * -3.0f;
   c.maxVel = rtp_baked_constant(30.0f);
   c.effectRadiusSq = rtp_baked_constant(1.0f * (float)cfg.box[0] * (float)cfg.box[0] / (float)((size_t)cfg.grid[0] * cfg.grid[0]));
   // (sqrtf(sq) < h) <=> (sq < supportSq): sqrtf is correctly rounded and monotonic
@@ -122,7 +123,7 @@ static void updateDerivedFluidParams(rtp_handle* h)
   // poly6L(artPressureRadius * EFFECT_RADIUS) without its coefficient (fluids.cl:56)
   const float len = h->fp.f.artPressureRadius * h->c.h;
   const float t = h->c.h * h->c.h - len * len;
-  const float den = (len < h->c.h) ? t * t * t : 0.0f;
+  const float den = (len < h->c.h) ? (t * t) * t : 0.0f;
   h->fp.invArtDenom = 1.0f / den;
 }
 

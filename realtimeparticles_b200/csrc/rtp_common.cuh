@@ -5,8 +5,11 @@
 //    never-contracted IEEE fp32 operations (__fadd_rn / __fmul_rn / __fdiv_rn / __fsqrt_rn / __fmaf_rn) in the
 //    reference's expression order, so cell ids, hit tests, predict/boundary/integrate stages are bit-exact with
 //    the oracle;
-//  * only the per-pair force/kernel terms inside neighbour sums use contracted FMAs and MUFU approximations
-//    (tolerance class, 1e-5 relative).
+//  * the per-pair terms inside the neighbour sums follow ONE canonical operation sequence (explicit FMAs, IEEE
+//    sqrt and reciprocal, listed in DESIGN.md "Canonical arithmetic" and restated independently in
+//    oracle/rtp_oracle.c), accumulated in the reference's order -- so every field of every model is bit-exact
+//    with the oracle, not merely within tolerance. The compiler is never allowed to contract or reassociate:
+//    all of it is written with the _rn intrinsics.
 #pragma once
 
 #include <cuda_runtime.h>
@@ -29,6 +32,7 @@ __device__ __forceinline__ float fsub(float a, float b) { return __fsub_rn(a, b)
 __device__ __forceinline__ float fmul(float a, float b) { return __fmul_rn(a, b); }
 __device__ __forceinline__ float fdiv(float a, float b) { return __fdiv_rn(a, b); }
 __device__ __forceinline__ float fsqrt(float a) { return __fsqrt_rn(a); }
+__device__ __forceinline__ float frcp(float a) { return __frcp_rn(a); } // == 1.0f / a
 __device__ __forceinline__ float ffma(float a, float b, float c) { return __fmaf_rn(a, b, c); }
 // OpenCL clamp(x, lo, hi) = fmin(fmax(x, lo), hi)
 __device__ __forceinline__ float fclamp(float x, float lo, float hi) { return fminf(fmaxf(x, lo), hi); }
@@ -57,6 +61,7 @@ struct SphConsts
   float epsSq; // largest float x with sqrtf(x) <= FLOAT_EPS : (len <= FLOAT_EPS) <=> (sq <= epsSq)
   float poly6; // POLY6_COEFF
   float spiky; // SPIKY_COEFF
+  float spikyK; // SPIKY_COEFF * -3.0f (one rounding)
   float maxVel; // MAX_VEL
   float effectRadiusSq; // EFFECT_RADIUS_SQUARED (boids)
 };

@@ -1,7 +1,10 @@
 """GPU parity tests proper: the CUDA path (through the C ABI) against the CPU oracle on identical seeded inputs.
 
 Bars (BASELINE.json north_star): cell ids, sorted permutation, cell start/end table BIT-EXACT; single-step positions
-and velocities within 1e-5 relative (norm-wise: max|a-b| <= 1e-5 max|b|); multi-step aggregate invariants within 1 %.
+and velocities within 1e-5 relative; 100-step aggregate invariants within 1 %.
+What is enforced here is stricter: the CUDA kernels implement the same canonical fp32 operation sequence as the
+oracle (DESIGN.md "Canonical arithmetic") and sum in the reference's order, so EVERY field is required to be
+bit-identical (TOL = 0), single-step and multi-step. rel_err() is only used to print how far off a failure is.
 """
 import numpy as np
 import pytest
@@ -13,7 +16,7 @@ from scenarios import (M130K, make_boids, make_clouds, make_fluids, pbf_invarian
 
 pytestmark = pytest.mark.gpu
 
-TOL = 1e-5  # relative, fp32, north_star
+TOL = 0.0  # bit-exact; the north_star bar is 1e-5 relative
 
 
 def assert_ids_exact(p, N=None):
@@ -26,8 +29,14 @@ def assert_close(p, fields, tol=TOL, N=None):
     N = p.N if N is None else N
     for f in fields:
         a, b = p.get(f)
-        e = rel_err(b[:N], a[:N])
-        assert e <= tol, "%s rel err %.3g > %.1g" % (f, e, tol)
+        a, b = a[:N], b[:N]
+        if tol == 0.0:
+            same = (a.view(np.uint32) == b.view(np.uint32)) | ((a == b) & np.isfinite(a)) | (np.isnan(a) & np.isnan(b))
+            assert same.all(), "%s not bit-exact: %d of %d elements differ, rel err %.3g" % (
+                f, int((~same).sum()), same.size, rel_err(b, a))
+        else:
+            e = rel_err(b, a)
+            assert e <= tol, "%s rel err %.3g > %.1g" % (f, e, tol)
 
 
 # ---------------------------------------------------------------- sort
@@ -63,7 +72,7 @@ def test_fluids_dam_130k_single_step():
     assert_ids_exact(p)
     assert_close(p, ("POS", "VEL", "PRED_POS"))
     assert_close(p, ("DENSITY", "CONST_FACTOR"))
-    assert_close(p, ("CORR_POS", "VORT"), tol=1e-4)  # cancelling sums of O(1e3) terms; not part of the 1e-5 bar
+    assert_close(p, ("CORR_POS", "VORT"))
 
 
 @pytest.mark.parametrize("jacobi,vort,art", [(1, 1, 1), (2, 0, 1), (6, 1, 0)])
@@ -71,7 +80,7 @@ def test_fluids_variants(jacobi, vort, art):
     p = make_fluids(M=16384, res=(32, 32, 16), jacobi=jacobi, isVorticityConfEnabled=vort, isArtPressureEnabled=art)
     for _ in range(2):
         p.step(O.STEP_PHYSICS)
-    assert_close(p, ("POS", "VEL", "PRED_POS", "DENSITY"), tol=5e-5)
+    assert_close(p, ("POS", "VEL", "PRED_POS", "DENSITY"))
 
 
 def test_fluids_ragged_and_tail():
@@ -107,7 +116,7 @@ def test_fluids_wall_quirks():
     p = make_fluids(M=4096, verts=verts, jacobi=2)
     p.step(O.STEP_PHYSICS)
     assert_ids_exact(p)
-    assert_close(p, ("POS", "VEL"), tol=5e-5)
+    assert_close(p, ("POS", "VEL"))
 
 
 def test_fluids_cap_binds():
@@ -132,8 +141,9 @@ def test_fluids_100_step_invariants():
     (do, dg), (vo, vg) = p.get("DENSITY"), p.get("VEL")
     eo, ko = pbf_invariants(do, vo, p.N)
     eg, kg = pbf_invariants(dg, vg, p.N)
-    assert abs(eg - eo) <= 0.01 * eo, (eg, eo)
+    assert abs(eg - eo) <= 0.01 * eo, (eg, eo)  # north_star bar
     assert abs(kg - ko) <= 0.01 * ko, (kg, ko)
+    assert_close(p, ("POS", "VEL", "DENSITY"))  # and in fact bit-identical after 100 steps
 
 
 def test_step_n_graph_replay_equals_single_steps():
@@ -158,7 +168,7 @@ def test_full_update_with_camera_sort():
         assert np.array_equal(a, b), f
     assert_close(p, ("POS", "VEL", "COL"))
     p.step(flags)
-    assert_close(p, ("POS", "VEL"), tol=5e-5)
+    assert_close(p, ("POS", "VEL"))
 
 
 # ---------------------------------------------------------------- boids
@@ -209,7 +219,7 @@ def test_boids_2d():
 def test_clouds_init_fields():
     p = make_clouds(M=65536, N=65536)
     for f in ("TEMP", "VAPOR_DENS"):
-        assert rel_err(p.init_gpu[f], p.w.download(f)) <= 1e-6, f
+        assert np.array_equal(p.init_gpu[f], p.w.download(f)), (f, rel_err(p.init_gpu[f], p.w.download(f)))
 
 
 def test_clouds_130k_single_step():
@@ -218,7 +228,7 @@ def test_clouds_130k_single_step():
     assert_ids_exact(p)
     assert_close(p, ("POS", "VEL", "PRED_POS", "TOT_CORR_POS"))
     assert_close(p, ("TEMP", "VAPOR_DENS", "CLOUD_DENS", "BUOYANCY", "PART_ID", "DENSITY", "CONST_FACTOR"))
-    assert_close(p, ("LAPLACIAN_TEMP", "CONST_FACTOR_TEMP", "CORR_TEMP", "CLOUD_GEN", "VORT"), tol=1e-4)
+    assert_close(p, ("LAPLACIAN_TEMP", "CONST_FACTOR_TEMP", "CORR_TEMP", "CLOUD_GEN", "VORT"))
 
 
 def test_clouds_periodic_images_and_steps():
@@ -226,7 +236,7 @@ def test_clouds_periodic_images_and_steps():
     p = make_clouds(M=32768, N=32768, region=((-5.0, -10.0, -5.0), (5.0, 10.0, 5.0)), jacobi=2)
     for _ in range(3):
         p.step(O.STEP_PHYSICS | O.STEP_RENDER_AUX | O.STEP_CAMERA_SORT)
-    assert_close(p, ("POS", "VEL", "TEMP", "VAPOR_DENS", "CLOUD_DENS", "COL"), tol=5e-5)
+    assert_close(p, ("POS", "VEL", "TEMP", "VAPOR_DENS", "CLOUD_DENS", "COL"))
 
 
 def test_clouds_no_smoothing_no_vorticity():
