@@ -113,21 +113,28 @@ __global__ void __launch_bounds__(BD_THREADS) boidsRulesKernel(DeviceState s, Gr
       }
   }
 
-  float ax = 0.f, ay = 0.f, az = 0.f;
+  // From here on the w lane is carried like the reference's float4 arithmetic does: it is 0 unless a
+  // fast_normalize() of a zero vector poisons it (0 * inf = NaN), and the oracle reproduces exactly that.
+  float ax = 0.f, ay = 0.f, az = 0.f, aw = 0.f;
   if (count != 0)
   {
     // boids.cl:115-131
     const float fc = (float)count;
+    const float vs = p.rules.velocityScale;
     apx = fsub(fdiv(apx, fc), pi.x); apy = fsub(fdiv(apy, fc), pi.y); apz = fsub(fdiv(apz, fc), pi.z);
     float r = fdiv(1.0f, fsqrt(dot3c(apx, apy, apz, apx, apy, apz)));
-    apx = fmul(fmul(apx, r), p.rules.velocityScale); apy = fmul(fmul(apy, r), p.rules.velocityScale); apz = fmul(fmul(apz, r), p.rules.velocityScale);
+    apx = fmul(fmul(apx, r), vs); apy = fmul(fmul(apy, r), vs); apz = fmul(fmul(apz, r), vs);
+    const float apw = fmul(fmul(0.0f, r), vs);
     r = fdiv(1.0f, fsqrt(dot3c(avx, avy, avz, avx, avy, avz)));
-    avx = fmul(fmul(avx, r), p.rules.velocityScale); avy = fmul(fmul(avy, r), p.rules.velocityScale); avz = fmul(fmul(avz, r), p.rules.velocityScale);
+    avx = fmul(fmul(avx, r), vs); avy = fmul(fmul(avy, r), vs); avz = fmul(fmul(avz, r), vs);
+    const float avw = fmul(fmul(0.0f, r), vs);
     r = fdiv(1.0f, fsqrt(dot3c(rpx, rpy, rpz, rpx, rpy, rpz)));
-    rpx = fmul(fmul(rpx, r), p.rules.velocityScale); rpy = fmul(fmul(rpy, r), p.rules.velocityScale); rpz = fmul(fmul(rpz, r), p.rules.velocityScale);
+    rpx = fmul(fmul(rpx, r), vs); rpy = fmul(fmul(rpy, r), vs); rpz = fmul(fmul(rpz, r), vs);
+    const float rpw = fmul(fmul(0.0f, r), vs);
     ax = fadd(fadd(fmul(avx, p.rules.alignmentScale), fmul(rpx, p.rules.separationScale)), fmul(apx, p.rules.cohesionScale));
     ay = fadd(fadd(fmul(avy, p.rules.alignmentScale), fmul(rpy, p.rules.separationScale)), fmul(apy, p.rules.cohesionScale));
     az = fadd(fadd(fmul(avz, p.rules.alignmentScale), fmul(rpz, p.rules.separationScale)), fmul(apz, p.rules.cohesionScale));
+    aw = fadd(fadd(fmul(avw, p.rules.alignmentScale), fmul(rpw, p.rules.separationScale)), fmul(apw, p.rules.cohesionScale));
   }
 
   // bd_addTargetRule boids.cl:226-241
@@ -142,18 +149,19 @@ __global__ void __launch_bounds__(BD_THREADS) boidsRulesKernel(DeviceState s, Gr
       ax = fadd(ax, fmul(fmul(tx, sgn), k));
       ay = fadd(ay, fmul(fmul(ty, sgn), k));
       az = fadd(az, fmul(fmul(tz, sgn), k));
+      aw = fadd(aw, fmul(fmul(fsub(p.targetPos[3], pi.w), sgn), k));
     }
   }
-  s.acc[i] = make_float4(ax, ay, az, 0.f);
+  s.acc[i] = make_float4(ax, ay, az, aw);
 
   // bd_updateVel boids.cl:246-259
   const float4 vi = s.velB[i];
   const float maxV = p.rules.velocityScale;
-  float nvx = fadd(vi.x, fmul(ax, p.dt)), nvy = fadd(vi.y, fmul(ay, p.dt)), nvz = fadd(vi.z, fmul(az, p.dt));
+  const float nvx = fadd(vi.x, fmul(ax, p.dt)), nvy = fadd(vi.y, fmul(ay, p.dt)), nvz = fadd(vi.z, fmul(az, p.dt)), nvw = fadd(vi.w, fmul(aw, p.dt));
   const float len = fsqrt(dot3c(nvx, nvy, nvz, nvx, nvy, nvz));
   const float norm = fclamp(len, fmul(0.2f, maxV), maxV);
   const float rn = fdiv(1.0f, len);
-  float vx = fmul(fmul(nvx, rn), norm), vy = fmul(fmul(nvy, rn), norm), vz = fmul(fmul(nvz, rn), norm);
+  float vx = fmul(fmul(nvx, rn), norm), vy = fmul(fmul(nvy, rn), norm), vz = fmul(fmul(nvz, rn), norm), vw = fmul(fmul(nvw, rn), norm);
 
   // bd_updatePosAndApplyWallBC boids.cl:264-284 / bd_updatePosAndApplyPeriodicBC :289-315
   const float npx = fadd(pi.x, fmul(vx, p.dt)), npy = fadd(pi.y, fmul(vy, p.dt)), npz = fadd(pi.z, fmul(vz, p.dt));
@@ -166,10 +174,10 @@ __global__ void __launch_bounds__(BD_THREADS) boidsRulesKernel(DeviceState s, Gr
   }
   else if (!(cpx == npx && cpy == npy && cpz == npz))
   {
-    vx = fmul(vx, -0.5f); vy = fmul(vy, -0.5f); vz = fmul(vz, -0.5f);
+    vx = fmul(vx, -0.5f); vy = fmul(vy, -0.5f); vz = fmul(vz, -0.5f); vw = fmul(vw, -0.5f);
   }
-  s.posA[i] = make_float4(cpx, cpy, cpz, 0.f);
-  s.velA[i] = make_float4(vx, vy, vz, 0.f);
+  s.posA[i] = make_float4(cpx, cpy, cpz, 0.f); // w: clamp(w, 0, 0) == 0 even for NaN
+  s.velA[i] = make_float4(vx, vy, vz, vw);
 }
 
 void launchBoidsCellIds(const DeviceState& s, const GridParams& g, u32* keysOut, cudaStream_t st)

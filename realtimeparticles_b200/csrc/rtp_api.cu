@@ -615,6 +615,12 @@ static int enqueueStep(rtp_handle* h, unsigned flags, const float cam[3], bool p
   StepRecorder rec { h, profile };
   rec.mark("begin");
 
+  if ((flags & RTP_STEP_PHYSICS) && !s.N)
+  {
+    // no particle: the step still runs resetStartEndCell over the cells (Fluids.cpp:419)
+    launchBoidsCellIds(s, g, s.keysTmp, st);
+    ++launches;
+  }
   if ((flags & RTP_STEP_PHYSICS) && s.N)
   {
     u32* keysIn = (h->cellPlan.passes % 2 == 0) ? s.cellID : s.keysTmp;
