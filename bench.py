@@ -1,0 +1,348 @@
+#!/usr/bin/env python
+"""Headless benchmark of the hot path (BASELINE.json metric: particle-updates/sec, % of HBM roofline).
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload NAME]
+
+N = 1 (default): PBF 3D dam break, 131072 particles, 3 Jacobi iterations, vorticity confinement + XSPH
+                 (BASELINE.json configs[2], the config its 2000 steps/s target is quoted on).
+A "step" is one pass of the hot path (the physics part of Fluids::update(), Fluids.cpp:400-457) over the whole state.
+
+JSON keys (one line on stdout, rank 0):
+  value      whole-job particle-updates/s, state resident in HBM, CUDA-event timed on the launching stream, L2 flushed
+             between timed steps (the 17 MB state would otherwise live in the 126 MB L2)
+  e2e        same metric through the public API (models.Fluids.update()) with HOST buffers: H2D of p_pos/p_vel from
+             pinned memory and D2H of p_pos inside the timed region, every step
+  roofline   dominant kernel: algorithmic bytes per launch / its event-timed duration vs MEASURED_PEAKS.json hbm_gbs
+  cpu_baseline  the CPU oracle (oracle/, a port of the reference kernels) timed on this box's host cores, bounded sample
+--impl reference times that CPU port alone, all host threads, on the same workload and metric.
+"""
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+N130K = 131072
+FLUID_DEFAULTS = (450.0, 600.0, 0.010, 3, 1, 0.006, 0.001, 4, 1, 0.0004, 0.0001)
+JACOBI = 3
+
+# algorithmic bytes per particle per launch; t = cell-table bytes per particle per pass
+def algorithmic_bytes(ncells, n):
+    t = 8.0 * ncells / n
+    return {
+        "predictPosition+fillCellIDs": 48 + 20,
+        "radixSort(onesweep)": 4 + 16 * 2,
+        "gather+cellTable": 100 + 4 + t,
+        "adjustEndCell": t,
+        "densityLambda": (20 + t) + (24 + t),  # fld_computeDensity + fld_computeConstraintFactor, fused
+        "correction": (36 + t) + 48 + 32,  # constraintCorrection + correctPosition + boundary (fused)
+        "vorticity": 48 + t,
+        "confinement": 64 + t,
+        "xsph": 32 + (48 + t) + 32,  # copy + xsph + updatePosition (fused)
+    }
+
+
+PBF_BYTES_PER_PARTICLE_STEP = 486.6 + 164.9 * JACOBI  # 981 B at I=3, P=2
+
+
+def measured_peak():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler(threading.Thread):
+    """Samples SM clock and throttle reasons during the timed region (NVML, ~5 ms period)."""
+
+    def __init__(self, index=0):
+        super().__init__(daemon=True)
+        self.samples, self.reasons, self.stop_flag, self.max_mhz, self.ok = [], set(), False, None, False
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.dev = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.dev, pynvml.NVML_CLOCK_SM)
+            self.ok = True
+        except Exception:
+            self.ok = False
+
+    def run(self):
+        if not self.ok:
+            return
+        nv = self.nv
+        names = {"hw_slowdown": 0x8, "sw_power_cap": 0x4, "hw_thermal_slowdown": 0x40, "sw_thermal_slowdown": 0x20,
+                 "hw_power_brake": 0x80, "sync_boost": 0x10, "applications_clocks": 0x2}
+        while not self.stop_flag:
+            try:
+                self.samples.append(nv.nvmlDeviceGetClockInfo(self.dev, nv.NVML_CLOCK_SM))
+                r = nv.nvmlDeviceGetCurrentClocksEventReasons(self.dev)
+                for k, bit in names.items():
+                    if r & bit:
+                        self.reasons.add(k)
+            except Exception:
+                pass
+            time.sleep(0.005)
+
+    def result(self):
+        if not self.ok or not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": self.max_mhz, "reasons": ["unavailable"]}
+        s = sorted(self.samples)
+        return {"sm_mhz": s[len(s) // 2], "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons), "samples": len(s)}
+
+
+def dist_env():
+    return int(os.environ.get("RANK", 0)), int(os.environ.get("LOCAL_RANK", 0)), int(os.environ.get("WORLD_SIZE", 1))
+
+
+# ------------------------------------------------------------------------------------------------ reference arm
+
+def run_reference(args):
+    """The reference's CPU implementation of the path: the OpenCL kernels cannot be built here (no OpenCL ICD/headers), so
+    this is the oracle port of them, all host threads, bounded to ~150 s."""
+    rank, _, world = dist_env()
+    if rank != 0:
+        return
+    import numpy as np
+    from oracle import oracle_py as O
+    pos = O.gen_box_grid((64, 64, 32), (-5.0, -5.0, -5.0), (5.0, 0.0, 0.0))
+    w = O.World(O.FLUIDS, N130K, N130K)
+    w.set_fluid_params(O.default_fluid_params(), JACOBI)
+    w.upload("POS", pos)
+    w.upload("VEL", np.zeros((N130K, 4), np.float32))
+    w.reset_ids()
+    cores = O.max_threads()
+    budget = 150.0
+    for _ in range(min(args.warmup, 2)):
+        w.step(O.STEP_PHYSICS)
+    done, t0 = 0, time.perf_counter()
+    while done < args.steps and (time.perf_counter() - t0) < budget:
+        w.step(O.STEP_PHYSICS)
+        done += 1
+    dt = time.perf_counter() - t0
+    value = N130K * done / dt
+    sample = "%d of %d requested steps of the full 131072-particle PBF step (time-bounded to %ds)" % (done, args.steps, int(budget))
+    out = {
+        "impl": "reference", "metric": "particle-updates/sec", "value": value, "unit": "particle-updates/s",
+        "n_gpus": args.gpus, "steps": done, "warmup": min(args.warmup, 2), "ms_per_step": 1e3 * dt / max(done, 1),
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "pbf_dam_130k_I3_vorticity_xsph", "particles": N130K, "jacobi_iterations": JACOBI,
+                   "grid": [30, 30, 30], "box": [10, 10, 10]},
+        "cpu_baseline": {"value": value, "unit": "particle-updates/s", "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": "particle-updates/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(out), flush=True)
+
+
+# ------------------------------------------------------------------------------------------------ our arm
+
+def make_pbf(abi, device):
+    import numpy as np
+    pos = abi.gen_box_grid((64, 64, 32), (-5.0, -5.0, -5.0), (5.0, 0.0, 0.0))
+    h = abi.Handle(abi.FLUIDS, N130K, N130K, (10, 10, 10), (30, 30, 30), 3, 0, device)
+    h.set_fluid_params(abi.FluidParams(*FLUID_DEFAULTS), JACOBI)
+    h.upload("p_pos", pos)
+    h.upload("p_vel", np.zeros((N130K, 4), np.float32))
+    h.reset_ids()
+    return h, pos
+
+
+def run_ours(args):
+    import numpy as np
+    import torch
+    from realtimeparticles_b200 import _abi as abi, models
+
+    rank, local_rank, world = dist_env()
+    if not torch.cuda.is_available() or abi.lib().rtp_device_count() == 0:
+        raise SystemExit("bench.py: no CUDA device -- the CUDA backend has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    dev = torch.device("cuda", local_rank)
+
+    h, pos0 = make_pbf(abi, local_rank)
+    stream = torch.cuda.ExternalStream(h.stream(), device=dev)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)  # > 126 MB L2
+    K, W = args.steps, max(args.warmup, 3)
+    flags = abi.STEP_PHYSICS
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- warm-up (also builds the CUDA graph of one step)
+    with torch.cuda.stream(stream):
+        for _ in range(W):
+            h.step_n(1, flags)
+    h.sync()
+    launches_per_step = h.last_launch_count()
+
+    # ---- timed region: K steps, L2 flushed before each, per-step events on the launching stream
+    sampler = ClockSampler(local_rank)
+    starts = [torch.cuda.Event(enable_timing=True) for _ in range(K)]
+    stops = [torch.cuda.Event(enable_timing=True) for _ in range(K)]
+    barrier()
+    sampler.start()
+    t_wall0 = time.perf_counter()
+    with torch.cuda.stream(stream):
+        for i in range(K):
+            flush.zero_()
+            starts[i].record(stream)
+            h.step_n(1, flags)
+            stops[i].record(stream)
+    h.sync()
+    barrier()
+    t_wall = time.perf_counter() - t_wall0
+    sampler.stop_flag = True
+    sampler.join()
+    ms = sum(s.elapsed_time(e) for s, e in zip(starts, stops))
+    t = torch.tensor([ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_total = float(t.item())
+    value = world * N130K * K / (ms_total * 1e-3)
+
+    # ---- same K steps back to back without the flush (state L2-resident: the regime the app runs in)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    with torch.cuda.stream(stream):
+        e0.record(stream)
+        h.step_n(K, flags)
+        e1.record(stream)
+    h.sync()
+    warm_ms = e0.elapsed_time(e1)
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    # ---- per-kernel durations (events between launches, L2 flushed before each step)
+    h.enable_profiling(True)
+    acc, cnt, reps = {}, {}, 20
+    for _ in range(reps):
+        with torch.cuda.stream(stream):
+            flush.zero_()
+        h.step(flags)
+        for name, v in h.stage_times():
+            acc[name] = acc.get(name, 0.0) + v
+            cnt[name] = cnt.get(name, 0) + 1
+    h.enable_profiling(False)
+    abytes = algorithmic_bytes(27000, N130K)
+    peak, peak_src = measured_peak()
+    kernels = {}
+    step_ms = sum(acc.values()) / reps
+    for name in acc:
+        per_launch_ms = acc[name] / cnt[name]
+        b = abytes.get(name)
+        gbs = (b * N130K / (per_launch_ms * 1e-3) / 1e9) if b else None
+        kernels[name] = {"ms_per_launch": round(per_launch_ms, 5), "launches_per_step": cnt[name] // reps,
+                         "share": round(acc[name] / reps / step_ms, 4),
+                         "algorithmic_GBps": None if gbs is None else round(gbs, 1),
+                         "frac_of_hbm": None if gbs is None else round(gbs / peak, 4)}
+    dom = max((k for k in kernels if abytes.get(k)), key=lambda k: kernels[k]["share"])
+    roofline = {"bound": "hbm", "kernel": dom, "achieved": kernels[dom]["algorithmic_GBps"], "peak": peak, "unit": "GB/s",
+                "frac": kernels[dom]["frac_of_hbm"], "traffic": None, "peak_source": peak_src,
+                "algorithmic_bytes_per_launch": abytes[dom] * N130K,
+                "whole_step": {"algorithmic_bytes_per_particle": PBF_BYTES_PER_PARTICLE_STEP,
+                               "achieved": round(value / world * PBF_BYTES_PER_PARTICLE_STEP / 1e9, 1),
+                               "frac": round(value / world * PBF_BYTES_PER_PARTICLE_STEP / 1e9 / peak, 4)},
+                "note": "neighbour sweeps do ~460 pair evaluations per particle on 16-64 B of compulsory traffic: FP32-issue "
+                        "bound, far below the HBM line by construction (SURVEY 8d); traffic = ncu dram bytes, see profiles/"}
+    try:
+        with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
+            roofline["traffic"] = json.load(f).get(dom)
+    except Exception:
+        pass
+
+    # ---- e2e through the public API with host buffers
+    params = models.ModelParams(currNbParticles=N130K, maxNbParticles=N130K, boxSize=(10, 10, 10), gridRes=(30, 30, 30),
+                                pCase=models.PhysicsCase.FLUIDS_DAM, device=local_rank)
+    m = models.CreateModel(models.ModelType.FLUIDS, params)
+    js = m.getInputJson()
+    js["Fluids"]["Nb Jacobi Iterations"][0] = JACOBI
+    m.updateInputJson(js)
+    m.setStepFlags(abi.STEP_PHYSICS)
+    hpos = torch.from_numpy(pos0.copy()).pin_memory()
+    hvel = torch.zeros((N130K, 4), dtype=torch.float32).pin_memory()
+    hout = torch.empty((N130K, 4), dtype=torch.float32).pin_memory()
+    ke = max(20, min(K, 500))
+
+    def e2e_step():
+        m.upload("p_pos", hpos.numpy())
+        m.upload("p_vel", hvel.numpy())
+        m.update()
+        m._h.download("p_pos", out=hout.numpy())
+    for _ in range(3):
+        e2e_step()
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for _ in range(ke):
+        e2e_step()
+    torch.cuda.synchronize()
+    e2e_dt = time.perf_counter() - t0
+    e2e = {"value": N130K * ke / e2e_dt, "unit": "particle-updates/s", "h2d_bytes_per_step": 2 * N130K * 16,
+           "d2h_bytes_per_step": N130K * 16, "steps": ke, "ms_per_step": round(1e3 * e2e_dt / ke, 4),
+           "api": "realtimeparticles_b200.models.Fluids: upload(p_pos,p_vel) + update() + download(p_pos), pinned host buffers"}
+
+    # ---- CPU baseline: the oracle port on this box's host cores, bounded sample
+    cpu = None
+    if not args.no_cpu_baseline:
+        from oracle import oracle_py as O
+        w = O.World(O.FLUIDS, N130K, N130K)
+        w.set_fluid_params(O.default_fluid_params(), JACOBI)
+        w.upload("POS", pos0)
+        w.upload("VEL", np.zeros((N130K, 4), np.float32))
+        w.reset_ids()
+        w.step(O.STEP_PHYSICS)
+        n, t0 = 0, time.perf_counter()
+        while n < 12 and time.perf_counter() - t0 < 20.0:
+            w.step(O.STEP_PHYSICS)
+            n += 1
+        dt = time.perf_counter() - t0
+        cpu = {"value": N130K * n / dt, "unit": "particle-updates/s", "cores": O.max_threads(), "kind": "port",
+               "sample": "%d full steps of the same 131072-particle PBF workload after 1 warm-up (%.1f s)" % (n, dt)}
+
+    out = {
+        "metric": "particle-updates/sec", "value": value, "unit": "particle-updates/s", "n_gpus": world, "steps": K, "warmup": W,
+        "ms_per_step": ms_total / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+        "data": "synthetic",
+        "config": {"workload": "pbf_dam_130k_I3_vorticity_xsph", "particles": N130K, "jacobi_iterations": JACOBI,
+                   "grid": [30, 30, 30], "box": [10, 10, 10], "l2": "flushed before every timed step (256 MiB memset, untimed)",
+                   "parallelism": "replicas" if world > 1 else "single"},
+        "steps_per_s": K / (ms_total * 1e-3),
+        "l2_resident": {"value": N130K * K / (warm_ms * 1e-3), "steps_per_s": K / (warm_ms * 1e-3),
+                        "note": "same K steps replayed back to back from one CUDA graph, no flush"},
+        "e2e": e2e, "gpu_launches": launches_per_step * K, "launches_per_step": launches_per_step,
+        "roofline": roofline, "kernels": kernels, "cpu_baseline": cpu, "clocks": sampler.result(),
+        "wall_s_timed_region": round(t_wall, 3),
+    }
+    print(json.dumps(out), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=2000)
+    ap.add_argument("--warmup", type=int, default=50)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

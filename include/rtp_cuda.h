@@ -202,6 +202,8 @@ RTP_API int rtp_step(rtp_handle* h, unsigned flags, const float camera_pos[3]);
 /* n back-to-back steps replayed from one CUDA graph (bench / headless runs); same result as n rtp_step calls */
 RTP_API int rtp_step_n(rtp_handle* h, unsigned flags, const float camera_pos[3], int n);
 RTP_API int rtp_sync(rtp_handle* h);
+/* the handle's cudaStream_t, so callers can time with events on the launching stream or order their own work */
+RTP_API int rtp_get_stream(rtp_handle* h, void** stream);
 
 /* ---- stand-alone access to the neighbour-search primitives (parity tests, other callers) ---- */
 /* stable ascending sort of n 32-bit keys (device pointers); perm_out[i] = index of the i-th smallest key.
@@ -216,7 +218,7 @@ RTP_API int rtp_sort_keys_host(rtp_handle* h, const uint32_t* keys_in, uint32_t*
 RTP_API int rtp_enable_profiling(rtp_handle* h, int enable);
 /* fills up to cap entries with the stage names / milliseconds of the last profiled step; returns the count */
 RTP_API int rtp_get_stage_times(rtp_handle* h, const char** names, float* ms, int cap);
-/* number of kernel launches issued by the last rtp_step / per step of rtp_step_n */
+/* number of kernel launches (memset/memcpy nodes excluded) issued by the last rtp_step / per step of rtp_step_n */
 RTP_API int rtp_last_launch_count(const rtp_handle* h);
 
 /* ---- initial-condition generators (host side; semantics of utils/Geometry.cpp:198-272) ---- */

@@ -79,7 +79,7 @@ EXPORTS = ["rtp_abi_version", "rtp_device_count", "rtp_create", "rtp_destroy", "
            "rtp_upload", "rtp_download", "rtp_device_ptr", "rtp_set_boids_params", "rtp_set_fluid_params",
            "rtp_set_cloud_params", "rtp_set_boundary", "rtp_set_nb_particles", "rtp_set_dimension",
            "rtp_set_displayed_quantity", "rtp_reset_ids", "rtp_init_clouds_fields", "rtp_step", "rtp_step_n",
-           "rtp_sync", "rtp_sort_keys", "rtp_sort_keys_host", "rtp_enable_profiling", "rtp_get_stage_times",
+           "rtp_sync", "rtp_get_stream", "rtp_sort_keys", "rtp_sort_keys_host", "rtp_enable_profiling", "rtp_get_stage_times",
            "rtp_last_launch_count", "rtp_gen_box_grid", "rtp_gen_sphere_grid", "rtp_gen_random_box",
            "rtp_baked_constant"]
 
@@ -120,6 +120,7 @@ def lib():
     L.rtp_step.argtypes = [vp, C.c_uint, fp]
     L.rtp_step_n.argtypes = [vp, C.c_uint, fp, C.c_int]
     L.rtp_sync.argtypes = [vp]
+    L.rtp_get_stream.argtypes = [vp, C.POINTER(vp)]
     L.rtp_sort_keys.argtypes = [vp, vp, vp, vp, C.c_uint64, C.c_int]
     L.rtp_sort_keys_host.argtypes = [vp, vp, vp, vp, C.c_uint64, C.c_int]
     L.rtp_enable_profiling.argtypes = [vp, C.c_int]
@@ -254,6 +255,12 @@ class Handle:
 
     def sync(self):
         self._check(self.L.rtp_sync(self.h), "rtp_sync")
+
+    def stream(self):
+        """cudaStream_t of the handle as an int (wrap with torch.cuda.ExternalStream to record events on it)"""
+        p = C.c_void_p()
+        self._check(self.L.rtp_get_stream(self.h, C.byref(p)), "rtp_get_stream")
+        return p.value or 0
 
     def sort_keys_host(self, keys, key_bits=32):
         keys = np.ascontiguousarray(keys, dtype=np.uint32)

@@ -576,19 +576,17 @@ static int enqueueCameraSort(rtp_handle* h, const float cam[3])
   launchCameraGather(s, model, h->predFinal, predScratch, st);
   ++launches;
   const size_t n4 = (size_t)s.N * sizeof(float4), n1 = (size_t)s.N * sizeof(float);
+  // copy nodes are not counted as kernel launches
   cudaMemcpyAsync(s.posA, s.posB, n4, cudaMemcpyDeviceToDevice, st);
   cudaMemcpyAsync(s.col, s.colB, n4, cudaMemcpyDeviceToDevice, st);
   cudaMemcpyAsync(s.velA, s.velB, n4, cudaMemcpyDeviceToDevice, st);
-  launches += 3;
   if (model == RTP_MODEL_BOIDS)
   {
     cudaMemcpyAsync(s.acc, s.velC, n4, cudaMemcpyDeviceToDevice, st);
-    ++launches;
   }
   else
   {
     cudaMemcpyAsync(h->predFinal, predScratch, n4, cudaMemcpyDeviceToDevice, st);
-    ++launches;
     if (model == RTP_MODEL_CLOUDS)
     {
       cudaMemcpyAsync(s.tempA, s.tempB, n1, cudaMemcpyDeviceToDevice, st);
@@ -596,7 +594,6 @@ static int enqueueCameraSort(rtp_handle* h, const float cam[3])
       cudaMemcpyAsync(s.vaporA, s.vaporB, n1, cudaMemcpyDeviceToDevice, st);
       cudaMemcpyAsync(s.cloudA, s.cloudB, n1, cudaMemcpyDeviceToDevice, st);
       cudaMemcpyAsync(s.partIdA, s.partIdB, n1, cudaMemcpyDeviceToDevice, st);
-      launches += 5;
     }
   }
   return launches;
@@ -632,9 +629,10 @@ static int enqueueStep(rtp_handle* h, unsigned flags, const float cam[3], bool p
       launches += enqueueSort(h->cellPlan, s.cellID, s.perm, s.keysTmp, s.permTmp, s.sortCtrl, s.sortStatus, st);
       rec.mark("radixSort(onesweep)");
       launchBoidsGather(s, g, st);
+      rec.mark("gather+cellTable");
       launchAdjustEndCell(s, g, st);
       launches += 2;
-      rec.mark("permutate+cellTable");
+      rec.mark("adjustEndCell");
       launchBoidsRules(s, g, c, h->bp, st);
       ++launches;
       rec.mark("boidsRules+updateVel+updatePos");
@@ -654,16 +652,19 @@ static int enqueueStep(rtp_handle* h, unsigned flags, const float cam[3], bool p
         launchCloudsGather(s, g, st);
       else
         launchFluidGather(s, g, st);
+      rec.mark("gather+cellTable");
       launchAdjustEndCell(s, g, st);
       launches += 2;
-      rec.mark("permutate+cellTable");
+      rec.mark("adjustEndCell");
       if (clouds && h->cp.isTempSmoothingEnabled)
       {
         launchCloudsLaplacianTemp(s, g, c, h->cp, st);
+        rec.mark("laplacianTemp");
         launchCloudsLambdaTemp(s, g, c, h->cp, st);
+        rec.mark("lambdaTemp");
         launchCloudsCorrectTemp(s, g, c, h->cp, st);
+        rec.mark("correctTemp");
         launches += 3;
-        rec.mark("temperatureConstraint(3 sweeps)");
       }
       float4* cur = s.pred1;
       float4* nxt = s.pred0;
@@ -671,21 +672,24 @@ static int enqueueStep(rtp_handle* h, unsigned flags, const float cam[3], bool p
       {
         const bool last = it == h->jacobi - 1;
         launchDensityLambda(s, model, g, c, h->fp, cur, st);
+        rec.mark("densityLambda");
         launchCorrection(s, model, g, c, h->fp, h->cp, cur, nxt, last, debug, st);
+        rec.mark("correction");
         launches += 2;
         float4* t = cur;
         cur = nxt;
         nxt = t;
       }
-      rec.mark("jacobi(density+lambda, correction)");
       h->predFinal = cur;
       if (h->fp.f.isVorticityConfEnabled)
       {
         launchVorticity(s, model, g, c, cur, st);
+        rec.mark("vorticity");
         launchConfinement(s, model, g, c, h->fp, cur, st);
+        rec.mark("confinement");
         launchXsph(s, model, g, c, h->fp, h->cp, cur, st);
+        rec.mark("xsph");
         launches += 3;
-        rec.mark("vorticity+confinement+xsph");
       }
       if (clouds)
       {
@@ -777,6 +781,14 @@ extern "C" int rtp_step_n(rtp_handle* h, unsigned flags, const float camera_pos[
   }
   for (int i = 0; i < n; ++i)
     CUDA_TRY(h, cudaGraphLaunch(h->graphExec, h->stream));
+  return RTP_OK;
+}
+
+extern "C" int rtp_get_stream(rtp_handle* h, void** stream)
+{
+  if (!h || !stream)
+    return RTP_ERR_INVALID;
+  *stream = (void*)h->stream;
   return RTP_OK;
 }
 

@@ -218,8 +218,7 @@ int enqueueSort(const SortPlan& plan, u32* keys0, u32* vals0, u32* keys1, u32* v
   if (plan.n == 0)
     return 0;
   int launches = 0;
-  cudaMemsetAsync(ctrl, 0, SORT_CTRL_WORDS * sizeof(u32), stream);
-  ++launches;
+  cudaMemsetAsync(ctrl, 0, SORT_CTRL_WORDS * sizeof(u32), stream); // memset node, not counted as a kernel
   PassDesc desc;
   for (int i = 0; i < SORT_MAX_PASSES; ++i)
   {

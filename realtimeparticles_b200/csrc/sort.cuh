@@ -46,7 +46,7 @@ size_t sortStatusWords(const SortPlan& plan); // passes * tiles * 256
 
 // Enqueue the whole sort. keys0/vals0 and keys1/vals1 are ping-pong buffers of n entries; the input keys are in
 // (passes even ? keys0 : keys1) so that the sorted keys and the permutation always END in keys0 / vals0.
-// Returns the number of kernel launches (+ memset nodes) enqueued.
+// Returns the number of kernel launches enqueued (the control-block memset node is not counted).
 int enqueueSort(const SortPlan& plan, u32* keys0, u32* vals0, u32* keys1, u32* vals1, u32* ctrl, u32* status,
     cudaStream_t stream);
 
