@@ -214,6 +214,10 @@ RTP_API int rtp_sort_keys(rtp_handle* h, const uint32_t* d_keys_in, uint32_t* d_
 RTP_API int rtp_sort_keys_host(rtp_handle* h, const uint32_t* keys_in, uint32_t* keys_out, uint32_t* perm_out,
     uint64_t n, int key_bits);
 
+/* device self-test: the kernels' range-check-free exact sqrt / reciprocal vs the IEEE intrinsics over every float in
+ * [lo, hi] (lo > 0); returns the number of bit mismatches of each */
+RTP_API int rtp_selftest_math(rtp_handle* h, float lo, float hi, uint64_t* sqrt_mismatches, uint64_t* rcp_mismatches);
+
 /* ---- profiling (replaces Context::enableProfiler + per-kernel event logging, Context.cpp:692-705) ---- */
 RTP_API int rtp_enable_profiling(rtp_handle* h, int enable);
 /* fills up to cap entries with the stage names / milliseconds of the last profiled step; returns the count */

@@ -79,7 +79,7 @@ EXPORTS = ["rtp_abi_version", "rtp_device_count", "rtp_create", "rtp_destroy", "
            "rtp_upload", "rtp_download", "rtp_device_ptr", "rtp_set_boids_params", "rtp_set_fluid_params",
            "rtp_set_cloud_params", "rtp_set_boundary", "rtp_set_nb_particles", "rtp_set_dimension",
            "rtp_set_displayed_quantity", "rtp_reset_ids", "rtp_init_clouds_fields", "rtp_step", "rtp_step_n",
-           "rtp_sync", "rtp_get_stream", "rtp_sort_keys", "rtp_sort_keys_host", "rtp_enable_profiling", "rtp_get_stage_times",
+           "rtp_sync", "rtp_get_stream", "rtp_sort_keys", "rtp_sort_keys_host", "rtp_selftest_math", "rtp_enable_profiling", "rtp_get_stage_times",
            "rtp_last_launch_count", "rtp_gen_box_grid", "rtp_gen_sphere_grid", "rtp_gen_random_box",
            "rtp_baked_constant"]
 
@@ -123,6 +123,7 @@ def lib():
     L.rtp_get_stream.argtypes = [vp, C.POINTER(vp)]
     L.rtp_sort_keys.argtypes = [vp, vp, vp, vp, C.c_uint64, C.c_int]
     L.rtp_sort_keys_host.argtypes = [vp, vp, vp, vp, C.c_uint64, C.c_int]
+    L.rtp_selftest_math.argtypes = [vp, C.c_float, C.c_float, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]
     L.rtp_enable_profiling.argtypes = [vp, C.c_int]
     L.rtp_get_stage_times.argtypes = [vp, C.POINTER(C.c_char_p), fp, C.c_int]
     L.rtp_last_launch_count.argtypes = [vp]
@@ -268,6 +269,11 @@ class Handle:
         self._check(self.L.rtp_sort_keys_host(self.h, keys.ctypes.data, out.ctypes.data, perm.ctypes.data, keys.size,
                                               key_bits), "rtp_sort_keys_host")
         return out, perm
+
+    def selftest_math(self, lo, hi):
+        a, b = C.c_uint64(), C.c_uint64()
+        self._check(self.L.rtp_selftest_math(self.h, lo, hi, C.byref(a), C.byref(b)), "rtp_selftest_math")
+        return a.value, b.value
 
     def enable_profiling(self, on):
         self._check(self.L.rtp_enable_profiling(self.h, int(on)), "rtp_enable_profiling")

@@ -77,26 +77,26 @@ __global__ void __launch_bounds__(BD_THREADS) boidsRulesKernel(DeviceState s, Gr
 
   auto visit = [&](u32 start, u32 end, float, float)
   {
-    for (u32 e = start; e <= end; ++e)
-    {
-      const float4 pj = ld4(P, e);
-      const float dx = pi.x - pj.x, dy = pi.y - pj.y, dz = pi.z - pj.z;
-      const float sq = dot3c(dx, dy, dz, dx, dy, dz);
-      if (sq < c.effectRadiusSq && sq > RTP_FLOAT_EPS)
-      {
-        const float4 nv = ld4(NV, e);
-        apx += pj.x; apy += pj.y; apz += pj.z;
-        avx += nv.x; avy += nv.y; avz += nv.z;
-        const float r = frcp(sq); // vec / squaredDist == vec * (1 / squaredDist), one fused op per component
-        rpx = ffma(dx, r, rpx); rpy = ffma(dy, r, rpy); rpz = ffma(dz, r, rpz);
-        ++count;
-      }
-    }
+    forRangeLoad4(P, start, end,
+        [&](u32 e, const float4 pj)
+        {
+          const float dx = pi.x - pj.x, dy = pi.y - pj.y, dz = pi.z - pj.z;
+          const float sq = dot3c(dx, dy, dz, dx, dy, dz);
+          if (sq < c.effectRadiusSq && sq > RTP_FLOAT_EPS)
+          {
+            const float4 nv = ld4(NV, e);
+            apx = fadd(apx, pj.x); apy = fadd(apy, pj.y); apz = fadd(apz, pj.z);
+            avx = fadd(avx, nv.x); avy = fadd(avy, nv.y); avz = fadd(avz, nv.z);
+            const float r = frcp(sq); // vec / squaredDist == vec * (1 / squaredDist), one fused op per component
+            rpx = ffma(dx, r, rpx); rpy = ffma(dy, r, rpy); rpz = ffma(dz, r, rpz);
+            ++count;
+          }
+        });
   };
 
   if (!DIM2)
   {
-    forEachNeighbourCell<TRAV_BOIDS>(g, s.table, ci, visit);
+    forEachNeighbourRun<TRAV_BOIDS>(g, s.table, ci, visit);
   }
   else
   {
@@ -109,7 +109,8 @@ __global__ void __launch_bounds__(BD_THREADS) boidsRulesKernel(DeviceState s, Gr
         if (cx < 0 || cy < 0 || cz < 0 || cx >= RX || cy >= RX || cz >= RX)
           continue;
         const uint2 se = __ldg(&s.table[(RX / 2 * RX + cy) * RY + cz]);
-        visit(se.x, se.y, 0.f, 0.f);
+        if (se.x <= se.y)
+          visit(se.x, se.y, 0.f, 0.f);
       }
   }
 

@@ -21,6 +21,7 @@
 // canonical operation sequence (rtp_common.cuh, DESIGN.md "Canonical arithmetic"); sums run in the reference's
 // order (27 cells, ascending e, one fp32 accumulator per component).
 #include "kernels.cuh"
+#include "sweep.cuh"
 
 namespace rtp
 {
@@ -60,45 +61,6 @@ __device__ __forceinline__ float4 cloudBoundary(const GridParams& g, float4 np)
   return p;
 }
 
-// Visit every candidate j of particle i in the reference's order and call pairF for those inside the support.
-template <int TRAV, typename PairF>
-__device__ __forceinline__ void sweepNeighbours(const GridParams& g, const SphConsts& c, const uint2* __restrict__ table,
-    const float4* __restrict__ P, const float4 pi, PairF&& pairF)
-{
-  const int3 ci = cell3D(g, pi.x, pi.y, pi.z);
-  forEachNeighbourCell<TRAV>(g, table, ci,
-      [&](u32 start, u32 end, float sx, float sz)
-      {
-        for (u32 e = start; e <= end; ++e)
-        {
-          const float4 pj = ld4(P, e);
-          float dx = pi.x - pj.x, dy = pi.y - pj.y, dz = pi.z - pj.z;
-          if (TRAV == TRAV_CLOUDS)
-          {
-            dx = dx - sx; // pos - predPos[e] - absWall * signAbsWall, clouds.cl:356
-            dz = dz - sz;
-          }
-          const float sq = dot3c(dx, dy, dz, dx, dy, dz);
-          if (sq < c.supportSq)
-            pairF(e, dx, dy, dz, sq);
-        }
-      });
-}
-
-// gradSpiky(vec) = vec * spikyCoef(sq) for FLOAT_EPS < len < h (sph.cl:26-34): ((K * (h-len)^2) * (1/len)), K = -3 SPIKY_COEFF
-__device__ __forceinline__ float spikyCoef(const SphConsts& c, float sq)
-{
-  const float len = fsqrt(sq);
-  const float hl = fsub(c.h, len);
-  return fmul(fmul(c.spikyK, fmul(hl, hl)), frcp(len));
-}
-// poly6(vec) / POLY6_COEFF = (h^2 - sq)^3 inside the support (sph.cl:10-14)
-__device__ __forceinline__ float poly6nc(const SphConsts& c, float sq)
-{
-  const float t = fsub(c.h2, sq);
-  return fmul(fmul(t, t), t);
-}
-
 // ------------------------------------------------------------------ element-wise kernels
 
 __global__ void __launch_bounds__(EW_THREADS) fluidPredictKernel(DeviceState s, GridParams g, float dt, u32* __restrict__ keys)
@@ -106,6 +68,8 @@ __global__ void __launch_bounds__(EW_THREADS) fluidPredictKernel(DeviceState s, 
   const u32 i = blockIdx.x * EW_THREADS + threadIdx.x;
   if (i < g.numCells)
     s.table[i] = make_uint2(1u, 0u);
+  if (i < NBR_EPOCHS && s.nbrInvalid)
+    s.nbrInvalid[i] = 0u;
   if (i >= s.N)
     return;
   const float4 p = s.posA[i], v = s.velA[i];
@@ -199,6 +163,8 @@ __global__ void __launch_bounds__(EW_THREADS) cloudsThermoPredictKernel(DeviceSt
   const u32 i = blockIdx.x * EW_THREADS + threadIdx.x;
   if (i < g.numCells)
     s.table[i] = make_uint2(1u, 0u);
+  if (i < NBR_EPOCHS && s.nbrInvalid)
+    s.nbrInvalid[i] = 0u;
   if (i >= s.N)
     return;
   const float4 p = s.posA[i], v = s.velA[i];
@@ -272,29 +238,27 @@ __global__ void __launch_bounds__(EW_THREADS) cloudsFinishKernel(DeviceState s, 
   s.totCorrA[i] = s.totCorrB[i];
 }
 
-// ------------------------------------------------------------------ neighbour kernels
+// ------------------------------------------------------------------ neighbour kernels (engine: sweep.cuh)
 
 template <int TRAV>
 __global__ void __launch_bounds__(NB_THREADS) densityLambdaKernel(DeviceState s, GridParams g, SphConsts c, float rho0, float cfm,
-    const float4* __restrict__ pred)
+    const float4* __restrict__ pred, int nbrMode, int epoch)
 {
   const u32 i = blockIdx.x * NB_THREADS + threadIdx.x;
   if (i >= s.N)
     return;
   const float4 pi = pred[i];
   float density = 0.f, gx = 0.f, gy = 0.f, gz = 0.f, sumG2 = 0.f;
-  sweepNeighbours<TRAV>(g, c, s.table, pred, pi,
-      [&](u32, float dx, float dy, float dz, float sq)
+  sweepProducer<TRAV>(g, c, s, pred, pi, i, nbrMode, epoch,
+      [&](u32, float dx, float dy, float dz, float sq) -> float
       {
         density = fadd(density, fmul(c.poly6, poly6nc(c, sq)));
-        if (sq > c.epsSq)
-        {
-          const float cs = spikyCoef(c, sq);
-          gx = ffma(dx, cs, gx);
-          gy = ffma(dy, cs, gy);
-          gz = ffma(dz, cs, gz);
-          sumG2 = fadd(sumG2, fmul(fmul(cs, cs), sq));
-        }
+        const float cs = spikyCoefOrZero(c, sq);
+        gx = ffma(dx, cs, gx);
+        gy = ffma(dy, cs, gy);
+        gz = ffma(dz, cs, gz);
+        sumG2 = fadd(sumG2, fmul(fmul(cs, cs), sq));
+        return cs;
       });
   s.density[i] = density;
   // fluids.cl:189-192
@@ -306,7 +270,7 @@ __global__ void __launch_bounds__(NB_THREADS) densityLambdaKernel(DeviceState s,
 
 template <int TRAV, bool LAST>
 __global__ void __launch_bounds__(NB_THREADS) correctionKernel(DeviceState s, GridParams g, SphConsts c, FluidStepParams fp,
-    const float4* __restrict__ pred, float4* __restrict__ predOut, int writeCorr)
+    const float4* __restrict__ pred, float4* __restrict__ predOut, int writeCorr, int nbrMode, int epoch)
 {
   const u32 i = blockIdx.x * NB_THREADS + threadIdx.x;
   if (i >= s.N)
@@ -318,26 +282,25 @@ __global__ void __launch_bounds__(NB_THREADS) correctionKernel(DeviceState s, Gr
   const u32 artExp = fp.f.artPressureExp;
   const float artCoeff = fp.f.artPressureCoeff, invDen = fp.invArtDenom;
   float cx = 0.f, cy = 0.f, cz = 0.f;
-  sweepNeighbours<TRAV>(g, c, s.table, pred, pi,
-      [&](u32 e, float dx, float dy, float dz, float sq)
+  sweepConsumer<TRAV>(g, c, s, pred, pi, i, nbrMode, epoch,
+      [&](u32 e, float dx, float dy, float dz, float sq, float cs)
       {
-        if (sq > c.epsSq)
+        float sc = fadd(li, __ldg(lambda + e));
+        if (art)
         {
-          float sc = fadd(li, __ldg(lambda + e));
-          if (art)
-          {
-            // artPressure fluids.cl:51-57: -k * (W(vec) / W(dq h))^n ; POLY6_COEFF cancels in the ratio
-            const float ratio = fmul(poly6nc(c, sq), invDen);
-            float pw = ratio;
-            for (u32 q = 1; q < artExp; ++q)
+          // artPressure fluids.cl:51-57: -k * (W(vec) / W(dq h))^n ; POLY6_COEFF cancels in the ratio; n <= 6
+          const float ratio = fmul(poly6nc(c, sq), invDen);
+          float pw = ratio;
+#pragma unroll
+          for (u32 q = 1; q < 6; ++q)
+            if (q < artExp)
               pw = fmul(pw, ratio);
-            sc = fadd(sc, -fmul(artCoeff, pw));
-          }
-          const float w = fmul(sc, spikyCoef(c, sq));
-          cx = ffma(dx, w, cx);
-          cy = ffma(dy, w, cy);
-          cz = ffma(dz, w, cz);
+          sc = fadd(sc, -fmul(artCoeff, pw));
         }
+        const float w = fmul(sc, cs);
+        cx = ffma(dx, w, cx);
+        cy = ffma(dy, w, cy);
+        cz = ffma(dz, w, cz);
       });
   const float rho0 = fp.f.restDensity;
   const float4 corr = make_float4(fdiv(cx, rho0), fdiv(cy, rho0), fdiv(cz, rho0), 0.0f);
@@ -350,7 +313,8 @@ __global__ void __launch_bounds__(NB_THREADS) correctionKernel(DeviceState s, Gr
   {
     if (!LAST)
     {
-      predOut[i] = fluidBoundary(g, np); // next iteration's fld_applyBoundaryCondition (Fluids.cpp:430)
+      np = fluidBoundary(g, np); // next iteration's fld_applyBoundaryCondition (Fluids.cpp:430)
+      predOut[i] = np;
     }
     else
     {
@@ -376,7 +340,8 @@ __global__ void __launch_bounds__(NB_THREADS) correctionKernel(DeviceState s, Gr
     const float4 t0 = s.totCorrB[i];
     const float4 tot = make_float4(fadd(t0.x, corr.x), fadd(t0.y, corr.y), fadd(t0.z, corr.z), 0.0f);
     s.totCorrB[i] = tot;
-    predOut[i] = cloudBoundary(g, np);
+    np = cloudBoundary(g, np);
+    predOut[i] = np;
     if (LAST)
     {
       // cld_updateVel clouds.cl:958-967
@@ -384,10 +349,13 @@ __global__ void __launch_bounds__(NB_THREADS) correctionKernel(DeviceState s, Gr
           fclamp(fdiv(tot.z, idt), -c.maxVel, c.maxVel), 0.0f);
     }
   }
+  if (nbrMode != NBR_OFF)
+    checkListValidity<TRAV>(g, c, s, i, np, epoch + 1);
 }
 
 template <int TRAV>
-__global__ void __launch_bounds__(NB_THREADS) vorticityKernel(DeviceState s, GridParams g, SphConsts c, const float4* __restrict__ pred)
+__global__ void __launch_bounds__(NB_THREADS) vorticityKernel(DeviceState s, GridParams g, SphConsts c, const float4* __restrict__ pred,
+    int nbrMode, int epoch)
 {
   const u32 i = blockIdx.x * NB_THREADS + threadIdx.x;
   if (i >= s.N)
@@ -396,19 +364,17 @@ __global__ void __launch_bounds__(NB_THREADS) vorticityKernel(DeviceState s, Gri
   const float4* __restrict__ V = s.velB;
   const float4 vi = V[i];
   float wx = 0.f, wy = 0.f, wz = 0.f;
-  sweepNeighbours<TRAV>(g, c, s.table, pred, pi,
-      [&](u32 e, float dx, float dy, float dz, float sq)
+  sweepProducer<TRAV>(g, c, s, pred, pi, i, nbrMode, epoch,
+      [&](u32 e, float dx, float dy, float dz, float sq) -> float
       {
-        if (sq > c.epsSq)
-        {
-          const float cs = spikyCoef(c, sq);
-          const float4 vj = ld4(V, e);
-          const float ax = fsub(vj.x, vi.x), ay = fsub(vj.y, vi.y), az = fsub(vj.z, vi.z);
-          // cross(dv, vec * c) = cross(dv, vec) * c, cross(a,b).x = fma(a.y, b.z, -(a.z * b.y))
-          wx = ffma(ffma(ay, dz, -fmul(az, dy)), cs, wx);
-          wy = ffma(ffma(az, dx, -fmul(ax, dz)), cs, wy);
-          wz = ffma(ffma(ax, dy, -fmul(ay, dx)), cs, wz);
-        }
+        const float cs = spikyCoefOrZero(c, sq);
+        const float4 vj = ld4(V, e);
+        const float ax = fsub(vj.x, vi.x), ay = fsub(vj.y, vi.y), az = fsub(vj.z, vi.z);
+        // cross(dv, vec * c) = cross(dv, vec) * c, cross(a,b).x = fma(a.y, b.z, -(a.z * b.y))
+        wx = ffma(ffma(ay, dz, -fmul(az, dy)), cs, wx);
+        wy = ffma(ffma(az, dx, -fmul(ax, dz)), cs, wy);
+        wz = ffma(ffma(ax, dy, -fmul(ay, dx)), cs, wz);
+        return cs;
       });
   s.vort[i] = make_float4(wx, wy, wz, 0.0f);
   s.vortNorm[i] = fsqrt(dot3c(wx, wy, wz, wx, wy, wz)); // fast_length(vort[e]) of the next sweep
@@ -416,7 +382,7 @@ __global__ void __launch_bounds__(NB_THREADS) vorticityKernel(DeviceState s, Gri
 
 template <int TRAV>
 __global__ void __launch_bounds__(NB_THREADS) confinementKernel(DeviceState s, GridParams g, SphConsts c, float coeff, float dt,
-    const float4* __restrict__ pred)
+    const float4* __restrict__ pred, int nbrMode, int epoch)
 {
   const u32 i = blockIdx.x * NB_THREADS + threadIdx.x;
   if (i >= s.N)
@@ -424,16 +390,13 @@ __global__ void __launch_bounds__(NB_THREADS) confinementKernel(DeviceState s, G
   const float4 pi = pred[i];
   const float* __restrict__ wn = s.vortNorm;
   float nx = 0.f, ny = 0.f, nz = 0.f;
-  sweepNeighbours<TRAV>(g, c, s.table, pred, pi,
-      [&](u32 e, float dx, float dy, float dz, float sq)
+  sweepConsumer<TRAV>(g, c, s, pred, pi, i, nbrMode, epoch,
+      [&](u32 e, float dx, float dy, float dz, float, float cs)
       {
-        if (sq > c.epsSq)
-        {
-          const float w = fmul(__ldg(wn + e), spikyCoef(c, sq));
-          nx = ffma(dx, w, nx);
-          ny = ffma(dy, w, ny);
-          nz = ffma(dz, w, nz);
-        }
+        const float w = fmul(__ldg(wn + e), cs);
+        nx = ffma(dx, w, nx);
+        ny = ffma(dy, w, ny);
+        nz = ffma(dz, w, nz);
       });
   // normalize(n) with normalize(0) = 0, then vel += coeff * cross(n, vorticity) * dt   (fluids.cl:376)
   const float l = fsqrt(dot3c(nx, ny, nz, nx, ny, nz));
@@ -452,7 +415,8 @@ __global__ void __launch_bounds__(NB_THREADS) confinementKernel(DeviceState s, G
 }
 
 template <int TRAV>
-__global__ void __launch_bounds__(NB_THREADS) xsphKernel(DeviceState s, GridParams g, SphConsts c, float coeff, const float4* __restrict__ pred)
+__global__ void __launch_bounds__(NB_THREADS) xsphKernel(DeviceState s, GridParams g, SphConsts c, float coeff, const float4* __restrict__ pred,
+    int nbrMode, int epoch)
 {
   const u32 i = blockIdx.x * NB_THREADS + threadIdx.x;
   if (i >= s.N)
@@ -461,8 +425,8 @@ __global__ void __launch_bounds__(NB_THREADS) xsphKernel(DeviceState s, GridPara
   const float4* __restrict__ V = s.velC;
   const float4 vi = V[i];
   float sx = 0.f, sy = 0.f, sz = 0.f;
-  sweepNeighbours<TRAV>(g, c, s.table, pred, pi,
-      [&](u32 e, float, float, float, float sq)
+  sweepConsumer<TRAV>(g, c, s, pred, pi, i, nbrMode, epoch,
+      [&](u32 e, float, float, float, float sq, float)
       {
         const float W = fmul(c.poly6, poly6nc(c, sq));
         const float4 vj = ld4(V, e);
@@ -476,7 +440,7 @@ __global__ void __launch_bounds__(NB_THREADS) xsphKernel(DeviceState s, GridPara
 }
 
 // cld_computeLaplacianTemp clouds.cl:508-569 -- on the SORTED p_pos with the table built from p_predPos (Clouds.cpp:253)
-__global__ void __launch_bounds__(NB_THREADS) laplacianTempKernel(DeviceState s, GridParams g, SphConsts c, float rho0)
+__global__ void __launch_bounds__(NB_THREADS) laplacianTempKernel(DeviceState s, GridParams g, SphConsts c, float rho0, int nbrMode)
 {
   const u32 i = blockIdx.x * NB_THREADS + threadIdx.x;
   if (i >= s.N)
@@ -485,39 +449,38 @@ __global__ void __launch_bounds__(NB_THREADS) laplacianTempKernel(DeviceState s,
   const float* __restrict__ T = s.tempB;
   const float Ti = T[i];
   float lap = 0.f;
-  sweepNeighbours<TRAV_CLOUDS>(g, c, s.table, s.posB, pi,
-      [&](u32 e, float, float, float, float sq)
+  sweepProducer<TRAV_CLOUDS>(g, c, s, s.posB, pi, i, nbrMode, NBR_EPOCH_TEMP,
+      [&](u32 e, float, float, float, float sq) -> float
       {
-        if (sq > c.epsSq)
-          lap = ffma(fmul(fsub(Ti, __ldg(T + e)), fmul(spikyCoef(c, sq), sq)), frcp(fadd(sq, RTP_FLOAT_EPS)), lap);
+        const float cs = spikyCoefOrZero(c, sq);
+        // dot(vec, grad) = c * sq ; x / d = x * (1/d)
+        lap = ffma(fmul(fsub(Ti, __ldg(T + e)), fmul(cs, sq)), rcpInRange(fadd(sq, RTP_FLOAT_EPS)), lap);
+        return cs;
       });
   s.lapTemp[i] = fdiv(lap, rho0);
 }
 
 // cld_computeConstraintFactorTemp clouds.cl:575-648
-__global__ void __launch_bounds__(NB_THREADS) lambdaTempKernel(DeviceState s, GridParams g, SphConsts c, float rho0, float cfm)
+__global__ void __launch_bounds__(NB_THREADS) lambdaTempKernel(DeviceState s, GridParams g, SphConsts c, float rho0, float cfm, int nbrMode)
 {
   const u32 i = blockIdx.x * NB_THREADS + threadIdx.x;
   if (i >= s.N)
     return;
   const float4 pi = s.posB[i];
   float sumD = 0.f, sumD2 = 0.f;
-  sweepNeighbours<TRAV_CLOUDS>(g, c, s.table, s.posB, pi,
-      [&](u32, float, float, float, float sq)
+  sweepConsumer<TRAV_CLOUDS>(g, c, s, s.posB, pi, i, nbrMode, NBR_EPOCH_TEMP,
+      [&](u32, float, float, float, float sq, float cs)
       {
-        if (sq > c.epsSq)
-        {
-          const float d = fmul(fmul(spikyCoef(c, sq), sq), frcp(ffma(sq, rho0, RTP_FLOAT_EPS)));
-          sumD = fadd(sumD, d);
-          sumD2 = ffma(d, d, sumD2);
-        }
+        const float d = fmul(fmul(cs, sq), rcpInRange(ffma(sq, rho0, RTP_FLOAT_EPS)));
+        sumD = fadd(sumD, d);
+        sumD2 = ffma(d, d, sumD2);
       });
   const float ssg = fadd(sumD2, fmul(sumD, sumD));
   s.lambdaTemp[i] = fdiv(-s.lapTemp[i], fadd(ssg, cfm));
 }
 
 // cld_computeConstraintCorrectionTemp clouds.cl:654-722 + cld_correctTemperature :931-937
-__global__ void __launch_bounds__(NB_THREADS) correctTempKernel(DeviceState s, GridParams g, SphConsts c, float rho0)
+__global__ void __launch_bounds__(NB_THREADS) correctTempKernel(DeviceState s, GridParams g, SphConsts c, float rho0, int nbrMode)
 {
   const u32 i = blockIdx.x * NB_THREADS + threadIdx.x;
   if (i >= s.N)
@@ -526,14 +489,11 @@ __global__ void __launch_bounds__(NB_THREADS) correctTempKernel(DeviceState s, G
   const float* __restrict__ L = s.lambdaTemp;
   const float li = L[i];
   float corr = 0.f;
-  sweepNeighbours<TRAV_CLOUDS>(g, c, s.table, s.posB, pi,
-      [&](u32 e, float, float, float, float sq)
+  sweepConsumer<TRAV_CLOUDS>(g, c, s, s.posB, pi, i, nbrMode, NBR_EPOCH_TEMP,
+      [&](u32 e, float, float, float, float sq, float cs)
       {
-        if (sq > c.epsSq)
-        {
-          const float d = fmul(fmul(spikyCoef(c, sq), sq), frcp(ffma(sq, rho0, RTP_FLOAT_EPS)));
-          corr = ffma(fadd(li, __ldg(L + e)), d, corr);
-        }
+        const float d = fmul(fmul(cs, sq), rcpInRange(ffma(sq, rho0, RTP_FLOAT_EPS)));
+        corr = ffma(fadd(li, __ldg(L + e)), d, corr);
       });
   s.corrTemp[i] = corr;
   s.tempB[i] = fadd(s.tempB[i], fmul(0.3f, corr));
@@ -554,17 +514,17 @@ void launchFluidGather(const DeviceState& s, const GridParams& g, cudaStream_t s
     fluidGatherKernel<<<ewBlocks(s.N), EW_THREADS, 0, st>>>(s, g);
 }
 void launchDensityLambda(const DeviceState& s, int model, const GridParams& g, const SphConsts& c, const FluidStepParams& p,
-    const float4* pred, cudaStream_t st)
+    const float4* pred, int nbrMode, int epoch, cudaStream_t st)
 {
   if (!s.N)
     return;
   if (model == RTP_MODEL_CLOUDS)
-    densityLambdaKernel<TRAV_CLOUDS><<<nbBlocks(s.N), NB_THREADS, 0, st>>>(s, g, c, p.f.restDensity, p.f.relaxCFM, pred);
+    densityLambdaKernel<TRAV_CLOUDS><<<nbBlocks(s.N), NB_THREADS, 0, st>>>(s, g, c, p.f.restDensity, p.f.relaxCFM, pred, nbrMode, epoch);
   else
-    densityLambdaKernel<TRAV_FLUIDS><<<nbBlocks(s.N), NB_THREADS, 0, st>>>(s, g, c, p.f.restDensity, p.f.relaxCFM, pred);
+    densityLambdaKernel<TRAV_FLUIDS><<<nbBlocks(s.N), NB_THREADS, 0, st>>>(s, g, c, p.f.restDensity, p.f.relaxCFM, pred, nbrMode, epoch);
 }
 void launchCorrection(const DeviceState& s, int model, const GridParams& g, const SphConsts& c, const FluidStepParams& p,
-    const rtp_cloud_params&, const float4* pred, float4* predOut, bool last, bool writeCorr, cudaStream_t st)
+    const rtp_cloud_params&, const float4* pred, float4* predOut, bool last, bool writeCorr, int nbrMode, int epoch, cudaStream_t st)
 {
   if (!s.N)
     return;
@@ -572,46 +532,47 @@ void launchCorrection(const DeviceState& s, int model, const GridParams& g, cons
   if (model == RTP_MODEL_CLOUDS)
   {
     if (last)
-      correctionKernel<TRAV_CLOUDS, true><<<nb, NB_THREADS, 0, st>>>(s, g, c, p, pred, predOut, wc);
+      correctionKernel<TRAV_CLOUDS, true><<<nb, NB_THREADS, 0, st>>>(s, g, c, p, pred, predOut, wc, nbrMode, epoch);
     else
-      correctionKernel<TRAV_CLOUDS, false><<<nb, NB_THREADS, 0, st>>>(s, g, c, p, pred, predOut, wc);
+      correctionKernel<TRAV_CLOUDS, false><<<nb, NB_THREADS, 0, st>>>(s, g, c, p, pred, predOut, wc, nbrMode, epoch);
   }
   else
   {
     if (last)
-      correctionKernel<TRAV_FLUIDS, true><<<nb, NB_THREADS, 0, st>>>(s, g, c, p, pred, predOut, wc);
+      correctionKernel<TRAV_FLUIDS, true><<<nb, NB_THREADS, 0, st>>>(s, g, c, p, pred, predOut, wc, nbrMode, epoch);
     else
-      correctionKernel<TRAV_FLUIDS, false><<<nb, NB_THREADS, 0, st>>>(s, g, c, p, pred, predOut, wc);
+      correctionKernel<TRAV_FLUIDS, false><<<nb, NB_THREADS, 0, st>>>(s, g, c, p, pred, predOut, wc, nbrMode, epoch);
   }
 }
-void launchVorticity(const DeviceState& s, int model, const GridParams& g, const SphConsts& c, const float4* pred, cudaStream_t st)
+void launchVorticity(const DeviceState& s, int model, const GridParams& g, const SphConsts& c, const float4* pred, int nbrMode,
+    int epoch, cudaStream_t st)
 {
   if (!s.N)
     return;
   if (model == RTP_MODEL_CLOUDS)
-    vorticityKernel<TRAV_CLOUDS><<<nbBlocks(s.N), NB_THREADS, 0, st>>>(s, g, c, pred);
+    vorticityKernel<TRAV_CLOUDS><<<nbBlocks(s.N), NB_THREADS, 0, st>>>(s, g, c, pred, nbrMode, epoch);
   else
-    vorticityKernel<TRAV_FLUIDS><<<nbBlocks(s.N), NB_THREADS, 0, st>>>(s, g, c, pred);
+    vorticityKernel<TRAV_FLUIDS><<<nbBlocks(s.N), NB_THREADS, 0, st>>>(s, g, c, pred, nbrMode, epoch);
 }
 void launchConfinement(const DeviceState& s, int model, const GridParams& g, const SphConsts& c, const FluidStepParams& p,
-    const float4* pred, cudaStream_t st)
+    const float4* pred, int nbrMode, int epoch, cudaStream_t st)
 {
   if (!s.N)
     return;
   if (model == RTP_MODEL_CLOUDS)
-    confinementKernel<TRAV_CLOUDS><<<nbBlocks(s.N), NB_THREADS, 0, st>>>(s, g, c, p.f.vorticityConfCoeff, p.f.timeStep, pred);
+    confinementKernel<TRAV_CLOUDS><<<nbBlocks(s.N), NB_THREADS, 0, st>>>(s, g, c, p.f.vorticityConfCoeff, p.f.timeStep, pred, nbrMode, epoch);
   else
-    confinementKernel<TRAV_FLUIDS><<<nbBlocks(s.N), NB_THREADS, 0, st>>>(s, g, c, p.f.vorticityConfCoeff, p.f.timeStep, pred);
+    confinementKernel<TRAV_FLUIDS><<<nbBlocks(s.N), NB_THREADS, 0, st>>>(s, g, c, p.f.vorticityConfCoeff, p.f.timeStep, pred, nbrMode, epoch);
 }
 void launchXsph(const DeviceState& s, int model, const GridParams& g, const SphConsts& c, const FluidStepParams& p,
-    const rtp_cloud_params&, const float4* pred, cudaStream_t st)
+    const rtp_cloud_params&, const float4* pred, int nbrMode, int epoch, cudaStream_t st)
 {
   if (!s.N)
     return;
   if (model == RTP_MODEL_CLOUDS)
-    xsphKernel<TRAV_CLOUDS><<<nbBlocks(s.N), NB_THREADS, 0, st>>>(s, g, c, p.f.xsphViscosityCoeff, pred);
+    xsphKernel<TRAV_CLOUDS><<<nbBlocks(s.N), NB_THREADS, 0, st>>>(s, g, c, p.f.xsphViscosityCoeff, pred, nbrMode, epoch);
   else
-    xsphKernel<TRAV_FLUIDS><<<nbBlocks(s.N), NB_THREADS, 0, st>>>(s, g, c, p.f.xsphViscosityCoeff, pred);
+    xsphKernel<TRAV_FLUIDS><<<nbBlocks(s.N), NB_THREADS, 0, st>>>(s, g, c, p.f.xsphViscosityCoeff, pred, nbrMode, epoch);
 }
 void launchCloudsInitFields(const DeviceState& s, const GridParams& g, const rtp_cloud_params& cloud, cudaStream_t st)
 {
@@ -626,20 +587,20 @@ void launchCloudsGather(const DeviceState& s, const GridParams& g, cudaStream_t 
   if (s.N)
     cloudsGatherKernel<<<ewBlocks(s.N), EW_THREADS, 0, st>>>(s, g);
 }
-void launchCloudsLaplacianTemp(const DeviceState& s, const GridParams& g, const SphConsts& c, const rtp_cloud_params& cloud, cudaStream_t st)
+void launchCloudsLaplacianTemp(const DeviceState& s, const GridParams& g, const SphConsts& c, const rtp_cloud_params& cloud, int nbrMode, cudaStream_t st)
 {
   if (s.N)
-    laplacianTempKernel<<<nbBlocks(s.N), NB_THREADS, 0, st>>>(s, g, c, cloud.restDensity);
+    laplacianTempKernel<<<nbBlocks(s.N), NB_THREADS, 0, st>>>(s, g, c, cloud.restDensity, nbrMode);
 }
-void launchCloudsLambdaTemp(const DeviceState& s, const GridParams& g, const SphConsts& c, const rtp_cloud_params& cloud, cudaStream_t st)
+void launchCloudsLambdaTemp(const DeviceState& s, const GridParams& g, const SphConsts& c, const rtp_cloud_params& cloud, int nbrMode, cudaStream_t st)
 {
   if (s.N)
-    lambdaTempKernel<<<nbBlocks(s.N), NB_THREADS, 0, st>>>(s, g, c, cloud.restDensity, cloud.relaxCFM);
+    lambdaTempKernel<<<nbBlocks(s.N), NB_THREADS, 0, st>>>(s, g, c, cloud.restDensity, cloud.relaxCFM, nbrMode);
 }
-void launchCloudsCorrectTemp(const DeviceState& s, const GridParams& g, const SphConsts& c, const rtp_cloud_params& cloud, cudaStream_t st)
+void launchCloudsCorrectTemp(const DeviceState& s, const GridParams& g, const SphConsts& c, const rtp_cloud_params& cloud, int nbrMode, cudaStream_t st)
 {
   if (s.N)
-    correctTempKernel<<<nbBlocks(s.N), NB_THREADS, 0, st>>>(s, g, c, cloud.restDensity);
+    correctTempKernel<<<nbBlocks(s.N), NB_THREADS, 0, st>>>(s, g, c, cloud.restDensity, nbrMode);
 }
 void launchCloudsFinish(const DeviceState& s, const GridParams& g, const rtp_cloud_params& cloud, const float4* pred, bool copyVel, cudaStream_t st)
 {

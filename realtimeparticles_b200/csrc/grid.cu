@@ -1,5 +1,6 @@
 // grid.cu -- reset / cell-table / camera / render-side kernels shared by the three models.
 #include "kernels.cuh"
+#include "sweep.cuh"
 
 namespace rtp
 {
@@ -134,6 +135,28 @@ __global__ void __launch_bounds__(EW_THREADS) fillColorFloatKernel(const float* 
   val = fmul(val, (val < 0.0f) ? 0.0f : 1.0f);
   val = fmul(val, (1.0f < val) ? 0.0f : 1.0f);
   col[i] = make_float4(val, val, val, val);
+}
+
+// self-test of the range-check-free sqrt / reciprocal (sweep.cuh) against the IEEE intrinsics, over every float whose
+// bit pattern lies in [lo, hi]
+__global__ void __launch_bounds__(EW_THREADS) selftestMathKernel(u32 lo, u32 hi, unsigned long long* __restrict__ bad)
+{
+  unsigned long long badSqrt = 0, badRcp = 0;
+  for (unsigned long long b = (unsigned long long)lo + blockIdx.x * (unsigned long long)EW_THREADS + threadIdx.x; b <= hi;
+       b += (unsigned long long)gridDim.x * EW_THREADS)
+  {
+    const float x = __uint_as_float((u32)b);
+    badSqrt += __float_as_uint(sqrtInRange(x)) != __float_as_uint(__fsqrt_rn(x));
+    badRcp += __float_as_uint(rcpInRange(x)) != __float_as_uint(__frcp_rn(x));
+  }
+  if (badSqrt)
+    atomicAdd(bad, badSqrt);
+  if (badRcp)
+    atomicAdd(bad + 1, badRcp);
+}
+void launchSelftestMath(u32 lo, u32 hi, unsigned long long* bad, cudaStream_t st)
+{
+  selftestMathKernel<<<148 * 8, EW_THREADS, 0, st>>>(lo, hi, bad);
 }
 
 void launchResetIds(const DeviceState& s, u32 numCells, cudaStream_t st)

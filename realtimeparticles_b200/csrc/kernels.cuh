@@ -29,7 +29,26 @@ struct DeviceState
   u32 *cameraDist = nullptr, *cameraPerm = nullptr;
   uint2* table = nullptr; // c_startEndPartID
   u32 *sortCtrl = nullptr, *sortStatus = nullptr;
+  // per-step neighbour lists (fluids.cu "Neighbour lists"): entry k of particle i at nbrList[k * nbrStride + i]
+  u32 *nbrList = nullptr, *nbrCount = nullptr, *nbrInvalid = nullptr;
+  float4* nbrBuildPos = nullptr;
+  u32 nbrStride = 0, nbrCap = 0;
+  // per-epoch hit lists (sweep.cuh): pair k of particle i at hitList/hitCoef[k * nbrStride + i]
+  u32 *hitList = nullptr, *hitCount = nullptr;
+  float* hitCoef = nullptr;
+  u32 hitCap = 0;
 };
+
+// how a neighbour sweep treats the per-step neighbour lists
+enum NbrMode
+{
+  NBR_OFF = 0, // plain 27-cell traversal
+  NBR_BUILD = 1, // 27-cell traversal, (re)build the lists
+  NBR_BUILD_IF_INVALID = 2, // use the lists unless a particle moved too far since the build, then rebuild
+  NBR_USE = 3 // use the lists (built or validated earlier in the same position epoch)
+};
+constexpr int NBR_EPOCHS = 16;
+constexpr int NBR_EPOCH_TEMP = 15; // clouds temperature sweeps (on p_pos)
 
 struct BoidsStepParams
 {
@@ -49,6 +68,7 @@ struct FluidStepParams
 };
 
 // ---- grid.cu
+void launchSelftestMath(u32 lo, u32 hi, unsigned long long* bad, cudaStream_t st);
 void launchResetIds(const DeviceState& s, u32 numCells, cudaStream_t st);
 void launchAdjustEndCell(const DeviceState& s, const GridParams& g, cudaStream_t st);
 void launchFillCameraDist(const DeviceState& s, const float cam[3], u32* keysOut, cudaStream_t st);
@@ -66,21 +86,23 @@ void launchBoidsRules(const DeviceState& s, const GridParams& g, const SphConsts
 void launchFluidPredict(const DeviceState& s, const GridParams& g, const FluidStepParams& p, u32* keysOut, cudaStream_t st);
 void launchFluidGather(const DeviceState& s, const GridParams& g, cudaStream_t st);
 void launchDensityLambda(const DeviceState& s, int model, const GridParams& g, const SphConsts& c, const FluidStepParams& p,
-    const float4* pred, cudaStream_t st);
+    const float4* pred, int nbrMode, int epoch, cudaStream_t st);
 // last: also integrates velocity (updateVel) and, without vorticity, copies the position (updatePosition)
 void launchCorrection(const DeviceState& s, int model, const GridParams& g, const SphConsts& c, const FluidStepParams& p,
-    const rtp_cloud_params& cloud, const float4* pred, float4* predOut, bool last, bool writeCorr, cudaStream_t st);
-void launchVorticity(const DeviceState& s, int model, const GridParams& g, const SphConsts& c, const float4* pred, cudaStream_t st);
+    const rtp_cloud_params& cloud, const float4* pred, float4* predOut, bool last, bool writeCorr, int nbrMode, int epoch,
+    cudaStream_t st);
+void launchVorticity(const DeviceState& s, int model, const GridParams& g, const SphConsts& c, const float4* pred, int nbrMode,
+    int epoch, cudaStream_t st);
 void launchConfinement(const DeviceState& s, int model, const GridParams& g, const SphConsts& c, const FluidStepParams& p,
-    const float4* pred, cudaStream_t st);
+    const float4* pred, int nbrMode, int epoch, cudaStream_t st);
 void launchXsph(const DeviceState& s, int model, const GridParams& g, const SphConsts& c, const FluidStepParams& p,
-    const rtp_cloud_params& cloud, const float4* pred, cudaStream_t st);
+    const rtp_cloud_params& cloud, const float4* pred, int nbrMode, int epoch, cudaStream_t st);
 void launchCloudsInitFields(const DeviceState& s, const GridParams& g, const rtp_cloud_params& cloud, cudaStream_t st);
 void launchCloudsThermoPredict(const DeviceState& s, const GridParams& g, const rtp_cloud_params& cloud, u32* keysOut, cudaStream_t st);
 void launchCloudsGather(const DeviceState& s, const GridParams& g, cudaStream_t st);
-void launchCloudsLaplacianTemp(const DeviceState& s, const GridParams& g, const SphConsts& c, const rtp_cloud_params& cloud, cudaStream_t st);
-void launchCloudsLambdaTemp(const DeviceState& s, const GridParams& g, const SphConsts& c, const rtp_cloud_params& cloud, cudaStream_t st);
-void launchCloudsCorrectTemp(const DeviceState& s, const GridParams& g, const SphConsts& c, const rtp_cloud_params& cloud, cudaStream_t st);
+void launchCloudsLaplacianTemp(const DeviceState& s, const GridParams& g, const SphConsts& c, const rtp_cloud_params& cloud, int nbrMode, cudaStream_t st);
+void launchCloudsLambdaTemp(const DeviceState& s, const GridParams& g, const SphConsts& c, const rtp_cloud_params& cloud, int nbrMode, cudaStream_t st);
+void launchCloudsCorrectTemp(const DeviceState& s, const GridParams& g, const SphConsts& c, const rtp_cloud_params& cloud, int nbrMode, cudaStream_t st);
 void launchCloudsFinish(const DeviceState& s, const GridParams& g, const rtp_cloud_params& cloud, const float4* pred, bool smoothing, cudaStream_t st);
 
 } // namespace rtp

@@ -37,6 +37,8 @@ struct rtp_handle
   float dispMin = 1.0f, dispMax = 15.0f;
   SortPlan cellPlan, camPlan;
   float4* predFinal = nullptr;
+  float nbrMargin = 0.2f; // RTP_NBR_MARGIN
+  bool nbrEnabled = true; // RTP_NBR_LISTS=0 disables the lists (plain 27-cell traversal in every sweep)
   std::vector<void*> allocs;
   std::string err;
   // graph cache for rtp_step_n
@@ -116,6 +118,10 @@ static void computeConstants(rtp_handle* h)
   while (sqrtf(nextafterf(x, INFINITY)) <= RTP_FLOAT_EPS)
     x = nextafterf(x, INFINITY);
   c.epsSq = x;
+  // neighbour lists: radius (1 + margin) h, validity bound 0.45 margin h (fluids.cu "Neighbour lists")
+  const float lr = (1.0f + h->nbrMargin) * c.h, dm = 0.45f * h->nbrMargin * c.h;
+  c.nbrRadiusSq = lr * lr;
+  c.nbrDmaxSq = dm * dm;
 }
 
 static void updateDerivedFluidParams(rtp_handle* h)
@@ -245,6 +251,10 @@ extern "C" int rtp_create(const rtp_config* cfg, rtp_handle** out)
   } while (0)
   CREATE_TRY(cudaSetDevice(cfg->device));
   CREATE_TRY(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
+  if (const char* e = getenv("RTP_NBR_MARGIN"))
+    h->nbrMargin = fminf(fmaxf((float)atof(e), 0.01f), 1.0f);
+  if (const char* e = getenv("RTP_NBR_LISTS"))
+    h->nbrEnabled = atoi(e) != 0;
   computeConstants(h);
 
   // defaults: Boids.hpp:14-26, Fluids.hpp:17-32, Clouds.hpp:15-45 (+ Clouds.cpp:308-311)
@@ -285,6 +295,25 @@ extern "C" int rtp_create(const rtp_config* cfg, rtp_handle** out)
     CREATE_TRY(devAlloc(h, &s.lambda, M));
     CREATE_TRY(devAlloc(h, &s.vortNorm, M));
     h->predFinal = s.pred0;
+    if (h->nbrEnabled)
+    {
+      u32 cap = 256;
+      if (const char* e = getenv("RTP_NBR_CAP"))
+        cap = (u32)atoi(e);
+      s.nbrCap = cap;
+      s.nbrStride = (u32)M;
+      CREATE_TRY(devAlloc(h, &s.nbrList, (size_t)cap * M));
+      CREATE_TRY(devAlloc(h, &s.nbrCount, M));
+      CREATE_TRY(devAlloc(h, &s.nbrBuildPos, M));
+      CREATE_TRY(devAlloc(h, &s.nbrInvalid, (size_t)NBR_EPOCHS));
+      u32 hcap = 160;
+      if (const char* e = getenv("RTP_HIT_CAP"))
+        hcap = (u32)atoi(e);
+      s.hitCap = hcap;
+      CREATE_TRY(devAlloc(h, &s.hitList, (size_t)hcap * M));
+      CREATE_TRY(devAlloc(h, &s.hitCoef, (size_t)hcap * M));
+      CREATE_TRY(devAlloc(h, &s.hitCount, M));
+    }
   }
   if (model == RTP_MODEL_CLOUDS)
   {
@@ -640,6 +669,7 @@ static int enqueueStep(rtp_handle* h, unsigned flags, const float cam[3], bool p
     else
     {
       const bool clouds = model == RTP_MODEL_CLOUDS;
+      const bool lists = s.nbrList != nullptr && h->jacobi + 1 < NBR_EPOCH_TEMP;
       if (clouds)
         launchCloudsThermoPredict(s, g, h->cp, keysIn, st);
       else
@@ -658,11 +688,11 @@ static int enqueueStep(rtp_handle* h, unsigned flags, const float cam[3], bool p
       rec.mark("adjustEndCell");
       if (clouds && h->cp.isTempSmoothingEnabled)
       {
-        launchCloudsLaplacianTemp(s, g, c, h->cp, st);
+        launchCloudsLaplacianTemp(s, g, c, h->cp, lists ? NBR_BUILD : NBR_OFF, st);
         rec.mark("laplacianTemp");
-        launchCloudsLambdaTemp(s, g, c, h->cp, st);
+        launchCloudsLambdaTemp(s, g, c, h->cp, lists ? NBR_USE : NBR_OFF, st);
         rec.mark("lambdaTemp");
-        launchCloudsCorrectTemp(s, g, c, h->cp, st);
+        launchCloudsCorrectTemp(s, g, c, h->cp, lists ? NBR_USE : NBR_OFF, st);
         rec.mark("correctTemp");
         launches += 3;
       }
@@ -671,9 +701,9 @@ static int enqueueStep(rtp_handle* h, unsigned flags, const float cam[3], bool p
       for (int it = 0; it < h->jacobi; ++it)
       {
         const bool last = it == h->jacobi - 1;
-        launchDensityLambda(s, model, g, c, h->fp, cur, st);
+        launchDensityLambda(s, model, g, c, h->fp, cur, !lists ? NBR_OFF : (it == 0 ? NBR_BUILD : NBR_BUILD_IF_INVALID), it, st);
         rec.mark("densityLambda");
-        launchCorrection(s, model, g, c, h->fp, h->cp, cur, nxt, last, debug, st);
+        launchCorrection(s, model, g, c, h->fp, h->cp, cur, nxt, last, debug, lists ? NBR_USE : NBR_OFF, it, st);
         rec.mark("correction");
         launches += 2;
         float4* t = cur;
@@ -683,11 +713,11 @@ static int enqueueStep(rtp_handle* h, unsigned flags, const float cam[3], bool p
       h->predFinal = cur;
       if (h->fp.f.isVorticityConfEnabled)
       {
-        launchVorticity(s, model, g, c, cur, st);
+        launchVorticity(s, model, g, c, cur, lists ? NBR_BUILD_IF_INVALID : NBR_OFF, h->jacobi, st);
         rec.mark("vorticity");
-        launchConfinement(s, model, g, c, h->fp, cur, st);
+        launchConfinement(s, model, g, c, h->fp, cur, lists ? NBR_USE : NBR_OFF, h->jacobi, st);
         rec.mark("confinement");
-        launchXsph(s, model, g, c, h->fp, h->cp, cur, st);
+        launchXsph(s, model, g, c, h->fp, h->cp, cur, lists ? NBR_USE : NBR_OFF, h->jacobi, st);
         rec.mark("xsph");
         launches += 3;
       }
@@ -857,6 +887,30 @@ extern "C" int rtp_sort_keys_host(rtp_handle* h, const uint32_t* keys_in, uint32
   cudaFree(dk);
   cudaFree(dp);
   return rc;
+}
+
+extern "C" int rtp_selftest_math(rtp_handle* h, float lo, float hi, uint64_t* sqrt_mismatches, uint64_t* rcp_mismatches)
+{
+  if (!h || !(lo > 0.0f) || !(hi >= lo))
+    return RTP_ERR_INVALID;
+  CUDA_TRY(h, cudaSetDevice(h->cfg.device));
+  unsigned long long* d = nullptr;
+  CUDA_TRY(h, cudaMalloc(&d, 16));
+  cudaMemsetAsync(d, 0, 16, h->stream);
+  u32 lb, hb;
+  memcpy(&lb, &lo, 4);
+  memcpy(&hb, &hi, 4);
+  launchSelftestMath(lb, hb, d, h->stream);
+  unsigned long long r[2] = { 0, 0 };
+  cudaMemcpyAsync(r, d, 16, cudaMemcpyDeviceToHost, h->stream);
+  cudaError_t e = cudaStreamSynchronize(h->stream);
+  cudaFree(d);
+  CUDA_TRY(h, e);
+  if (sqrt_mismatches)
+    *sqrt_mismatches = r[0];
+  if (rcp_mismatches)
+    *rcp_mismatches = r[1];
+  return RTP_OK;
 }
 
 // ------------------------------------------------------------------ profiling

@@ -64,6 +64,8 @@ struct SphConsts
   float spikyK; // SPIKY_COEFF * -3.0f (one rounding)
   float maxVel; // MAX_VEL
   float effectRadiusSq; // EFFECT_RADIUS_SQUARED (boids)
+  float nbrRadiusSq; // neighbour-list radius ((1 + margin) h)^2
+  float nbrDmaxSq; // a list stays valid while every particle moved less than sqrt(nbrDmaxSq) = 0.45 margin h
 };
 
 // grid.cl:14-24 getCell3DIndexFromPos -- bit-exact: clamp, add, IEEE divide, floor, truncate
@@ -93,9 +95,12 @@ enum Traversal
 };
 
 // Visit the 27 neighbour cells of ci in the reference's order (iX, iY, iZ ascending) and call
-// f(start, end, shiftX, shiftZ) with the inclusive particle range of each visited cell (end capped by the table).
+// f(start, end, shiftX, shiftZ) with inclusive particle ranges taken from the table. The three z cells of one
+// (iX, iY) column are fetched together and, because cell ids are z-fastest and particles are cell-sorted, usually
+// form ONE contiguous index run: exactly-adjacent ranges with the same image shift are merged, which never changes
+// the candidate sequence (quirks such as the cap or the start=1 cell simply break the merge).
 template <int TRAV, typename F>
-__device__ __forceinline__ void forEachNeighbourCell(const GridParams& g, const uint2* __restrict__ table, int3 ci, F&& f)
+__device__ __forceinline__ void forEachNeighbourRun(const GridParams& g, const uint2* __restrict__ table, int3 ci, F&& f)
 {
   const int RX = g.res[0], RY = g.res[1], RZ = g.res[2];
 #pragma unroll 1
@@ -122,27 +127,73 @@ __device__ __forceinline__ void forEachNeighbourCell(const GridParams& g, const 
         cy = (cy + RY) % RY;
       else if (cy < 0 || cy >= RY)
         continue;
+      const uint2* __restrict__ row = table + (cx * RY + cy) * RZ;
+      uint2 se[3];
+      float sz[3];
 #pragma unroll
-      for (int iZ = -1; iZ <= 1; ++iZ)
+      for (int k = 0; k < 3; ++k)
       {
-        int cz = ci.z + iZ;
-        float sz = 0.0f;
+        int cz = ci.z + k - 1;
+        sz[k] = 0.0f;
+        bool skip = false;
         if (TRAV == TRAV_BOIDS)
         {
-          if (cz < 0 || cz >= RZ)
-            continue;
+          skip = cz < 0 || cz >= RZ;
         }
         else
         {
           if (TRAV == TRAV_CLOUDS)
-            sz = (cz >= RZ) ? 2.0f * g.absW[2] : ((cz < 0) ? -2.0f * g.absW[2] : 0.0f);
+            sz[k] = (cz >= RZ) ? 2.0f * g.absW[2] : ((cz < 0) ? -2.0f * g.absW[2] : 0.0f);
           cz = (cz + RZ) % RZ;
         }
-        const uint2 se = __ldg(&table[(cx * RY + cy) * RZ + cz]);
-        f(se.x, se.y, sx, sz);
+        se[k] = skip ? make_uint2(1u, 0u) : __ldg(row + cz);
       }
+      // merge exactly-adjacent non-empty ranges
+      u32 cs = se[0].x, ce = se[0].y;
+      float csz = sz[0];
+#pragma unroll
+      for (int k = 1; k < 3; ++k)
+      {
+        const bool curEmpty = cs > ce, nxtEmpty = se[k].x > se[k].y;
+        if (nxtEmpty)
+          continue;
+        if (!curEmpty && ce + 1u == se[k].x && csz == sz[k])
+        {
+          ce = se[k].y;
+        }
+        else
+        {
+          if (!curEmpty)
+            f(cs, ce, sx, csz);
+          cs = se[k].x;
+          ce = se[k].y;
+          csz = sz[k];
+        }
+      }
+      if (cs <= ce)
+        f(cs, ce, sx, csz);
     }
   }
+}
+
+// Run body(e, P[e]) for e = start..end in ascending order; loads are hoisted four at a time so that their latency
+// overlaps (the bodies still execute strictly in order: sums stay bit-identical).
+template <typename Body>
+__device__ __forceinline__ void forRangeLoad4(const float4* __restrict__ P, u32 start, u32 end, Body&& body)
+{
+  u32 e = start;
+#pragma unroll 1
+  for (; e + 3u <= end; e += 4u)
+  {
+    const float4 a = __ldg(P + e), b = __ldg(P + e + 1), c = __ldg(P + e + 2), d = __ldg(P + e + 3);
+    body(e, a);
+    body(e + 1, b);
+    body(e + 2, c);
+    body(e + 3, d);
+  }
+#pragma unroll 1
+  for (; e <= end; ++e)
+    body(e, __ldg(P + e));
 }
 
 __device__ __forceinline__ float4 ld4(const float4* __restrict__ p, u32 i) { return __ldg(p + i); }

@@ -39,6 +39,15 @@ def assert_close(p, fields, tol=TOL, N=None):
             assert e <= tol, "%s rel err %.3g > %.1g" % (f, e, tol)
 
 
+# ---------------------------------------------------------------- exact math helpers
+
+def test_inrange_sqrt_rcp_are_ieee_exact():
+    # every float in [1e-17, 1e5]: the kernels' range-check-free sqrt / reciprocal == __fsqrt_rn / __frcp_rn
+    h = _abi.Handle(_abi.BOIDS, 1024, 0)
+    bad_sqrt, bad_rcp = h.selftest_math(1e-17, 1e5)
+    assert bad_sqrt == 0 and bad_rcp == 0, (bad_sqrt, bad_rcp)
+
+
 # ---------------------------------------------------------------- sort
 
 @pytest.mark.parametrize("n,bits,hi", [(0, 8, 200), (1, 8, 200), (31, 16, 60000), (1000, 16, 55000), (4097, 32, 2**32 - 1),
@@ -144,6 +153,25 @@ def test_fluids_100_step_invariants():
     assert abs(eg - eo) <= 0.01 * eo, (eg, eo)  # north_star bar
     assert abs(kg - ko) <= 0.01 * ko, (kg, ko)
     assert_close(p, ("POS", "VEL", "DENSITY"))  # and in fact bit-identical after 100 steps
+
+
+def test_lists_on_off_bit_identical(monkeypatch):
+    # the neighbour-list engine (sweep.cuh) must not change a single bit relative to the plain 27-cell traversal,
+    # also when the margin is so small that the lists are invalidated and rebuilt inside the step
+    outs = []
+    for env in ({"RTP_NBR_LISTS": "0"}, {"RTP_NBR_LISTS": "1"}, {"RTP_NBR_LISTS": "1", "RTP_NBR_MARGIN": "0.02"},
+                {"RTP_NBR_LISTS": "1", "RTP_NBR_CAP": "64", "RTP_HIT_CAP": "48"}):
+        for k in ("RTP_NBR_LISTS", "RTP_NBR_MARGIN", "RTP_NBR_CAP", "RTP_HIT_CAP"):
+            monkeypatch.delenv(k, raising=False)
+        for k, v in env.items():
+            monkeypatch.setenv(k, v)
+        p = make_fluids(M=16384, res=(32, 32, 16), jacobi=3)
+        for _ in range(10):
+            p.step(O.STEP_PHYSICS, oracle=False)
+        outs.append([p.h.download(f) for f in ("p_pos", "p_vel", "p_density", "p_vort")])
+    for o in outs[1:]:
+        for a, b in zip(outs[0], o):
+            assert np.array_equal(a, b)
 
 
 def test_step_n_graph_replay_equals_single_steps():
