@@ -9,7 +9,7 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "lib", "librtp_cuda.so")
+LIB_PATH = os.environ.get("RTP_CUDA_LIB") or os.path.join(_HERE, "lib", "librtp_cuda.so")  # override: A/B builds
 
 RTP_OK = 0
 

@@ -241,7 +241,7 @@ __global__ void __launch_bounds__(EW_THREADS) cloudsFinishKernel(DeviceState s, 
 // ------------------------------------------------------------------ neighbour kernels (engine: sweep.cuh)
 
 template <int TRAV>
-__global__ void __launch_bounds__(NB_THREADS) densityLambdaKernel(DeviceState s, GridParams g, SphConsts c, float rho0, float cfm,
+__global__ void __launch_bounds__(NB_THREADS, 7) densityLambdaKernel(DeviceState s, GridParams g, SphConsts c, float rho0, float cfm,
     const float4* __restrict__ pred, int nbrMode, int epoch)
 {
   const u32 i = blockIdx.x * NB_THREADS + threadIdx.x;
@@ -269,7 +269,7 @@ __global__ void __launch_bounds__(NB_THREADS) densityLambdaKernel(DeviceState s,
 }
 
 template <int TRAV, bool LAST>
-__global__ void __launch_bounds__(NB_THREADS) correctionKernel(DeviceState s, GridParams g, SphConsts c, FluidStepParams fp,
+__global__ void __launch_bounds__(NB_THREADS, 7) correctionKernel(DeviceState s, GridParams g, SphConsts c, FluidStepParams fp,
     const float4* __restrict__ pred, float4* __restrict__ predOut, int writeCorr, int nbrMode, int epoch)
 {
   const u32 i = blockIdx.x * NB_THREADS + threadIdx.x;
@@ -354,7 +354,7 @@ __global__ void __launch_bounds__(NB_THREADS) correctionKernel(DeviceState s, Gr
 }
 
 template <int TRAV>
-__global__ void __launch_bounds__(NB_THREADS) vorticityKernel(DeviceState s, GridParams g, SphConsts c, const float4* __restrict__ pred,
+__global__ void __launch_bounds__(NB_THREADS, 7) vorticityKernel(DeviceState s, GridParams g, SphConsts c, const float4* __restrict__ pred,
     int nbrMode, int epoch)
 {
   const u32 i = blockIdx.x * NB_THREADS + threadIdx.x;
@@ -381,7 +381,7 @@ __global__ void __launch_bounds__(NB_THREADS) vorticityKernel(DeviceState s, Gri
 }
 
 template <int TRAV>
-__global__ void __launch_bounds__(NB_THREADS) confinementKernel(DeviceState s, GridParams g, SphConsts c, float coeff, float dt,
+__global__ void __launch_bounds__(NB_THREADS, 7) confinementKernel(DeviceState s, GridParams g, SphConsts c, float coeff, float dt,
     const float4* __restrict__ pred, int nbrMode, int epoch)
 {
   const u32 i = blockIdx.x * NB_THREADS + threadIdx.x;
@@ -415,7 +415,7 @@ __global__ void __launch_bounds__(NB_THREADS) confinementKernel(DeviceState s, G
 }
 
 template <int TRAV>
-__global__ void __launch_bounds__(NB_THREADS) xsphKernel(DeviceState s, GridParams g, SphConsts c, float coeff, const float4* __restrict__ pred,
+__global__ void __launch_bounds__(NB_THREADS, 7) xsphKernel(DeviceState s, GridParams g, SphConsts c, float coeff, const float4* __restrict__ pred,
     int nbrMode, int epoch)
 {
   const u32 i = blockIdx.x * NB_THREADS + threadIdx.x;
@@ -440,7 +440,7 @@ __global__ void __launch_bounds__(NB_THREADS) xsphKernel(DeviceState s, GridPara
 }
 
 // cld_computeLaplacianTemp clouds.cl:508-569 -- on the SORTED p_pos with the table built from p_predPos (Clouds.cpp:253)
-__global__ void __launch_bounds__(NB_THREADS) laplacianTempKernel(DeviceState s, GridParams g, SphConsts c, float rho0, int nbrMode)
+__global__ void __launch_bounds__(NB_THREADS, 7) laplacianTempKernel(DeviceState s, GridParams g, SphConsts c, float rho0, int nbrMode)
 {
   const u32 i = blockIdx.x * NB_THREADS + threadIdx.x;
   if (i >= s.N)
@@ -461,7 +461,7 @@ __global__ void __launch_bounds__(NB_THREADS) laplacianTempKernel(DeviceState s,
 }
 
 // cld_computeConstraintFactorTemp clouds.cl:575-648
-__global__ void __launch_bounds__(NB_THREADS) lambdaTempKernel(DeviceState s, GridParams g, SphConsts c, float rho0, float cfm, int nbrMode)
+__global__ void __launch_bounds__(NB_THREADS, 7) lambdaTempKernel(DeviceState s, GridParams g, SphConsts c, float rho0, float cfm, int nbrMode)
 {
   const u32 i = blockIdx.x * NB_THREADS + threadIdx.x;
   if (i >= s.N)
@@ -480,7 +480,7 @@ __global__ void __launch_bounds__(NB_THREADS) lambdaTempKernel(DeviceState s, Gr
 }
 
 // cld_computeConstraintCorrectionTemp clouds.cl:654-722 + cld_correctTemperature :931-937
-__global__ void __launch_bounds__(NB_THREADS) correctTempKernel(DeviceState s, GridParams g, SphConsts c, float rho0, int nbrMode)
+__global__ void __launch_bounds__(NB_THREADS, 7) correctTempKernel(DeviceState s, GridParams g, SphConsts c, float rho0, int nbrMode)
 {
   const u32 i = blockIdx.x * NB_THREADS + threadIdx.x;
   if (i >= s.N)
