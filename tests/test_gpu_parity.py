@@ -301,3 +301,74 @@ def test_pbf_2m_properties():
     assert np.isfinite(pos).all() and np.isfinite(vel).all()
     d = h.download("p_density")
     assert 0.0 < d.mean() < 2000.0
+
+
+# ---------------------------------------------------------------- the C++ drop-in (Physics::CUDA::* : Physics::Model)
+
+def _cpp_models():
+    import ctypes as C
+    import os
+    lib = os.path.join(os.path.dirname(_abi.LIB_PATH), "librtp_models.so")
+    if not os.path.exists(lib):
+        pytest.skip("librtp_models.so not built (needs /root/reference at build time)")
+    L = C.CDLL(lib)
+    L.rtpm_create.restype = C.c_void_p
+    L.rtpm_create.argtypes = [C.c_int, C.c_uint64, C.c_int, C.c_int, C.POINTER(C.c_uint32), C.POINTER(C.c_uint32)]
+    L.rtpm_handle.restype = C.c_void_p
+    L.rtpm_handle.argtypes = [C.c_void_p, C.c_int]
+    for f in ("rtpm_destroy", "rtpm_update", "rtpm_reset"):
+        getattr(L, f).argtypes = [C.c_void_p]
+    L.rtpm_nb_particles.argtypes = [C.c_void_p]
+    L.rtpm_nb_particles.restype = C.c_uint64
+    L.rtpm_is_init.argtypes = [C.c_void_p]
+    L.rtpm_update_input_json.argtypes = [C.c_void_p, C.c_char_p]
+    L.rtpm_get_input_json.argtypes = [C.c_void_p, C.c_char_p, C.c_size_t]
+    L.rtpm_set_step_flags.argtypes = [C.c_void_p, C.c_int, C.c_uint]
+    return L, C
+
+
+@pytest.mark.parametrize("kind", ["fluids", "boids", "clouds"])
+def test_cpp_model_equals_python_model(kind):
+    """Physics::CUDA::X driven through the reference's own Model interface == the Python mirror, bit for bit"""
+    from realtimeparticles_b200 import models
+    L, C = _cpp_models()
+    t, case, box, grid = {"fluids": (1, models.PhysicsCase.FLUIDS_DAM, (10, 10, 10), (30, 30, 30)),
+                          "boids": (0, models.PhysicsCase.BOIDS_LARGE, (10, 10, 10), (30, 30, 30)),
+                          "clouds": (2, models.PhysicsCase.CLOUDS_CUMULUS, (10, 20, 10), (30, 60, 30))}[kind]
+    M = 131072
+    m = L.rtpm_create(t, M, int(case), 1, (C.c_uint32 * 3)(*box), (C.c_uint32 * 3)(*grid))
+    assert m and L.rtpm_is_init(m)
+    if kind != "boids":
+        assert L.rtpm_update_input_json(m, b'{"Fluids": {"Nb Jacobi Iterations": [3, 1, 6]}}') == 0
+        assert L.rtpm_update_input_json(m, b'{"Fluids": {"Nb Jacobi Iterations": "oops"}}') == -1  # "Wrong Json parsing"
+        assert L.rtpm_update_input_json(m, b'{"Fluids": {"Nb Jacobi Iterations": [3, 1, 6]}}') == 0
+    py = models.CreateModel(t, models.ModelParams(currNbParticles=M, maxNbParticles=M, boxSize=box, gridRes=grid, pCase=case))
+    if kind == "clouds":
+        # the reference seeds nothing: both sides draw from glibc rand(); make the two draws identical
+        verts = _abi.gen_random_box(65536, (-5.0, -10.0, -5.0), (5.0, -5.0, 5.0), 1)
+        py.loadCloudsState(verts)
+        h = _abi.Handle.__new__(_abi.Handle)  # borrowed view of the C++ model's handle: never let it destroy it
+        h.L, h.h, h.model, h.M, h.N = _abi.lib(), C.c_void_p(L.rtpm_handle(m, t)), t, M, 65536
+        pos = np.full((M, 4), np.inf, np.float32)
+        pos[:, 3] = 0
+        pos[:65536] = verts
+        h.upload("p_pos", pos)
+        h.init_clouds_fields()
+        h.h = None
+    if kind != "boids":
+        js = py.getInputJson()
+        js["Fluids"]["Nb Jacobi Iterations"][0] = 3
+        py.updateInputJson(js)
+    assert L.rtpm_nb_particles(m) == py.nbParticles()
+    for _ in range(3):
+        L.rtpm_update(m)
+        py.update()
+    h = _abi.Handle.__new__(_abi.Handle)
+    h.L, h.h, h.model, h.M, h.N = _abi.lib(), C.c_void_p(L.rtpm_handle(m, t)), t, M, py.nbParticles()
+    h.sync()
+    py.sync()
+    for f in ("p_pos", "p_vel", "p_col", "p_cellID", "p_cameraDist"):
+        a, b = h.download(f), py.download(f)
+        assert np.array_equal(a, b, equal_nan=True), f
+    h.h = None
+    L.rtpm_destroy(m)

@@ -111,3 +111,15 @@ def test_no_gpu_means_loud_failure_not_fallback():
         assert "no CPU fallback" in str(e)
     else:
         raise AssertionError("rtp_create must fail without a CUDA device")
+
+
+def test_cpp_dropin_library_exports():
+    # Physics::CUDA::{Boids,Fluids,Clouds} behind the unmodified Physics::Model (built only where /root/reference exists)
+    lib = os.path.join(ROOT, "realtimeparticles_b200", "lib", "librtp_models.so")
+    if not os.path.exists(lib):
+        import pytest
+        pytest.skip("librtp_models.so not built (needs /root/reference)")
+    L = ctypes.CDLL(lib)
+    for name in ("rtpm_create", "rtpm_destroy", "rtpm_update", "rtpm_reset", "rtpm_update_input_json", "rtpm_get_input_json",
+                 "rtpm_handle", "rtpm_nb_particles", "rtpm_is_init", "rtpm_pause", "rtpm_set_boundary", "rtpm_set_step_flags"):
+        assert hasattr(L, name), name
