@@ -143,15 +143,80 @@ def run_reference(args):
 
 # ------------------------------------------------------------------------------------------------ our arm
 
-def make_pbf(abi, device):
+# BASELINE.json configs -> (particles, algorithmic bytes per particle-step from BASELINE.md section 3)
+WORKLOADS = {
+    "pbf_dam_130k_I3_vorticity_xsph": (N130K, 486.6 + 164.9 * 3),
+    "boids_130k": (N130K, 275.0),
+    "clouds_130k_I2": (N130K, 823.0 + 218.0 * 2),
+    "pbf_dam_16m_I3_vorticity_xsph": (1 << 24, 486.6 + 164.9 * 3 + 16.0),
+}
+
+
+def make_workload(abi, name, device):
+    """Synthetic initial state of a BASELINE.json config loaded into a fresh handle."""
     import numpy as np
-    pos = abi.gen_box_grid((64, 64, 32), (-5.0, -5.0, -5.0), (5.0, 0.0, 0.0))
-    h = abi.Handle(abi.FLUIDS, N130K, N130K, (10, 10, 10), (30, 30, 30), 3, 0, device)
-    h.set_fluid_params(abi.FluidParams(*FLUID_DEFAULTS), JACOBI)
+    n = WORKLOADS[name][0]
+    if name.startswith("pbf_dam_130k"):
+        pos = abi.gen_box_grid((64, 64, 32), (-5.0, -5.0, -5.0), (5.0, 0.0, 0.0))
+        h = abi.Handle(abi.FLUIDS, n, n, (10, 10, 10), (30, 30, 30), 3, 0, device)
+        h.set_fluid_params(abi.FluidParams(*FLUID_DEFAULTS), JACOBI)
+        vel = np.zeros((n, 4), np.float32)
+    elif name.startswith("pbf_dam_16m"):
+        pos = abi.gen_box_grid((512, 256, 128), (-40.0, -20.0, -20.0), (40.0, 0.0, 0.0))
+        h = abi.Handle(abi.FLUIDS, n, n, (80, 40, 40), (240, 120, 120), 3, 0, device)
+        h.set_fluid_params(abi.FluidParams(*FLUID_DEFAULTS), JACOBI)
+        vel = np.zeros((n, 4), np.float32)
+    elif name.startswith("boids"):
+        pos = abi.gen_sphere_grid((64, 64, 32), (-10 / 6.0,) * 3, (10 / 6.0,) * 3)
+        h = abi.Handle(abi.BOIDS, n, n, (10, 10, 10), (30, 30, 30), 3, 0, device)
+        vel = pos
+    elif name.startswith("clouds"):
+        pos = abi.gen_random_box(n, (-5.0, -10.0, -5.0), (5.0, -5.0, 5.0), 1)
+        h = abi.Handle(abi.CLOUDS, n, n, (10, 20, 10), (30, 60, 30), 3, 0, device)
+        h.set_fluid_params(abi.FluidParams(*FLUID_DEFAULTS), 2)
+        h.set_cloud_params(abi.CloudParams(3, 0.01, 450.0, 10.0, 0.10, 0.0005, 5.0, 0.3485, 0.07, 1, 600.0, 0.75, 1.0))
+        vel = np.zeros((n, 4), np.float32)
+    else:
+        raise SystemExit("unknown workload " + name)
     h.upload("p_pos", pos)
-    h.upload("p_vel", np.zeros((N130K, 4), np.float32))
+    h.upload("p_vel", vel)
+    if name.startswith("clouds"):
+        h.upload("p_cloudDens", np.zeros(n, np.float32))
+        h.upload("p_partID", np.arange(n, dtype=np.float32))
+        h.init_clouds_fields()
     h.reset_ids()
     return h, pos
+
+
+def make_pbf(abi, device):
+    return make_workload(abi, "pbf_dam_130k_I3_vorticity_xsph", device)
+
+
+def quick_bench(abi, torch, name, device, steps, warmup, flush):
+    """steps/s of another BASELINE.json config (same timing rules: events on the library stream, L2 flush per step)"""
+    dev = torch.device("cuda", device)
+    h, _ = make_workload(abi, name, device)
+    n, bpp = WORKLOADS[name]
+    stream = torch.cuda.ExternalStream(h.stream(), device=dev)
+    with torch.cuda.stream(stream):
+        h.step_n(warmup, abi.STEP_PHYSICS)
+    h.sync()
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
+    with torch.cuda.stream(stream):
+        for a, b in ev:
+            if n * 150 < (100 << 20):
+                flush.zero_()
+            a.record(stream)
+            h.step_n(1, abi.STEP_PHYSICS)
+            b.record(stream)
+    h.sync()
+    ms = sum(a.elapsed_time(b) for a, b in ev)
+    peak, _ = measured_peak()
+    out = {"particles": n, "steps": steps, "warmup": warmup, "steps_per_s": round(steps / (ms * 1e-3), 2),
+           "value": n * steps / (ms * 1e-3), "unit": "particle-updates/s", "launches_per_step": h.last_launch_count(),
+           "algorithmic_bytes_per_particle": bpp, "whole_step_frac_of_hbm": round(n * steps / (ms * 1e-3) * bpp / 1e9 / peak, 4)}
+    h.close()
+    return out
 
 
 def run_ours(args):
@@ -311,6 +376,14 @@ def run_ours(args):
         cpu = {"value": N130K * n / dt, "unit": "particle-updates/s", "cores": O.max_threads(), "kind": "port",
                "sample": "%d full steps of the same 131072-particle PBF workload after 1 warm-up (%.1f s)" % (n, dt)}
 
+    others = {}
+    if not args.no_other_workloads:
+        for name, (k2, w2) in (("boids_130k", (300, 20)), ("clouds_130k_I2", (300, 20)), ("pbf_dam_16m_I3_vorticity_xsph", (12, 3))):
+            try:
+                others[name] = quick_bench(abi, torch, name, local_rank, k2, w2, flush)
+            except Exception as e:  # e.g. not enough free memory for the 16M config
+                others[name] = {"error": str(e)[:200]}
+
     out = {
         "metric": "particle-updates/sec", "value": value, "unit": "particle-updates/s", "n_gpus": world, "steps": K, "warmup": W,
         "ms_per_step": ms_total / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
@@ -323,6 +396,7 @@ def run_ours(args):
                         "note": "same K steps replayed back to back from one CUDA graph, no flush"},
         "e2e": e2e, "gpu_launches": launches_per_step * K, "launches_per_step": launches_per_step,
         "roofline": roofline, "kernels": kernels, "cpu_baseline": cpu, "clocks": sampler.result(),
+        "other_workloads": others,
         "wall_s_timed_region": round(t_wall, 3),
     }
     print(json.dumps(out), flush=True)
@@ -337,6 +411,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=50)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-other-workloads", action="store_true", help="skip the quick boids / clouds / 16M numbers")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

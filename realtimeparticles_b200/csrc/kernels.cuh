@@ -29,13 +29,12 @@ struct DeviceState
   u32 *cameraDist = nullptr, *cameraPerm = nullptr;
   uint2* table = nullptr; // c_startEndPartID
   u32 *sortCtrl = nullptr, *sortStatus = nullptr;
-  // per-step neighbour lists (fluids.cu "Neighbour lists"): entry k of particle i at nbrList[k * nbrStride + i]
+  // per-step margin lists (sweep.cuh): rows of 4 entries, row r of particle i = ((uint4*)nbrList)[r * nbrStride + i]
   u32 *nbrList = nullptr, *nbrCount = nullptr, *nbrInvalid = nullptr;
   float4* nbrBuildPos = nullptr;
   u32 nbrStride = 0, nbrCap = 0;
-  // per-epoch hit lists (sweep.cuh): pair k of particle i at hitList/hitCoef[k * nbrStride + i]
+  // per-epoch hit lists (sweep.cuh), same row layout
   u32 *hitList = nullptr, *hitCount = nullptr;
-  float* hitCoef = nullptr;
   u32 hitCap = 0;
 };
 

@@ -300,6 +300,7 @@ extern "C" int rtp_create(const rtp_config* cfg, rtp_handle** out)
       u32 cap = 256;
       if (const char* e = getenv("RTP_NBR_CAP"))
         cap = (u32)atoi(e);
+      cap = (cap + 3u) & ~3u;
       s.nbrCap = cap;
       s.nbrStride = (u32)M;
       CREATE_TRY(devAlloc(h, &s.nbrList, (size_t)cap * M));
@@ -309,9 +310,9 @@ extern "C" int rtp_create(const rtp_config* cfg, rtp_handle** out)
       u32 hcap = 160;
       if (const char* e = getenv("RTP_HIT_CAP"))
         hcap = (u32)atoi(e);
+      hcap = (hcap + 3u) & ~3u;
       s.hitCap = hcap;
       CREATE_TRY(devAlloc(h, &s.hitList, (size_t)hcap * M));
-      CREATE_TRY(devAlloc(h, &s.hitCoef, (size_t)hcap * M));
       CREATE_TRY(devAlloc(h, &s.hitCount, M));
     }
   }
