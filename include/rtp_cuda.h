@@ -234,7 +234,43 @@ RTP_API int64_t rtp_gen_random_box(float* out_xyzw, int64_t n, const float start
 /* the float a reference kernel sees for a -D constant: parse(FloatToStr(v)) (utils/Utils.cpp:24-29) */
 RTP_API float rtp_baked_constant(float v);
 
-/* ---- multi-GPU slab decomposition (new design): see rtp_cuda_sharded.h ---- */
+/* ---- multi-GPU slab decomposition (new design; fluids model) ----
+ * One handle per GPU over the GLOBAL box/grid (cell ids stay global); it holds the rank's owned particles followed by
+ * ghost copies of its slab neighbours' boundary layers. The kernels are the single-GPU ones; the caller
+ * (realtimeparticles_b200/sharded.py) runs the step stage by stage and refreshes the ghost entries of the fields a
+ * stage produced before the next stage reads them. */
+typedef enum rtp_shard_stage_id
+{
+  RTP_SHARD_PREDICT = 0, /* predict + cell ids of the first n_owned particles, table reset */
+  RTP_SHARD_GHOST_KEYS = 1, /* cell ids of the ghosts appended at [n_owned, nb_particles) from their p_predPos */
+  RTP_SHARD_SORT = 2, /* sort by cell, payload gather (+ first boundary clamp), cell table */
+  RTP_SHARD_DENSITY_LAMBDA = 3, /* iteration `iter` */
+  RTP_SHARD_CORRECTION = 4, /* iteration `iter`; `last` != 0 also integrates the velocity */
+  RTP_SHARD_VORTICITY = 5,
+  RTP_SHARD_CONFINEMENT = 6,
+  RTP_SHARD_XSPH = 7 /* + updatePosition: state back in p_pos / p_vel, sorted order */
+} rtp_shard_stage_id;
+
+/* internal buffers a slab exchange touches (device pointers valid until the next RTP_SHARD_SORT) */
+typedef enum rtp_shard_buffer_id
+{
+  RTP_SHARD_BUF_KEYS_IN = 0, /* u32[M]   unsorted cell ids written by PREDICT / GHOST_KEYS */
+  RTP_SHARD_BUF_PRED_IN = 1, /* f4[M]    unsorted predicted positions */
+  RTP_SHARD_BUF_PRED_CUR = 2, /* f4[M]   sorted predicted positions the next stage reads */
+  RTP_SHARD_BUF_LAMBDA = 3, /* f[M] */
+  RTP_SHARD_BUF_VEL_SORTED = 4, /* f4[M] velocity after the last correction (input of the vorticity sweep) */
+  RTP_SHARD_BUF_VORT_NORM = 5, /* f[M] */
+  RTP_SHARD_BUF_VEL_CONFINED = 6, /* f4[M] velocity after vorticity confinement (input of the XSPH sweep) */
+  RTP_SHARD_BUF_LIST_BUILD_POS = 7, /* f4[M] positions the neighbour lists were built from */
+  RTP_SHARD_BUF_LIST_INVALID = 8 /* u32[16] per-epoch "lists invalid" flags */
+} rtp_shard_buffer_id;
+
+/* number of leading (unsorted) particles this rank owns; the rest of nb_particles are ghosts */
+RTP_API int rtp_shard_set_owned(rtp_handle* h, uint64_t n_owned);
+RTP_API int rtp_shard_stage(rtp_handle* h, int stage, int iter, int last);
+RTP_API int rtp_shard_buffer(rtp_handle* h, int which, void** dptr, size_t* bytes);
+/* neighbour-list validity: radius^2 a particle may move from its list-build position (see sweep.cuh) */
+RTP_API float rtp_shard_list_dmax_sq(const rtp_handle* h);
 
 #ifdef __cplusplus
 }

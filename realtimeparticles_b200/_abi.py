@@ -80,7 +80,8 @@ EXPORTS = ["rtp_abi_version", "rtp_device_count", "rtp_create", "rtp_destroy", "
            "rtp_set_cloud_params", "rtp_set_boundary", "rtp_set_nb_particles", "rtp_set_dimension",
            "rtp_set_displayed_quantity", "rtp_reset_ids", "rtp_init_clouds_fields", "rtp_step", "rtp_step_n",
            "rtp_sync", "rtp_get_stream", "rtp_sort_keys", "rtp_sort_keys_host", "rtp_selftest_math", "rtp_enable_profiling", "rtp_get_stage_times",
-           "rtp_last_launch_count", "rtp_gen_box_grid", "rtp_gen_sphere_grid", "rtp_gen_random_box",
+           "rtp_last_launch_count", "rtp_shard_set_owned", "rtp_shard_stage", "rtp_shard_buffer", "rtp_shard_list_dmax_sq",
+           "rtp_gen_box_grid", "rtp_gen_sphere_grid", "rtp_gen_random_box",
            "rtp_baked_constant"]
 
 _lib = None
@@ -125,9 +126,15 @@ def lib():
     L.rtp_sort_keys_host.argtypes = [vp, vp, vp, vp, C.c_uint64, C.c_int]
     L.rtp_selftest_math.argtypes = [vp, C.c_float, C.c_float, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]
     L.rtp_enable_profiling.argtypes = [vp, C.c_int]
+    L.rtp_shard_set_owned.argtypes = [vp, C.c_uint64]
+    L.rtp_shard_stage.argtypes = [vp, C.c_int, C.c_int, C.c_int]
+    L.rtp_shard_buffer.argtypes = [vp, C.c_int, C.POINTER(vp), C.POINTER(C.c_size_t)]
+    L.rtp_shard_list_dmax_sq.argtypes = [vp]
+    L.rtp_shard_list_dmax_sq.restype = C.c_float
     L.rtp_get_stage_times.argtypes = [vp, C.POINTER(C.c_char_p), fp, C.c_int]
     L.rtp_last_launch_count.argtypes = [vp]
-    for g in ("rtp_gen_box_grid", "rtp_gen_sphere_grid"):
+    for g in ("rtp_shard_set_owned", "rtp_shard_stage", "rtp_shard_buffer", "rtp_shard_list_dmax_sq",
+           "rtp_gen_box_grid", "rtp_gen_sphere_grid"):
         getattr(L, g).argtypes = [vp, C.POINTER(C.c_int), fp, fp]
         getattr(L, g).restype = C.c_int64
     L.rtp_gen_random_box.argtypes = [vp, C.c_int64, fp, fp, C.c_int]
@@ -274,6 +281,20 @@ class Handle:
         a, b = C.c_uint64(), C.c_uint64()
         self._check(self.L.rtp_selftest_math(self.h, lo, hi, C.byref(a), C.byref(b)), "rtp_selftest_math")
         return a.value, b.value
+
+    def shard_set_owned(self, n):
+        self._check(self.L.rtp_shard_set_owned(self.h, int(n)), "rtp_shard_set_owned")
+
+    def shard_stage(self, stage, it=0, last=False):
+        self._check(self.L.rtp_shard_stage(self.h, int(stage), int(it), int(bool(last))), "rtp_shard_stage")
+
+    def shard_buffer(self, which):
+        p, n = C.c_void_p(), C.c_size_t()
+        self._check(self.L.rtp_shard_buffer(self.h, int(which), C.byref(p), C.byref(n)), "rtp_shard_buffer")
+        return p.value, n.value
+
+    def shard_list_dmax_sq(self):
+        return float(self.L.rtp_shard_list_dmax_sq(self.h))
 
     def enable_profiling(self, on):
         self._check(self.L.rtp_enable_profiling(self.h, int(on)), "rtp_enable_profiling")

@@ -13,6 +13,7 @@ namespace rtp
 struct DeviceState
 {
   u32 M = 0, N = 0;
+  u32 nOwned = 0xFFFFFFFFu; // slab decomposition: unsorted indices >= nOwned are ghost copies (sweep.cuh validity check)
   // float4[M]
   float4 *posA = nullptr, *posB = nullptr, *velA = nullptr, *velB = nullptr, *velC = nullptr;
   float4 *col = nullptr, *colB = nullptr, *acc = nullptr;

@@ -37,6 +37,7 @@ struct rtp_handle
   float dispMin = 1.0f, dispMax = 15.0f;
   SortPlan cellPlan, camPlan;
   float4* predFinal = nullptr;
+  float4* shardCur = nullptr; // slab decomposition: prediction buffer the next stage reads
   float nbrMargin = 0.2f; // RTP_NBR_MARGIN
   bool nbrEnabled = true; // RTP_NBR_LISTS=0 disables the lists (plain 27-cell traversal in every sweep)
   std::vector<void*> allocs;
@@ -830,6 +831,116 @@ extern "C" int rtp_sync(rtp_handle* h)
   CUDA_TRY(h, cudaSetDevice(h->cfg.device));
   CUDA_TRY(h, cudaStreamSynchronize(h->stream));
   CUDA_TRY(h, cudaGetLastError());
+  return RTP_OK;
+}
+
+// ------------------------------------------------------------------ slab decomposition (stage-wise step)
+
+extern "C" int rtp_shard_set_owned(rtp_handle* h, uint64_t n_owned)
+{
+  if (!h)
+    return RTP_ERR_INVALID;
+  h->s.nOwned = n_owned >= 0xFFFFFFFFull ? 0xFFFFFFFFu : (u32)n_owned;
+  invalidateGraph(h);
+  return RTP_OK;
+}
+
+extern "C" float rtp_shard_list_dmax_sq(const rtp_handle* h) { return h ? h->c.nbrDmaxSq : 0.0f; }
+
+extern "C" int rtp_shard_stage(rtp_handle* h, int stage, int iter, int last)
+{
+  if (!h)
+    return RTP_ERR_INVALID;
+  if (h->cfg.model != RTP_MODEL_FLUIDS)
+    return fail(h, RTP_ERR_STATE, "slab decomposition is implemented for the fluids model");
+  CUDA_TRY(h, cudaSetDevice(h->cfg.device));
+  DeviceState& s = h->s;
+  const GridParams& g = h->g;
+  const SphConsts& c = h->c;
+  cudaStream_t st = h->stream;
+  const bool lists = s.nbrList != nullptr && h->jacobi + 1 < NBR_EPOCH_TEMP;
+  u32* keysIn = (h->cellPlan.passes % 2 == 0) ? s.cellID : s.keysTmp;
+  // iteration it reads shardCur and writes the other prediction buffer
+  switch (stage)
+  {
+  case RTP_SHARD_PREDICT:
+  {
+    DeviceState own = s;
+    own.N = min(s.nOwned, s.N);
+    launchFluidPredict(own, g, h->fp, keysIn, st);
+    break;
+  }
+  case RTP_SHARD_GHOST_KEYS:
+  {
+    const u32 first = min(s.nOwned, s.N);
+    if (s.N > first)
+    {
+      DeviceState gh = s;
+      gh.N = s.N - first;
+      gh.posA = s.pred0 + first; // cell ids of the ghosts come from their predicted positions
+      launchBoidsCellIds(gh, g, keysIn + first, st);
+    }
+    break;
+  }
+  case RTP_SHARD_SORT:
+    enqueueSort(h->cellPlan, s.cellID, s.perm, s.keysTmp, s.permTmp, s.sortCtrl, s.sortStatus, st);
+    launchFluidGather(s, g, st);
+    launchAdjustEndCell(s, g, st);
+    h->shardCur = s.pred1;
+    h->predFinal = s.pred1;
+    break;
+  case RTP_SHARD_DENSITY_LAMBDA:
+    launchDensityLambda(s, RTP_MODEL_FLUIDS, g, c, h->fp, h->shardCur, !lists ? NBR_OFF : (iter == 0 ? NBR_BUILD : NBR_BUILD_IF_INVALID), iter, st);
+    break;
+  case RTP_SHARD_CORRECTION:
+  {
+    float4* nxt = (h->shardCur == s.pred1) ? s.pred0 : s.pred1;
+    launchCorrection(s, RTP_MODEL_FLUIDS, g, c, h->fp, h->cp, h->shardCur, nxt, last != 0, false, lists ? NBR_USE : NBR_OFF, iter, st);
+    h->shardCur = nxt;
+    h->predFinal = nxt;
+    break;
+  }
+  case RTP_SHARD_VORTICITY:
+    launchVorticity(s, RTP_MODEL_FLUIDS, g, c, h->shardCur, lists ? NBR_BUILD_IF_INVALID : NBR_OFF, iter, st);
+    break;
+  case RTP_SHARD_CONFINEMENT:
+    launchConfinement(s, RTP_MODEL_FLUIDS, g, c, h->fp, h->shardCur, lists ? NBR_USE : NBR_OFF, iter, st);
+    break;
+  case RTP_SHARD_XSPH:
+    launchXsph(s, RTP_MODEL_FLUIDS, g, c, h->fp, h->cp, h->shardCur, lists ? NBR_USE : NBR_OFF, iter, st);
+    break;
+  default: return fail(h, RTP_ERR_INVALID, "unknown shard stage");
+  }
+  CUDA_TRY(h, cudaGetLastError());
+  return RTP_OK;
+}
+
+extern "C" int rtp_shard_buffer(rtp_handle* h, int which, void** dptr, size_t* bytes)
+{
+  if (!h || !dptr)
+    return RTP_ERR_INVALID;
+  DeviceState& s = h->s;
+  const size_t M = s.M;
+  void* p = nullptr;
+  size_t b = 0;
+  switch (which)
+  {
+  case RTP_SHARD_BUF_KEYS_IN: p = (h->cellPlan.passes % 2 == 0) ? s.cellID : s.keysTmp; b = 4 * M; break;
+  case RTP_SHARD_BUF_PRED_IN: p = s.pred0; b = 16 * M; break;
+  case RTP_SHARD_BUF_PRED_CUR: p = h->shardCur ? h->shardCur : s.pred1; b = 16 * M; break;
+  case RTP_SHARD_BUF_LAMBDA: p = s.lambda; b = 4 * M; break;
+  case RTP_SHARD_BUF_VEL_SORTED: p = s.velB; b = 16 * M; break;
+  case RTP_SHARD_BUF_VORT_NORM: p = s.vortNorm; b = 4 * M; break;
+  case RTP_SHARD_BUF_VEL_CONFINED: p = s.velC; b = 16 * M; break;
+  case RTP_SHARD_BUF_LIST_BUILD_POS: p = s.nbrBuildPos; b = 16 * M; break;
+  case RTP_SHARD_BUF_LIST_INVALID: p = s.nbrInvalid; b = 4 * (size_t)NBR_EPOCHS; break;
+  default: return fail(h, RTP_ERR_INVALID, "unknown shard buffer");
+  }
+  if (!p)
+    return fail(h, RTP_ERR_STATE, "buffer does not exist for this model / configuration");
+  *dptr = p;
+  if (bytes)
+    *bytes = b;
   return RTP_OK;
 }
 

@@ -1,0 +1,140 @@
+"""Helpers for the slab-decomposition tests: a CPU engine (the oracle behind the SlabDecomposition engine interface) and
+multi-process runners. TEST INFRASTRUCTURE (imports oracle/)."""
+import contextlib
+import os
+
+import numpy as np
+import torch
+
+from oracle import oracle_py as O
+
+
+class OracleSlabEngine:
+    """The oracle as a local slab engine (CPU tensors): lets the gloo tests drive realtimeparticles_b200/sharded.py."""
+
+    def __init__(self, capacity, box, grid, jacobi=3):
+        self.w = O.World(O.FLUIDS, capacity, 0, box, grid)
+        self.w.set_fluid_params(O.default_fluid_params(), jacobi)
+        self.capacity, self.jacobi, self.vorticity = capacity, jacobi, True
+        self.n_owned = 0
+
+    def stream_context(self):
+        return contextlib.nullcontext()
+
+    def _t(self, name):
+        a = self.w.field(name)
+        if a.dtype == np.uint32:
+            a = a.view(np.int32)
+        return torch.from_numpy(a)
+
+    def set_counts(self, n_owned, n_local):
+        self.n_owned = n_owned
+        self.w.set_nb_particles(n_local)
+
+    def pos(self):
+        return self._t("POS")
+
+    def vel(self):
+        return self._t("VEL")
+
+    def keys_in(self):
+        return self._t("CELL_ID")
+
+    def pred_in(self):
+        return self._t("PRED_POS")
+
+    def pred_cur(self):
+        return self._t("PRED_POS")
+
+    def perm(self):
+        return self._t("PERM")
+
+    def list_state(self):
+        return None
+
+    def stage(self, name, it=0, last=False):
+        w = self.w
+        seq = {"PREDICT": ["PREDICT_POS", "FILL_CELL_IDS"], "GHOST_KEYS": ["FILL_CELL_IDS"],
+               "SORT": ["SORT_BY_CELL", "BUILD_CELL_TABLE"],
+               "DENSITY_LAMBDA": ["APPLY_BOUNDARY", "DENSITY", "CONSTRAINT_FACTOR"],
+               "CORRECTION": ["CONSTRAINT_CORRECTION", "CORRECT_POS"] + (["UPDATE_VEL"] if last else []),
+               "VORTICITY": ["VORTICITY"], "CONFINEMENT": ["VORTICITY_CONFINEMENT"], "XSPH": ["XSPH", "UPDATE_POS"]}[name]
+        if name == "PREDICT":
+            w.reset_ids()
+        for s in seq:
+            w.run_stage(s)
+
+    def refresh_fields(self, name, last=False):
+        if name == "DENSITY_LAMBDA":
+            return [self._t("CONST_FACTOR")]
+        if name == "CORRECTION":
+            return [self._t("PRED_POS")] + ([self._t("VEL")] if last else [])
+        if name == "VORTICITY":
+            return [self._t("VORT")]
+        if name == "CONFINEMENT":
+            return [self._t("VEL")]
+        return []
+
+    def sync(self):
+        pass
+
+
+def match_particles(a, b):
+    """max distance between two particle sets matched by nearest neighbour (must be a bijection)"""
+    from scipy.spatial import cKDTree
+    assert a.shape == b.shape, (a.shape, b.shape)
+    d, j = cKDTree(b[:, :3]).query(a[:, :3])
+    assert len(np.unique(j)) == len(j), "not a one-to-one match"
+    return float(d.max()), j
+
+
+def _cpu_worker(rank, world, port, cfg, out_dir):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    import torch.distributed as dist
+    from realtimeparticles_b200 import sharded
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    pos0 = cfg["pos"]
+    eng = OracleSlabEngine(cfg["capacity"], cfg["box"], cfg["grid"], cfg["jacobi"])
+    sd = sharded.SlabDecomposition(eng, cfg["grid"], rank, world)
+    mine = sharded.split_initial_state(pos0, cfg["box"], cfg["grid"], rank, world)
+    sd.load_owned(torch.from_numpy(pos0[mine]), torch.from_numpy(cfg["vel"][mine]))
+    hist = []
+    for _ in range(cfg["steps"]):
+        sd.step()
+        hist.append(dict(sd.stats))
+    p, v = sd.owned_state()
+    np.savez(os.path.join(out_dir, "rank%d.npz" % rank), pos=p.numpy(), vel=v.numpy(), migrated=sum(h.get("migrated_out", 0) for h in hist),
+             ghosts=hist[-1].get("ghosts", 0))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def _gpu_worker(rank, world, port, cfg, out_dir):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    import torch.distributed as dist
+    from realtimeparticles_b200 import sharded
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+    pos0 = cfg["pos"]
+    eng = sharded.CudaSlabEngine(cfg["capacity"], cfg["box"], cfg["grid"], rank, jacobi=cfg["jacobi"])
+    sd = sharded.SlabDecomposition(eng, cfg["grid"], rank, world)
+    mine = sharded.split_initial_state(pos0, cfg["box"], cfg["grid"], rank, world)
+    sd.load_owned(torch.from_numpy(pos0[mine]).cuda(rank), torch.from_numpy(cfg["vel"][mine]).cuda(rank))
+    hist = []
+    for _ in range(cfg["steps"]):
+        sd.step()
+        hist.append(dict(sd.stats))
+    p, v = sd.owned_state()
+    eng.sync()
+    np.savez(os.path.join(out_dir, "rank%d.npz" % rank), pos=p.cpu().numpy(), vel=v.cpu().numpy(),
+             migrated=sum(h.get("migrated_out", 0) for h in hist), ghosts=hist[-1].get("ghosts", 0))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def run_sharded(worker, world, cfg, out_dir, port=29571):
+    import torch.multiprocessing as mp
+    mp.spawn(worker, args=(world, port, cfg, out_dir), nprocs=world, join=True)
+    parts = [np.load(os.path.join(out_dir, "rank%d.npz" % r)) for r in range(world)]
+    return (np.concatenate([p["pos"] for p in parts]), np.concatenate([p["vel"] for p in parts]),
+            int(sum(p["migrated"] for p in parts)), [int(p["ghosts"]) for p in parts], [len(p["pos"]) for p in parts])

@@ -1,0 +1,106 @@
+"""Slab decomposition (realtimeparticles_b200/sharded.py).
+CPU: world_size-2 gloo run of the orchestration over oracle engines vs the single-domain oracle.
+GPU: world-1 stage-wise step == rtp_step bit for bit; 2-GPU NCCL run vs the single-GPU run (needs 2 devices)."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import oracle_py as O
+from realtimeparticles_b200 import _abi
+
+import slab_helpers as SH
+
+BOX, GRID = (10, 10, 10), (30, 30, 30)
+
+
+def _dam(res, end=(5.0, 0.0, 0.0)):
+    return O.gen_box_grid(res, (-5.0, -5.0, -5.0), end)
+
+
+def _drift(pos0, vx=4.0):
+    v = np.zeros_like(pos0)
+    v[:, 0] = vx  # 0.04 per step along +x: particles cross the slab face and must migrate
+    return v
+
+
+def _single_oracle(pos0, vel0, steps, jacobi):
+    n = len(pos0)
+    w = O.World(O.FLUIDS, n, n, BOX, GRID)
+    w.set_fluid_params(O.default_fluid_params(), jacobi)
+    w.upload("POS", pos0)
+    w.upload("VEL", vel0)
+    w.reset_ids()
+    for _ in range(steps):
+        w.step(O.STEP_PHYSICS)
+    return w.download("POS"), w.download("VEL")
+
+
+def test_slab_decomposition_gloo_2ranks_matches_single_domain(tmp_path):
+    # a block that straddles the slab boundary at x = 0 and moves across it (initial +x drift through gravity-free vel)
+    pos0 = _dam((16, 16, 16), end=(3.0, -1.0, -1.0))
+    steps, jacobi = 6, 2
+    vel0 = _drift(pos0)
+    cfg = dict(pos=pos0, vel=vel0, capacity=3 * len(pos0), box=BOX, grid=GRID, jacobi=jacobi, steps=steps)
+    pos, vel, migrated, ghosts, owned = SH.run_sharded(SH._cpu_worker, 2, cfg, str(tmp_path))
+    ref_pos, ref_vel = _single_oracle(pos0, vel0, steps, jacobi)
+    assert sum(owned) == len(pos0) and min(owned) > 0
+    assert min(ghosts) > 0  # both ranks did receive a halo
+    assert migrated > 0  # and particles did change owner
+    d, j = SH.match_particles(pos, ref_pos)
+    assert d <= 2e-5, d  # summation order inside a cell differs (arrivals are appended), nothing else
+    assert np.abs(vel - ref_vel[j]).max() <= 1e-5 * max(np.abs(ref_vel).max(), 1.0) + 2 * np.spacing(np.float32(5.0)) / 0.01
+
+
+def test_initial_split_is_a_partition():
+    from realtimeparticles_b200 import sharded
+    pos0 = _dam((16, 16, 16))
+    parts = [sharded.split_initial_state(pos0, BOX, GRID, r, 4) for r in range(4)]
+    allidx = np.sort(np.concatenate(parts))
+    assert np.array_equal(allidx, np.arange(len(pos0)))
+
+
+@pytest.mark.gpu
+def test_stagewise_world1_equals_rtp_step():
+    from realtimeparticles_b200 import sharded
+    pos0 = _dam((32, 32, 16))
+    n = len(pos0)
+    eng = sharded.CudaSlabEngine(n, BOX, GRID, 0, jacobi=3)
+    sd = sharded.SlabDecomposition(eng, GRID, rank=0, world=1)
+    sd.load_owned(torch.from_numpy(pos0).cuda(), torch.zeros((n, 4), device="cuda"))
+    h = _abi.Handle(_abi.FLUIDS, n, n, BOX, GRID)
+    h.set_fluid_params(_abi.FluidParams(450.0, 600.0, 0.010, 3, 1, 0.006, 0.001, 4, 1, 0.0004, 0.0001), 3)
+    h.upload("p_pos", pos0)
+    h.upload("p_vel", np.zeros((n, 4), np.float32))
+    h.reset_ids()
+    for _ in range(4):
+        sd.step()
+        h.step(_abi.STEP_PHYSICS)
+    p, v = sd.owned_state()
+    eng.sync()
+    h.sync()
+    assert np.array_equal(p.cpu().numpy(), h.download("p_pos"))
+    assert np.array_equal(v.cpu().numpy(), h.download("p_vel"))
+
+
+@pytest.mark.gpu
+def test_slab_decomposition_nccl_2gpus_matches_single_gpu(tmp_path):
+    if _abi.lib().rtp_device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    pos0 = _dam((32, 32, 32), end=(3.0, 0.0, 0.0))
+    steps, jacobi = 10, 3
+    vel0 = _drift(pos0)
+    cfg = dict(pos=pos0, vel=vel0, capacity=3 * len(pos0), box=BOX, grid=GRID, jacobi=jacobi, steps=steps)
+    pos, vel, migrated, ghosts, owned = SH.run_sharded(SH._gpu_worker, 2, cfg, str(tmp_path), port=29591)
+    n = len(pos0)
+    h = _abi.Handle(_abi.FLUIDS, n, n, BOX, GRID)
+    h.set_fluid_params(_abi.FluidParams(450.0, 600.0, 0.010, 3, 1, 0.006, 0.001, 4, 1, 0.0004, 0.0001), jacobi)
+    h.upload("p_pos", pos0)
+    h.upload("p_vel", vel0)
+    h.reset_ids()
+    h.step_n(steps, _abi.STEP_PHYSICS)
+    h.sync()
+    ref_pos, ref_vel = h.download("p_pos"), h.download("p_vel")
+    assert sum(owned) == n and min(ghosts) > 0 and migrated > 0
+    d, j = SH.match_particles(pos, ref_pos)
+    assert d <= 5e-5, d
+    assert np.abs(vel - ref_vel[j]).max() <= 1e-5 * max(np.abs(ref_vel).max(), 1.0) + 10 * np.spacing(np.float32(5.0)) / 0.01
