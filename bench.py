@@ -219,6 +219,69 @@ def quick_bench(abi, torch, name, device, steps, warmup, flush):
     return out
 
 
+def run_slab_16m(args, torch, abi, rank, local_rank, world, steps=10, warmup=3):
+    """BASELINE.json configs[4]: PBF dam break scaled to 2^24 particles (box 80x40x40, grid 240x120x120), x-slab
+    decomposed over `world` GPUs with halo exchange + migration (realtimeparticles_b200/sharded.py). Strong scaling:
+    the total problem is fixed; value = 2^24 * steps / max-over-ranks device time."""
+    import numpy as np
+    import torch.distributed as dist
+    from realtimeparticles_b200 import sharded
+    box, grid, total = (80, 40, 40), (240, 120, 120), 1 << 24
+    nx = 512 // world  # lattice planes per slab: spacing 80/512 = 0.15625 is exact in fp32, so sub-blocks reproduce the global lattice
+    x0 = -40.0 + rank * (80.0 / world)
+    pos = abi.gen_box_grid((nx, 256, 128), (x0, -20.0, -20.0), (x0 + 80.0 / world, 0.0, 0.0))
+    n_own = len(pos)
+    ghost_cap = 2 * sharded.GHOST_LAYERS * 120 * 120 * 40 if world > 1 else 0
+    capacity = int(n_own * 1.15) + ghost_cap
+    dev = torch.device("cuda", local_rank)
+    eng = sharded.CudaSlabEngine(capacity, box, grid, local_rank, jacobi=JACOBI)
+    sd = sharded.SlabDecomposition(eng, grid, rank, world)
+    sd.load_owned(torch.from_numpy(pos).to(dev), torch.zeros((n_own, 4), device=dev))
+    for _ in range(warmup):
+        sd.step()
+    sd.profile = True
+    sd.step()
+    phases = sd.stats.get("phases")
+    if world > 1:
+        allph = [None] * world
+        dist.all_gather_object(allph, phases)
+        phases = allph
+    sd.profile = False
+    eng.sync()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t0 = time.perf_counter()
+    with eng.stream_context():
+        e0.record(eng.stream)
+    for _ in range(steps):
+        sd.step()
+        if os.environ.get("RTP_SLAB_SYNC_EACH_STEP"):
+            eng.sync()
+    with eng.stream_context():
+        e1.record(eng.stream)
+    eng.sync()
+    torch.cuda.synchronize()
+    wall = time.perf_counter() - t0
+    t = torch.tensor([e0.elapsed_time(e1), wall * 1e3], dtype=torch.float64, device=dev)
+    owned = torch.tensor([sd.n_owned], dtype=torch.int64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dist.all_reduce(owned, op=dist.ReduceOp.SUM)
+    ms = float(t[0].item())
+    bpp = WORKLOADS["pbf_dam_16m_I3_vorticity_xsph"][1]
+    peak, _ = measured_peak()
+    out = {"workload": "pbf_dam_16m_I3_vorticity_xsph, x-slab decomposition (2 ghost layers, 2I+3 halo refreshes + migration per step)",
+           "particles": total, "particles_owned_sum": int(owned.item()), "n_gpus": world, "steps": steps, "warmup": warmup,
+           "scaling": "strong", "ms_per_step": ms / steps, "steps_per_s": steps / (ms * 1e-3),
+           "value": total * steps / (ms * 1e-3), "unit": "particle-updates/s", "wall_ms_per_step": float(t[1].item()) / steps,
+           "per_rank": {k: v for k, v in sd.stats.items() if k != "phases"}, "phases_ms_per_rank": phases, "algorithmic_bytes_per_particle": bpp,
+           "whole_step_frac_of_hbm_per_gpu": round(total * steps / (ms * 1e-3) * bpp / 1e9 / peak / world, 4)}
+    eng.h.close()
+    return out
+
+
 def run_ours(args):
     import numpy as np
     import torch
@@ -285,6 +348,19 @@ def run_ours(args):
     h.sync()
     warm_ms = e0.elapsed_time(e1)
 
+    slab = None
+    if world > 1 and not args.no_slab:
+        h.close()
+        h = None
+        del flush
+        torch.cuda.empty_cache()
+        try:
+            slab = run_slab_16m(args, torch, abi, rank, local_rank, world)
+        except Exception as e:  # keep the headline line even if the large config cannot run here
+            slab = {"error": repr(e)[:300]}
+        flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+        h, pos0 = make_pbf(abi, local_rank)
+        stream = torch.cuda.ExternalStream(h.stream(), device=dev)
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -396,7 +472,7 @@ def run_ours(args):
                         "note": "same K steps replayed back to back from one CUDA graph, no flush"},
         "e2e": e2e, "gpu_launches": launches_per_step * K, "launches_per_step": launches_per_step,
         "roofline": roofline, "kernels": kernels, "cpu_baseline": cpu, "clocks": sampler.result(),
-        "other_workloads": others,
+        "other_workloads": others, "slab_16m": slab,
         "wall_s_timed_region": round(t_wall, 3),
     }
     print(json.dumps(out), flush=True)
@@ -412,9 +488,24 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-other-workloads", action="store_true", help="skip the quick boids / clouds / 16M numbers")
+    ap.add_argument("--no-slab", action="store_true", help="N > 1: skip the slab-decomposed 16M-particle run")
+    ap.add_argument("--slab-only", action="store_true", help="run only the slab-decomposed 16M-particle config (any N)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)
+    elif args.slab_only:
+        import torch
+        from realtimeparticles_b200 import _abi as abi
+        rank, local_rank, world = dist_env()
+        torch.cuda.set_device(local_rank)
+        if world > 1:
+            import torch.distributed as dist
+            dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+        out = run_slab_16m(args, torch, abi, rank, local_rank, world, steps=max(args.steps, 1) if args.steps < 100 else 10, warmup=3)
+        if rank == 0:
+            print(json.dumps(out), flush=True)
+        if world > 1:
+            dist.destroy_process_group()
     else:
         run_ours(args)
 

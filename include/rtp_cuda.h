@@ -248,7 +248,8 @@ typedef enum rtp_shard_stage_id
   RTP_SHARD_CORRECTION = 4, /* iteration `iter`; `last` != 0 also integrates the velocity */
   RTP_SHARD_VORTICITY = 5,
   RTP_SHARD_CONFINEMENT = 6,
-  RTP_SHARD_XSPH = 7 /* + updatePosition: state back in p_pos / p_vel, sorted order */
+  RTP_SHARD_XSPH = 7, /* + updatePosition: state back in p_pos / p_vel, sorted order */
+  RTP_SHARD_DROP_GHOSTS = 8 /* compact p_pos / p_vel to the owned particles (first n_owned), cell-sorted order kept */
 } rtp_shard_stage_id;
 
 /* internal buffers a slab exchange touches (device pointers valid until the next RTP_SHARD_SORT) */

@@ -133,8 +133,7 @@ def lib():
     L.rtp_shard_list_dmax_sq.restype = C.c_float
     L.rtp_get_stage_times.argtypes = [vp, C.POINTER(C.c_char_p), fp, C.c_int]
     L.rtp_last_launch_count.argtypes = [vp]
-    for g in ("rtp_shard_set_owned", "rtp_shard_stage", "rtp_shard_buffer", "rtp_shard_list_dmax_sq",
-           "rtp_gen_box_grid", "rtp_gen_sphere_grid"):
+    for g in ("rtp_gen_box_grid", "rtp_gen_sphere_grid"):
         getattr(L, g).argtypes = [vp, C.POINTER(C.c_int), fp, fp]
         getattr(L, g).restype = C.c_int64
     L.rtp_gen_random_box.argtypes = [vp, C.c_int64, fp, fp, C.c_int]

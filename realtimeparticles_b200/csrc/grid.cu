@@ -159,6 +159,34 @@ void launchSelftestMath(u32 lo, u32 hi, unsigned long long* bad, cudaStream_t st
   selftestMathKernel<<<148 * 8, EW_THREADS, 0, st>>>(lo, hi, bad);
 }
 
+// slab decomposition: drop the ghost copies after a step. Keys = "is ghost" (1 bit) -> one stable radix pass gives the
+// owned particles first, in their cell-sorted order; then the state is gathered through that permutation.
+__global__ void __launch_bounds__(EW_THREADS) ghostFlagKernel(const u32* __restrict__ perm, u32 nOwned, u32* __restrict__ keys, u32 N)
+{
+  const u32 i = blockIdx.x * EW_THREADS + threadIdx.x;
+  if (i < N)
+    keys[i] = perm[i] >= nOwned ? 1u : 0u;
+}
+__global__ void __launch_bounds__(EW_THREADS) compactGatherKernel(DeviceState s, const u32* __restrict__ order, u32 n)
+{
+  const u32 i = blockIdx.x * EW_THREADS + threadIdx.x;
+  if (i >= n)
+    return;
+  const u32 j = order[i];
+  s.posB[i] = s.posA[j];
+  s.velB[i] = s.velA[j];
+}
+void launchGhostFlags(const DeviceState& s, u32* keysOut, cudaStream_t st)
+{
+  if (s.N)
+    ghostFlagKernel<<<ewBlocks(s.N), EW_THREADS, 0, st>>>(s.perm, s.nOwned, keysOut, s.N);
+}
+void launchCompactGather(const DeviceState& s, const u32* order, u32 n, cudaStream_t st)
+{
+  if (n)
+    compactGatherKernel<<<ewBlocks(n), EW_THREADS, 0, st>>>(s, order, n);
+}
+
 void launchResetIds(const DeviceState& s, u32 numCells, cudaStream_t st)
 {
   resetIdsKernel<<<ewBlocks(s.M), EW_THREADS, 0, st>>>(s.cellID, s.cameraDist, s.perm, s.cameraPerm, s.M, numCells);

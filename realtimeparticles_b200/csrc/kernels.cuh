@@ -69,6 +69,8 @@ struct FluidStepParams
 
 // ---- grid.cu
 void launchSelftestMath(u32 lo, u32 hi, unsigned long long* bad, cudaStream_t st);
+void launchGhostFlags(const DeviceState& s, u32* keysOut, cudaStream_t st);
+void launchCompactGather(const DeviceState& s, const u32* order, u32 n, cudaStream_t st);
 void launchResetIds(const DeviceState& s, u32 numCells, cudaStream_t st);
 void launchAdjustEndCell(const DeviceState& s, const GridParams& g, cudaStream_t st);
 void launchFillCameraDist(const DeviceState& s, const float cam[3], u32* keysOut, cudaStream_t st);

@@ -909,6 +909,22 @@ extern "C" int rtp_shard_stage(rtp_handle* h, int stage, int iter, int last)
   case RTP_SHARD_XSPH:
     launchXsph(s, RTP_MODEL_FLUIDS, g, c, h->fp, h->cp, h->shardCur, lists ? NBR_USE : NBR_OFF, iter, st);
     break;
+  case RTP_SHARD_DROP_GHOSTS:
+  {
+    // owned particles (unsorted index < nOwned) first, cell-sorted order preserved: stable 1-bit partition
+    const u32 nOwn = min(s.nOwned, s.N);
+    if (s.N > nOwn)
+    {
+      const SortPlan plan = makeSortPlan(s.N, 1);
+      // 1 pass (odd): input keys in the second buffer, result in the first; cameraDist/cameraPerm are free scratch here
+      launchGhostFlags(s, s.keysTmp, st);
+      enqueueSort(plan, s.cameraDist, s.cameraPerm, s.keysTmp, s.permTmp, s.sortCtrl, s.sortStatus, st);
+      launchCompactGather(s, s.cameraPerm, nOwn, st);
+      cudaMemcpyAsync(s.posA, s.posB, (size_t)nOwn * sizeof(float4), cudaMemcpyDeviceToDevice, st);
+      cudaMemcpyAsync(s.velA, s.velB, (size_t)nOwn * sizeof(float4), cudaMemcpyDeviceToDevice, st);
+    }
+    break;
+  }
   default: return fail(h, RTP_ERR_INVALID, "unknown shard stage");
   }
   CUDA_TRY(h, cudaGetLastError());

@@ -42,7 +42,7 @@ class _CudaArray:
 class CudaSlabEngine:
     """Local engine: one rtp handle (fluids model, GLOBAL box/grid) + torch views of the buffers the exchanges touch."""
 
-    ST = dict(PREDICT=0, GHOST_KEYS=1, SORT=2, DENSITY_LAMBDA=3, CORRECTION=4, VORTICITY=5, CONFINEMENT=6, XSPH=7)
+    ST = dict(PREDICT=0, GHOST_KEYS=1, SORT=2, DENSITY_LAMBDA=3, CORRECTION=4, VORTICITY=5, CONFINEMENT=6, XSPH=7, DROP_GHOSTS=8)
     BUF = dict(KEYS_IN=0, PRED_IN=1, PRED_CUR=2, LAMBDA=3, VEL_SORTED=4, VORT_NORM=5, VEL_CONFINED=6, LIST_BUILD_POS=7,
                LIST_INVALID=8)
 
@@ -140,6 +140,8 @@ class SlabDecomposition:
             raise ValueError("slab thinner than 2 x ghost layers")
         self.n_owned = 0
         self.stats = {}
+        self.profile = False  # record per-phase device times (ms) of the last step into stats["phases"]
+        self._marks = []
 
     # ---- initial distribution: every rank is given the full initial state and keeps the particles of its slab
     def slab_of(self, keys):
@@ -201,10 +203,25 @@ class SlabDecomposition:
         return recv_l, recv_r
 
     # ---- one PBF step
+    def _mark(self, name):
+        if self.profile and hasattr(self.e, "stream"):
+            ev = torch.cuda.Event(enable_timing=True)
+            ev.record(self.e.stream)
+            self._marks.append((name, ev))
+
     def step(self):
         e = self.e
+        self._marks = []
         with e.stream_context():
+            self._mark("begin")
             self._step()
+            self._mark("end")
+        if self.profile and self._marks:
+            e.sync()
+            ph = {}
+            for (_, a), (name, b) in zip(self._marks[:-1], self._marks[1:]):
+                ph[name] = ph.get(name, 0.0) + a.elapsed_time(b)
+            self.stats["phases"] = {k: round(v, 3) for k, v in ph.items()}
 
     def _step(self):
         e, n = self.e, self.n_owned
@@ -222,18 +239,38 @@ class SlabDecomposition:
             idx_l, idx_r = torch.nonzero(go_l).flatten(), torch.nonzero(go_r).flatten()
             n_in_l, n_in_r = self._exchange_counts(idx_l.numel(), idx_r.numel(), pos)
             self.stats["migrated_out"] = int(idx_l.numel() + idx_r.numel())
-            if idx_l.numel() + idx_r.numel() + n_in_l + n_in_r:
-                stay = torch.nonzero(~(go_l | go_r)).flatten()
-                pv = torch.cat([pos[:n], vel[:n]], dim=1)
-                in_l, in_r = self._exchange(pv[idx_l], pv[idx_r], n_in_l, n_in_r)
-                pv = torch.cat([pv[stay], in_l, in_r], dim=0)  # stayers keep their (cell-sorted) order, arrivals are appended
-                n = pv.shape[0]
-                if n > e.capacity:
-                    raise RuntimeError("slab capacity exceeded: %d > %d" % (n, e.capacity))
-                pos[:n] = pv[:, :4]
-                vel[:n] = pv[:, 4:]
+            k_out, k_in = idx_l.numel() + idx_r.numel(), n_in_l + n_in_r
+            if k_out + k_in:
+                # only the handful of migrating rows are touched: arrivals fill the slots of the leavers, a surplus is
+                # appended, a deficit is filled from the tail (order inside a cell is not preserved for moved rows)
+                in_l, in_r = self._exchange(torch.cat([pos[idx_l], vel[idx_l]], dim=1), torch.cat([pos[idx_r], vel[idx_r]], dim=1),
+                                            n_in_l, n_in_r)
+                arrivals = torch.cat([in_l, in_r], dim=0)
+                holes = torch.cat([idx_l, idx_r])
+                m = min(k_out, k_in)
+                if m:
+                    pos[holes[:m]] = arrivals[:m, :4]
+                    vel[holes[:m]] = arrivals[:m, 4:]
+                if k_in > k_out:
+                    extra = k_in - k_out
+                    if n + extra > e.capacity:
+                        raise RuntimeError("slab capacity exceeded: %d > %d" % (n + extra, e.capacity))
+                    pos[n:n + extra] = arrivals[m:, :4]
+                    vel[n:n + extra] = arrivals[m:, 4:]
+                    n += extra
+                elif k_out > k_in:
+                    rest = holes[m:]
+                    n_new = n - rest.numel()
+                    tail = torch.arange(n_new, n, device=rest.device)
+                    movers = tail[~torch.isin(tail, rest)]
+                    fill = rest[rest < n_new]
+                    if fill.numel():
+                        pos[fill] = pos[movers]
+                        vel[fill] = vel[movers]
+                    n = n_new
                 e.set_counts(n, n)
                 e.stage("PREDICT")
+        self._mark("predict+migrate")
 
         # 2. halo of predicted positions, sort everything by cell
         ng_l = ng_r = 0
@@ -255,7 +292,9 @@ class SlabDecomposition:
             e.stage("GHOST_KEYS")
         n_loc = n + ng_l + ng_r
         self.stats.update(owned=n, ghosts=ng_l + ng_r)
+        self._mark("halo")
         e.stage("SORT")
+        self._mark("sort")
 
         refresh = None
         if self.world > 1:
@@ -287,33 +326,42 @@ class SlabDecomposition:
         else:
             def check_ghost_displacement(next_epoch):
                 return
+        self._mark("index-maps")
 
         # 3. the solver stages, each followed by the refresh of what it produced
         for it in range(jacobi):
             last = it == jacobi - 1
             e.stage("DENSITY_LAMBDA", it)
+            self._mark("compute")
             if refresh:
                 refresh(e.refresh_fields("DENSITY_LAMBDA"))
+                self._mark("refresh")
             e.stage("CORRECTION", it, last)
+            self._mark("compute")
             if refresh:
                 refresh(e.refresh_fields("CORRECTION", last))
                 check_ghost_displacement(it + 1)
+                self._mark("refresh")
         if e.vorticity:
             e.stage("VORTICITY", jacobi)
+            self._mark("compute")
             if refresh:
                 refresh(e.refresh_fields("VORTICITY"))
+                self._mark("refresh")
             e.stage("CONFINEMENT", jacobi)
+            self._mark("compute")
             if refresh:
                 refresh(e.refresh_fields("CONFINEMENT"))
+                self._mark("refresh")
             e.stage("XSPH", jacobi)
+            self._mark("compute")
 
         # 4. drop the ghosts; owned particles stay in cell-sorted order
         if self.world > 1 and n_loc > n:
-            owned_sorted = torch.nonzero(e.perm()[:n_loc].to(torch.int64) < n).flatten()
-            pos[:n] = pos[owned_sorted]
-            vel[:n] = vel[owned_sorted]
+            e.stage("DROP_GHOSTS")
         e.set_counts(n, n)
         self.n_owned = n
+        self._mark("compact")
 
     def owned_state(self):
         n = self.n_owned

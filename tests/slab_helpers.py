@@ -58,7 +58,15 @@ class OracleSlabEngine:
                "SORT": ["SORT_BY_CELL", "BUILD_CELL_TABLE"],
                "DENSITY_LAMBDA": ["APPLY_BOUNDARY", "DENSITY", "CONSTRAINT_FACTOR"],
                "CORRECTION": ["CONSTRAINT_CORRECTION", "CORRECT_POS"] + (["UPDATE_VEL"] if last else []),
-               "VORTICITY": ["VORTICITY"], "CONFINEMENT": ["VORTICITY_CONFINEMENT"], "XSPH": ["XSPH", "UPDATE_POS"]}[name]
+               "VORTICITY": ["VORTICITY"], "CONFINEMENT": ["VORTICITY_CONFINEMENT"], "XSPH": ["XSPH", "UPDATE_POS"],
+               "DROP_GHOSTS": []}[name]
+        if name == "DROP_GHOSTS":  # owned particles (unsorted index < n_owned) first, sorted order kept
+            n_loc = self.w.N
+            keep = np.nonzero(self.w.field("PERM")[:n_loc] < self.n_owned)[0]
+            for f in ("POS", "VEL"):
+                a = self.w.field(f)
+                a[:len(keep)] = a[keep]
+            return
         if name == "PREDICT":
             w.reset_ids()
         for s in seq:

@@ -17,9 +17,9 @@ def _dam(res, end=(5.0, 0.0, 0.0)):
     return O.gen_box_grid(res, (-5.0, -5.0, -5.0), end)
 
 
-def _drift(pos0, vx=4.0):
+def _drift(pos0, vx=12.0):
     v = np.zeros_like(pos0)
-    v[:, 0] = vx  # 0.04 per step along +x: particles cross the slab face and must migrate
+    v[:, 0] = vx  # 0.12 per step along +x: particles cross the slab face and must migrate
     return v
 
 
