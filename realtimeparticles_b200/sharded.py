@@ -181,28 +181,69 @@ class SlabDecomposition:
         return (int(bufs["l"][1].item()) if "l" in bufs else 0), (int(bufs["r"][1].item()) if "r" in bufs else 0)
 
     def _exchange(self, send_left, send_right, n_from_left, n_from_right):
-        """send rows to the neighbours, receive n_from_* rows from them (row shape/dtype of the sends)"""
+        """send rows to the neighbours, receive n_from_* rows from them (row shape/dtype of the sends).
+        Every exchange posts exactly one send and one receive per existing neighbour, also for empty payloads (one pad
+        row is appended), so the NCCL operation pattern never changes: a new pattern (e.g. the first send-only
+        migration) otherwise costs a one-off 50-100 ms connection set-up in the middle of the run."""
         left, right = self._peers()
         ops = []
-        shape_tail = send_left.shape[1:]
-        recv_l = torch.empty((n_from_left,) + tuple(shape_tail), dtype=send_left.dtype, device=send_left.device)
-        recv_r = torch.empty((n_from_right,) + tuple(shape_tail), dtype=send_left.dtype, device=send_left.device)
+        tail = tuple(send_left.shape[1:])
+        pad = torch.zeros((1,) + tail, dtype=send_left.dtype, device=send_left.device)
+        recv_l = torch.empty((n_from_left + 1,) + tail, dtype=send_left.dtype, device=send_left.device)
+        recv_r = torch.empty((n_from_right + 1,) + tail, dtype=send_left.dtype, device=send_left.device)
         if left is not None:
-            if send_left.shape[0]:
-                ops.append(dist.P2POp(dist.isend, send_left.contiguous(), self._global(left), self.group))
-            if n_from_left:
-                ops.append(dist.P2POp(dist.irecv, recv_l, self._global(left), self.group))
+            ops.append(dist.P2POp(dist.isend, torch.cat([send_left, pad], dim=0), self._global(left), self.group))
+            ops.append(dist.P2POp(dist.irecv, recv_l, self._global(left), self.group))
         if right is not None:
-            if send_right.shape[0]:
-                ops.append(dist.P2POp(dist.isend, send_right.contiguous(), self._global(right), self.group))
-            if n_from_right:
-                ops.append(dist.P2POp(dist.irecv, recv_r, self._global(right), self.group))
+            ops.append(dist.P2POp(dist.isend, torch.cat([send_right, pad], dim=0), self._global(right), self.group))
+            ops.append(dist.P2POp(dist.irecv, recv_r, self._global(right), self.group))
         if ops:
             for w in dist.batch_isend_irecv(ops):
                 w.wait()
-        return recv_l, recv_r
+        return recv_l[:n_from_left], recv_r[:n_from_right]
 
-    # ---- one PBF step
+    def _apply_migration(self, pos, vel, n, holes, arrivals):
+        """arrivals (k_in, 8) fill the slots `holes` of the leavers; a surplus is appended, a deficit is filled from the tail"""
+        k_out, k_in = holes.numel(), arrivals.shape[0]
+        m = min(k_out, k_in)
+        if m:
+            pos[holes[:m]] = arrivals[:m, :4]
+            vel[holes[:m]] = arrivals[:m, 4:]
+        if k_in > k_out:
+            extra = k_in - k_out
+            if n + extra > pos.shape[0]:
+                raise RuntimeError("slab capacity exceeded: %d > %d" % (n + extra, pos.shape[0]))
+            pos[n:n + extra] = arrivals[m:, :4]
+            vel[n:n + extra] = arrivals[m:, 4:]
+            n += extra
+        elif k_out > k_in:
+            rest = holes[m:]
+            n_new = n - rest.numel()
+            tail = torch.arange(n_new, n, device=rest.device)
+            movers = tail[~torch.isin(tail, rest)]
+            fill = rest[rest < n_new]
+            if fill.numel():
+                pos[fill] = pos[movers]
+                vel[fill] = vel[movers]
+            n = n_new
+        return n
+
+    def warm_up_code_paths(self):
+        """Run the (rare) migration bookkeeping once on scratch tensors so that no lazily loaded torch kernel or allocator
+        growth lands inside a timed step (first use of a torch op costs tens of ms)."""
+        dev = self.e.pos().device
+        with self.e.stream_context():
+            for k_out, k_in in ((3, 1), (1, 3), (2, 2)):
+                p = torch.zeros((16, 4), device=dev)
+                v = torch.zeros((16, 4), device=dev)
+                holes = torch.arange(1, 1 + k_out, device=dev) * 3
+                self._apply_migration(p, v, 12, holes, torch.ones((k_in, 8), device=dev))
+                torch.cat([p[holes], v[holes]], dim=1)
+            lay = self.slab_of(torch.arange(8, device=dev, dtype=torch.int32))
+            torch.nonzero(lay < 1).flatten()
+            torch.nonzero((lay < 1) | (lay >= 2)).flatten()
+        self.e.sync()
+
     def _mark(self, name):
         if self.profile and hasattr(self.e, "stream"):
             ev = torch.cuda.Event(enable_timing=True)
@@ -240,34 +281,13 @@ class SlabDecomposition:
             n_in_l, n_in_r = self._exchange_counts(idx_l.numel(), idx_r.numel(), pos)
             self.stats["migrated_out"] = int(idx_l.numel() + idx_r.numel())
             k_out, k_in = idx_l.numel() + idx_r.numel(), n_in_l + n_in_r
+            # every rank takes part in the (possibly empty) migration exchange: its neighbours cannot know it has nothing
+            in_l, in_r = self._exchange(torch.cat([pos[idx_l], vel[idx_l]], dim=1), torch.cat([pos[idx_r], vel[idx_r]], dim=1),
+                                        n_in_l, n_in_r)
             if k_out + k_in:
                 # only the handful of migrating rows are touched: arrivals fill the slots of the leavers, a surplus is
                 # appended, a deficit is filled from the tail (order inside a cell is not preserved for moved rows)
-                in_l, in_r = self._exchange(torch.cat([pos[idx_l], vel[idx_l]], dim=1), torch.cat([pos[idx_r], vel[idx_r]], dim=1),
-                                            n_in_l, n_in_r)
-                arrivals = torch.cat([in_l, in_r], dim=0)
-                holes = torch.cat([idx_l, idx_r])
-                m = min(k_out, k_in)
-                if m:
-                    pos[holes[:m]] = arrivals[:m, :4]
-                    vel[holes[:m]] = arrivals[:m, 4:]
-                if k_in > k_out:
-                    extra = k_in - k_out
-                    if n + extra > e.capacity:
-                        raise RuntimeError("slab capacity exceeded: %d > %d" % (n + extra, e.capacity))
-                    pos[n:n + extra] = arrivals[m:, :4]
-                    vel[n:n + extra] = arrivals[m:, 4:]
-                    n += extra
-                elif k_out > k_in:
-                    rest = holes[m:]
-                    n_new = n - rest.numel()
-                    tail = torch.arange(n_new, n, device=rest.device)
-                    movers = tail[~torch.isin(tail, rest)]
-                    fill = rest[rest < n_new]
-                    if fill.numel():
-                        pos[fill] = pos[movers]
-                        vel[fill] = vel[movers]
-                    n = n_new
+                n = self._apply_migration(pos, vel, n, torch.cat([idx_l, idx_r]), torch.cat([in_l, in_r], dim=0))
                 e.set_counts(n, n)
                 e.stage("PREDICT")
         self._mark("predict+migrate")

@@ -104,3 +104,17 @@ def test_slab_decomposition_nccl_2gpus_matches_single_gpu(tmp_path):
     d, j = SH.match_particles(pos, ref_pos)
     assert d <= 5e-5, d
     assert np.abs(vel - ref_vel[j]).max() <= 1e-5 * max(np.abs(ref_vel).max(), 1.0) + 10 * np.spacing(np.float32(5.0)) / 0.01
+
+
+def test_slab_decomposition_gloo_4ranks_interior_ranks_and_idle_neighbours(tmp_path):
+    # 4 slabs: interior ranks have two neighbours, and in most steps only SOME ranks have particles to migrate -- every rank
+    # must still take part in every exchange (a rank-count dependent hang cost a 4-GPU run once)
+    pos0 = O.gen_box_grid((24, 8, 8), (-5.0, -5.0, -5.0), (4.0, -3.0, -3.0))
+    vel0 = _drift(pos0)
+    steps, jacobi = 6, 2
+    cfg = dict(pos=pos0, vel=vel0, capacity=3 * len(pos0), box=BOX, grid=GRID, jacobi=jacobi, steps=steps)
+    pos, vel, migrated, ghosts, owned = SH.run_sharded(SH._cpu_worker, 4, cfg, str(tmp_path), port=29611)
+    ref_pos, ref_vel = _single_oracle(pos0, vel0, steps, jacobi)
+    assert sum(owned) == len(pos0) and migrated > 0
+    d, j = SH.match_particles(pos, ref_pos)
+    assert d <= 2e-5, d
