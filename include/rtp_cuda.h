@@ -224,6 +224,10 @@ RTP_API int rtp_enable_profiling(rtp_handle* h, int enable);
 RTP_API int rtp_get_stage_times(rtp_handle* h, const char** names, float* ms, int cap);
 /* number of kernel launches (memset/memcpy nodes excluded) issued by the last rtp_step / per step of rtp_step_n */
 RTP_API int rtp_last_launch_count(const rtp_handle* h);
+/* Diagnostics of the neighbour lists after a physics-only rtp_step (no reference counterpart; the lists are an internal
+ * optimisation, sweep.cuh): out = { particles, margin lists overflowed, centre cell changed since the list build (those
+ * particles take the warp-cooperative 27-cell path), 0, sum of list lengths, longest list, hit lists overflowed, particles moved beyond the validity bound }. */
+RTP_API int rtp_list_stats(rtp_handle* h, unsigned long long out[8]);
 
 /* ---- initial-condition generators (host side; semantics of utils/Geometry.cpp:198-272) ---- */
 /* out: float4[res.x*res.y*res.z]; returns number of points or negative rtp_status */

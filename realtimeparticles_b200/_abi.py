@@ -80,7 +80,7 @@ EXPORTS = ["rtp_abi_version", "rtp_device_count", "rtp_create", "rtp_destroy", "
            "rtp_set_cloud_params", "rtp_set_boundary", "rtp_set_nb_particles", "rtp_set_dimension",
            "rtp_set_displayed_quantity", "rtp_reset_ids", "rtp_init_clouds_fields", "rtp_step", "rtp_step_n",
            "rtp_sync", "rtp_get_stream", "rtp_sort_keys", "rtp_sort_keys_host", "rtp_selftest_math", "rtp_enable_profiling", "rtp_get_stage_times",
-           "rtp_last_launch_count", "rtp_shard_set_owned", "rtp_shard_stage", "rtp_shard_buffer", "rtp_shard_list_dmax_sq",
+           "rtp_last_launch_count", "rtp_list_stats", "rtp_shard_set_owned", "rtp_shard_stage", "rtp_shard_buffer", "rtp_shard_list_dmax_sq",
            "rtp_gen_box_grid", "rtp_gen_sphere_grid", "rtp_gen_random_box",
            "rtp_baked_constant"]
 
@@ -133,6 +133,7 @@ def lib():
     L.rtp_shard_list_dmax_sq.restype = C.c_float
     L.rtp_get_stage_times.argtypes = [vp, C.POINTER(C.c_char_p), fp, C.c_int]
     L.rtp_last_launch_count.argtypes = [vp]
+    L.rtp_list_stats.argtypes = [vp, C.POINTER(C.c_ulonglong)]
     for g in ("rtp_gen_box_grid", "rtp_gen_sphere_grid"):
         getattr(L, g).argtypes = [vp, C.POINTER(C.c_int), fp, fp]
         getattr(L, g).restype = C.c_int64
@@ -307,6 +308,13 @@ class Handle:
 
     def last_launch_count(self):
         return int(self.L.rtp_last_launch_count(self.h))
+
+    def list_stats(self):
+        """Neighbour-list diagnostics after a physics-only step (rtp_list_stats)."""
+        out = (C.c_ulonglong * 8)()
+        self._check(self.L.rtp_list_stats(self.h, out), "rtp_list_stats")
+        keys = ("particles", "margin_overflow", "cell_changed", "reserved", "sum_len", "max_len", "hit_overflow", "moved_beyond_bound")
+        return dict(zip(keys, [int(v) for v in out]))
 
 
 def gen_box_grid(res, start, end):

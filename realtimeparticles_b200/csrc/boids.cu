@@ -34,6 +34,7 @@ __device__ __forceinline__ void fillCellTable(const u32* __restrict__ keys, u32 
 __global__ void __launch_bounds__(256) boidsCellIdsKernel(const float4* __restrict__ pos, GridParams g, u32* __restrict__ keys,
     uint2* __restrict__ table, u32 N)
 {
+  RTP_PDL_PROLOGUE();
   const u32 i = blockIdx.x * 256 + threadIdx.x;
   if (i < g.numCells)
     table[i] = make_uint2(1u, 0u);
@@ -46,6 +47,7 @@ __global__ void __launch_bounds__(256) boidsCellIdsKernel(const float4* __restri
 
 __global__ void __launch_bounds__(256) boidsGatherKernel(DeviceState s, GridParams g)
 {
+  RTP_PDL_PROLOGUE();
   const u32 i = blockIdx.x * 256 + threadIdx.x;
   if (i >= s.N)
     return;
@@ -62,6 +64,7 @@ __global__ void __launch_bounds__(256) boidsGatherKernel(DeviceState s, GridPara
 template <bool DIM2>
 __global__ void __launch_bounds__(BD_THREADS) boidsRulesKernel(DeviceState s, GridParams g, SphConsts c, BoidsStepParams p)
 {
+  RTP_PDL_PROLOGUE();
   const u32 i = blockIdx.x * BD_THREADS + threadIdx.x;
   if (i >= s.N)
     return;
@@ -184,12 +187,12 @@ __global__ void __launch_bounds__(BD_THREADS) boidsRulesKernel(DeviceState s, Gr
 void launchBoidsCellIds(const DeviceState& s, const GridParams& g, u32* keysOut, cudaStream_t st)
 {
   const u32 n = max(s.N, g.numCells);
-  boidsCellIdsKernel<<<(n + 255) / 256, 256, 0, st>>>(s.posA, g, keysOut, s.table, s.N);
+  launchPdl(boidsCellIdsKernel, (n + 255) / 256, 256, st, s.posA, g, keysOut, s.table, s.N);
 }
 void launchBoidsGather(const DeviceState& s, const GridParams& g, cudaStream_t st)
 {
   if (s.N)
-    boidsGatherKernel<<<(s.N + 255) / 256, 256, 0, st>>>(s, g);
+    launchPdl(boidsGatherKernel, (s.N + 255) / 256, 256, st, s, g);
 }
 void launchBoidsRules(const DeviceState& s, const GridParams& g, const SphConsts& c, const BoidsStepParams& p, cudaStream_t st)
 {
@@ -197,9 +200,9 @@ void launchBoidsRules(const DeviceState& s, const GridParams& g, const SphConsts
     return;
   const int blocks = (s.N + BD_THREADS - 1) / BD_THREADS;
   if (p.dim == 2)
-    boidsRulesKernel<true><<<blocks, BD_THREADS, 0, st>>>(s, g, c, p);
+    launchPdl(boidsRulesKernel<true>, blocks, BD_THREADS, st, s, g, c, p);
   else
-    boidsRulesKernel<false><<<blocks, BD_THREADS, 0, st>>>(s, g, c, p);
+    launchPdl(boidsRulesKernel<false>, blocks, BD_THREADS, st, s, g, c, p);
 }
 
 } // namespace rtp

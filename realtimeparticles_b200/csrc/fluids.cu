@@ -25,7 +25,11 @@
 
 namespace rtp
 {
-constexpr int NB_THREADS = 128; // neighbour kernels
+#ifndef RTP_NB_THREADS
+#define RTP_NB_THREADS 128
+#endif
+constexpr int NB_THREADS = RTP_NB_THREADS; // neighbour kernels
+constexpr int NB_MIN_BLOCKS = 896 / RTP_NB_THREADS; // 28 resident warps per SM (72 registers per thread)
 constexpr int EW_THREADS = 256; // element-wise kernels
 
 __device__ __forceinline__ void fillCellTable(const u32* __restrict__ keys, u32 i, u32 N, u32 numCells, uint2* __restrict__ table)
@@ -65,6 +69,7 @@ __device__ __forceinline__ float4 cloudBoundary(const GridParams& g, float4 np)
 
 __global__ void __launch_bounds__(EW_THREADS) fluidPredictKernel(DeviceState s, GridParams g, float dt, u32* __restrict__ keys)
 {
+  RTP_PDL_PROLOGUE();
   const u32 i = blockIdx.x * EW_THREADS + threadIdx.x;
   if (i < g.numCells)
     s.table[i] = make_uint2(1u, 0u);
@@ -82,6 +87,7 @@ __global__ void __launch_bounds__(EW_THREADS) fluidPredictKernel(DeviceState s, 
 
 __global__ void __launch_bounds__(EW_THREADS) fluidGatherKernel(DeviceState s, GridParams g)
 {
+  RTP_PDL_PROLOGUE();
   const u32 i = blockIdx.x * EW_THREADS + threadIdx.x;
   if (i >= s.N)
     return;
@@ -147,6 +153,7 @@ __device__ __forceinline__ float saturationVaporDensity(float T)
 // cld_initTemperature clouds.cl:116-122 + cld_initVaporDensity :127-135 over M
 __global__ void __launch_bounds__(EW_THREADS) cloudsInitFieldsKernel(DeviceState s, GridParams g, float coeff)
 {
+  RTP_PDL_PROLOGUE();
   const u32 i = blockIdx.x * EW_THREADS + threadIdx.x;
   if (i >= s.M)
     return;
@@ -160,6 +167,7 @@ __global__ void __launch_bounds__(EW_THREADS) cloudsInitFieldsKernel(DeviceState
 __global__ void __launch_bounds__(EW_THREADS) cloudsThermoPredictKernel(DeviceState s, GridParams g, rtp_cloud_params c,
     u32* __restrict__ keys)
 {
+  RTP_PDL_PROLOGUE();
   const u32 i = blockIdx.x * EW_THREADS + threadIdx.x;
   if (i < g.numCells)
     s.table[i] = make_uint2(1u, 0u);
@@ -199,6 +207,7 @@ __global__ void __launch_bounds__(EW_THREADS) cloudsThermoPredictKernel(DeviceSt
 
 __global__ void __launch_bounds__(EW_THREADS) cloudsGatherKernel(DeviceState s, GridParams g)
 {
+  RTP_PDL_PROLOGUE();
   const u32 i = blockIdx.x * EW_THREADS + threadIdx.x;
   if (i >= s.N)
     return;
@@ -219,6 +228,7 @@ __global__ void __launch_bounds__(EW_THREADS) cloudsGatherKernel(DeviceState s, 
 __global__ void __launch_bounds__(EW_THREADS) cloudsFinishKernel(DeviceState s, GridParams g, rtp_cloud_params c,
     const float4* __restrict__ pred, int copyVel)
 {
+  RTP_PDL_PROLOGUE();
   const u32 i = blockIdx.x * EW_THREADS + threadIdx.x;
   if (i >= s.N)
     return;
@@ -241,9 +251,10 @@ __global__ void __launch_bounds__(EW_THREADS) cloudsFinishKernel(DeviceState s, 
 // ------------------------------------------------------------------ neighbour kernels (engine: sweep.cuh)
 
 template <int TRAV>
-__global__ void __launch_bounds__(NB_THREADS, 7) densityLambdaKernel(DeviceState s, GridParams g, SphConsts c, float rho0, float cfm,
+__global__ void __launch_bounds__(NB_THREADS, NB_MIN_BLOCKS) densityLambdaKernel(DeviceState s, GridParams g, SphConsts c, float rho0, float cfm,
     const float4* __restrict__ pred, int nbrMode, int epoch)
 {
+  RTP_PDL_PROLOGUE();
   const u32 i = blockIdx.x * NB_THREADS + threadIdx.x;
   if (i >= s.N)
     return;
@@ -269,9 +280,10 @@ __global__ void __launch_bounds__(NB_THREADS, 7) densityLambdaKernel(DeviceState
 }
 
 template <int TRAV, bool LAST>
-__global__ void __launch_bounds__(NB_THREADS, 7) correctionKernel(DeviceState s, GridParams g, SphConsts c, FluidStepParams fp,
+__global__ void __launch_bounds__(NB_THREADS, NB_MIN_BLOCKS) correctionKernel(DeviceState s, GridParams g, SphConsts c, FluidStepParams fp,
     const float4* __restrict__ pred, float4* __restrict__ predOut, int writeCorr, int nbrMode, int epoch)
 {
+  RTP_PDL_PROLOGUE();
   const u32 i = blockIdx.x * NB_THREADS + threadIdx.x;
   if (i >= s.N)
     return;
@@ -354,9 +366,10 @@ __global__ void __launch_bounds__(NB_THREADS, 7) correctionKernel(DeviceState s,
 }
 
 template <int TRAV>
-__global__ void __launch_bounds__(NB_THREADS, 7) vorticityKernel(DeviceState s, GridParams g, SphConsts c, const float4* __restrict__ pred,
+__global__ void __launch_bounds__(NB_THREADS, NB_MIN_BLOCKS) vorticityKernel(DeviceState s, GridParams g, SphConsts c, const float4* __restrict__ pred,
     int nbrMode, int epoch)
 {
+  RTP_PDL_PROLOGUE();
   const u32 i = blockIdx.x * NB_THREADS + threadIdx.x;
   if (i >= s.N)
     return;
@@ -381,9 +394,10 @@ __global__ void __launch_bounds__(NB_THREADS, 7) vorticityKernel(DeviceState s, 
 }
 
 template <int TRAV>
-__global__ void __launch_bounds__(NB_THREADS, 7) confinementKernel(DeviceState s, GridParams g, SphConsts c, float coeff, float dt,
+__global__ void __launch_bounds__(NB_THREADS, NB_MIN_BLOCKS) confinementKernel(DeviceState s, GridParams g, SphConsts c, float coeff, float dt,
     const float4* __restrict__ pred, int nbrMode, int epoch)
 {
+  RTP_PDL_PROLOGUE();
   const u32 i = blockIdx.x * NB_THREADS + threadIdx.x;
   if (i >= s.N)
     return;
@@ -415,9 +429,10 @@ __global__ void __launch_bounds__(NB_THREADS, 7) confinementKernel(DeviceState s
 }
 
 template <int TRAV>
-__global__ void __launch_bounds__(NB_THREADS, 7) xsphKernel(DeviceState s, GridParams g, SphConsts c, float coeff, const float4* __restrict__ pred,
+__global__ void __launch_bounds__(NB_THREADS, NB_MIN_BLOCKS) xsphKernel(DeviceState s, GridParams g, SphConsts c, float coeff, const float4* __restrict__ pred,
     int nbrMode, int epoch)
 {
+  RTP_PDL_PROLOGUE();
   const u32 i = blockIdx.x * NB_THREADS + threadIdx.x;
   if (i >= s.N)
     return;
@@ -440,8 +455,9 @@ __global__ void __launch_bounds__(NB_THREADS, 7) xsphKernel(DeviceState s, GridP
 }
 
 // cld_computeLaplacianTemp clouds.cl:508-569 -- on the SORTED p_pos with the table built from p_predPos (Clouds.cpp:253)
-__global__ void __launch_bounds__(NB_THREADS, 7) laplacianTempKernel(DeviceState s, GridParams g, SphConsts c, float rho0, int nbrMode)
+__global__ void __launch_bounds__(NB_THREADS, NB_MIN_BLOCKS) laplacianTempKernel(DeviceState s, GridParams g, SphConsts c, float rho0, int nbrMode)
 {
+  RTP_PDL_PROLOGUE();
   const u32 i = blockIdx.x * NB_THREADS + threadIdx.x;
   if (i >= s.N)
     return;
@@ -461,8 +477,9 @@ __global__ void __launch_bounds__(NB_THREADS, 7) laplacianTempKernel(DeviceState
 }
 
 // cld_computeConstraintFactorTemp clouds.cl:575-648
-__global__ void __launch_bounds__(NB_THREADS, 7) lambdaTempKernel(DeviceState s, GridParams g, SphConsts c, float rho0, float cfm, int nbrMode)
+__global__ void __launch_bounds__(NB_THREADS, NB_MIN_BLOCKS) lambdaTempKernel(DeviceState s, GridParams g, SphConsts c, float rho0, float cfm, int nbrMode)
 {
+  RTP_PDL_PROLOGUE();
   const u32 i = blockIdx.x * NB_THREADS + threadIdx.x;
   if (i >= s.N)
     return;
@@ -480,8 +497,9 @@ __global__ void __launch_bounds__(NB_THREADS, 7) lambdaTempKernel(DeviceState s,
 }
 
 // cld_computeConstraintCorrectionTemp clouds.cl:654-722 + cld_correctTemperature :931-937
-__global__ void __launch_bounds__(NB_THREADS, 7) correctTempKernel(DeviceState s, GridParams g, SphConsts c, float rho0, int nbrMode)
+__global__ void __launch_bounds__(NB_THREADS, NB_MIN_BLOCKS) correctTempKernel(DeviceState s, GridParams g, SphConsts c, float rho0, int nbrMode)
 {
+  RTP_PDL_PROLOGUE();
   const u32 i = blockIdx.x * NB_THREADS + threadIdx.x;
   if (i >= s.N)
     return;
@@ -506,12 +524,12 @@ static inline int nbBlocks(size_t n) { return (int)((n + NB_THREADS - 1) / NB_TH
 
 void launchFluidPredict(const DeviceState& s, const GridParams& g, const FluidStepParams& p, u32* keysOut, cudaStream_t st)
 {
-  fluidPredictKernel<<<ewBlocks(max(s.N, g.numCells)), EW_THREADS, 0, st>>>(s, g, p.f.timeStep, keysOut);
+  launchPdl(fluidPredictKernel, ewBlocks(max(s.N, g.numCells)), EW_THREADS, st, s, g, p.f.timeStep, keysOut);
 }
 void launchFluidGather(const DeviceState& s, const GridParams& g, cudaStream_t st)
 {
   if (s.N)
-    fluidGatherKernel<<<ewBlocks(s.N), EW_THREADS, 0, st>>>(s, g);
+    launchPdl(fluidGatherKernel, ewBlocks(s.N), EW_THREADS, st, s, g);
 }
 void launchDensityLambda(const DeviceState& s, int model, const GridParams& g, const SphConsts& c, const FluidStepParams& p,
     const float4* pred, int nbrMode, int epoch, cudaStream_t st)
@@ -519,9 +537,9 @@ void launchDensityLambda(const DeviceState& s, int model, const GridParams& g, c
   if (!s.N)
     return;
   if (model == RTP_MODEL_CLOUDS)
-    densityLambdaKernel<TRAV_CLOUDS><<<nbBlocks(s.N), NB_THREADS, 0, st>>>(s, g, c, p.f.restDensity, p.f.relaxCFM, pred, nbrMode, epoch);
+    launchPdl(densityLambdaKernel<TRAV_CLOUDS>, nbBlocks(s.N), NB_THREADS, st, s, g, c, p.f.restDensity, p.f.relaxCFM, pred, nbrMode, epoch);
   else
-    densityLambdaKernel<TRAV_FLUIDS><<<nbBlocks(s.N), NB_THREADS, 0, st>>>(s, g, c, p.f.restDensity, p.f.relaxCFM, pred, nbrMode, epoch);
+    launchPdl(densityLambdaKernel<TRAV_FLUIDS>, nbBlocks(s.N), NB_THREADS, st, s, g, c, p.f.restDensity, p.f.relaxCFM, pred, nbrMode, epoch);
 }
 void launchCorrection(const DeviceState& s, int model, const GridParams& g, const SphConsts& c, const FluidStepParams& p,
     const rtp_cloud_params&, const float4* pred, float4* predOut, bool last, bool writeCorr, int nbrMode, int epoch, cudaStream_t st)
@@ -532,16 +550,16 @@ void launchCorrection(const DeviceState& s, int model, const GridParams& g, cons
   if (model == RTP_MODEL_CLOUDS)
   {
     if (last)
-      correctionKernel<TRAV_CLOUDS, true><<<nb, NB_THREADS, 0, st>>>(s, g, c, p, pred, predOut, wc, nbrMode, epoch);
+      launchPdl(correctionKernel<TRAV_CLOUDS, true>, nb, NB_THREADS, st, s, g, c, p, pred, predOut, wc, nbrMode, epoch);
     else
-      correctionKernel<TRAV_CLOUDS, false><<<nb, NB_THREADS, 0, st>>>(s, g, c, p, pred, predOut, wc, nbrMode, epoch);
+      launchPdl(correctionKernel<TRAV_CLOUDS, false>, nb, NB_THREADS, st, s, g, c, p, pred, predOut, wc, nbrMode, epoch);
   }
   else
   {
     if (last)
-      correctionKernel<TRAV_FLUIDS, true><<<nb, NB_THREADS, 0, st>>>(s, g, c, p, pred, predOut, wc, nbrMode, epoch);
+      launchPdl(correctionKernel<TRAV_FLUIDS, true>, nb, NB_THREADS, st, s, g, c, p, pred, predOut, wc, nbrMode, epoch);
     else
-      correctionKernel<TRAV_FLUIDS, false><<<nb, NB_THREADS, 0, st>>>(s, g, c, p, pred, predOut, wc, nbrMode, epoch);
+      launchPdl(correctionKernel<TRAV_FLUIDS, false>, nb, NB_THREADS, st, s, g, c, p, pred, predOut, wc, nbrMode, epoch);
   }
 }
 void launchVorticity(const DeviceState& s, int model, const GridParams& g, const SphConsts& c, const float4* pred, int nbrMode,
@@ -550,9 +568,9 @@ void launchVorticity(const DeviceState& s, int model, const GridParams& g, const
   if (!s.N)
     return;
   if (model == RTP_MODEL_CLOUDS)
-    vorticityKernel<TRAV_CLOUDS><<<nbBlocks(s.N), NB_THREADS, 0, st>>>(s, g, c, pred, nbrMode, epoch);
+    launchPdl(vorticityKernel<TRAV_CLOUDS>, nbBlocks(s.N), NB_THREADS, st, s, g, c, pred, nbrMode, epoch);
   else
-    vorticityKernel<TRAV_FLUIDS><<<nbBlocks(s.N), NB_THREADS, 0, st>>>(s, g, c, pred, nbrMode, epoch);
+    launchPdl(vorticityKernel<TRAV_FLUIDS>, nbBlocks(s.N), NB_THREADS, st, s, g, c, pred, nbrMode, epoch);
 }
 void launchConfinement(const DeviceState& s, int model, const GridParams& g, const SphConsts& c, const FluidStepParams& p,
     const float4* pred, int nbrMode, int epoch, cudaStream_t st)
@@ -560,9 +578,9 @@ void launchConfinement(const DeviceState& s, int model, const GridParams& g, con
   if (!s.N)
     return;
   if (model == RTP_MODEL_CLOUDS)
-    confinementKernel<TRAV_CLOUDS><<<nbBlocks(s.N), NB_THREADS, 0, st>>>(s, g, c, p.f.vorticityConfCoeff, p.f.timeStep, pred, nbrMode, epoch);
+    launchPdl(confinementKernel<TRAV_CLOUDS>, nbBlocks(s.N), NB_THREADS, st, s, g, c, p.f.vorticityConfCoeff, p.f.timeStep, pred, nbrMode, epoch);
   else
-    confinementKernel<TRAV_FLUIDS><<<nbBlocks(s.N), NB_THREADS, 0, st>>>(s, g, c, p.f.vorticityConfCoeff, p.f.timeStep, pred, nbrMode, epoch);
+    launchPdl(confinementKernel<TRAV_FLUIDS>, nbBlocks(s.N), NB_THREADS, st, s, g, c, p.f.vorticityConfCoeff, p.f.timeStep, pred, nbrMode, epoch);
 }
 void launchXsph(const DeviceState& s, int model, const GridParams& g, const SphConsts& c, const FluidStepParams& p,
     const rtp_cloud_params&, const float4* pred, int nbrMode, int epoch, cudaStream_t st)
@@ -570,42 +588,79 @@ void launchXsph(const DeviceState& s, int model, const GridParams& g, const SphC
   if (!s.N)
     return;
   if (model == RTP_MODEL_CLOUDS)
-    xsphKernel<TRAV_CLOUDS><<<nbBlocks(s.N), NB_THREADS, 0, st>>>(s, g, c, p.f.xsphViscosityCoeff, pred, nbrMode, epoch);
+    launchPdl(xsphKernel<TRAV_CLOUDS>, nbBlocks(s.N), NB_THREADS, st, s, g, c, p.f.xsphViscosityCoeff, pred, nbrMode, epoch);
   else
-    xsphKernel<TRAV_FLUIDS><<<nbBlocks(s.N), NB_THREADS, 0, st>>>(s, g, c, p.f.xsphViscosityCoeff, pred, nbrMode, epoch);
+    launchPdl(xsphKernel<TRAV_FLUIDS>, nbBlocks(s.N), NB_THREADS, st, s, g, c, p.f.xsphViscosityCoeff, pred, nbrMode, epoch);
 }
 void launchCloudsInitFields(const DeviceState& s, const GridParams& g, const rtp_cloud_params& cloud, cudaStream_t st)
 {
-  cloudsInitFieldsKernel<<<ewBlocks(s.M), EW_THREADS, 0, st>>>(s, g, cloud.initVaporDensityCoeff);
+  launchPdl(cloudsInitFieldsKernel, ewBlocks(s.M), EW_THREADS, st, s, g, cloud.initVaporDensityCoeff);
 }
 void launchCloudsThermoPredict(const DeviceState& s, const GridParams& g, const rtp_cloud_params& cloud, u32* keysOut, cudaStream_t st)
 {
-  cloudsThermoPredictKernel<<<ewBlocks(max(s.N, g.numCells)), EW_THREADS, 0, st>>>(s, g, cloud, keysOut);
+  launchPdl(cloudsThermoPredictKernel, ewBlocks(max(s.N, g.numCells)), EW_THREADS, st, s, g, cloud, keysOut);
 }
 void launchCloudsGather(const DeviceState& s, const GridParams& g, cudaStream_t st)
 {
   if (s.N)
-    cloudsGatherKernel<<<ewBlocks(s.N), EW_THREADS, 0, st>>>(s, g);
+    launchPdl(cloudsGatherKernel, ewBlocks(s.N), EW_THREADS, st, s, g);
 }
 void launchCloudsLaplacianTemp(const DeviceState& s, const GridParams& g, const SphConsts& c, const rtp_cloud_params& cloud, int nbrMode, cudaStream_t st)
 {
   if (s.N)
-    laplacianTempKernel<<<nbBlocks(s.N), NB_THREADS, 0, st>>>(s, g, c, cloud.restDensity, nbrMode);
+    launchPdl(laplacianTempKernel, nbBlocks(s.N), NB_THREADS, st, s, g, c, cloud.restDensity, nbrMode);
 }
 void launchCloudsLambdaTemp(const DeviceState& s, const GridParams& g, const SphConsts& c, const rtp_cloud_params& cloud, int nbrMode, cudaStream_t st)
 {
   if (s.N)
-    lambdaTempKernel<<<nbBlocks(s.N), NB_THREADS, 0, st>>>(s, g, c, cloud.restDensity, cloud.relaxCFM, nbrMode);
+    launchPdl(lambdaTempKernel, nbBlocks(s.N), NB_THREADS, st, s, g, c, cloud.restDensity, cloud.relaxCFM, nbrMode);
 }
 void launchCloudsCorrectTemp(const DeviceState& s, const GridParams& g, const SphConsts& c, const rtp_cloud_params& cloud, int nbrMode, cudaStream_t st)
 {
   if (s.N)
-    correctTempKernel<<<nbBlocks(s.N), NB_THREADS, 0, st>>>(s, g, c, cloud.restDensity, nbrMode);
+    launchPdl(correctTempKernel, nbBlocks(s.N), NB_THREADS, st, s, g, c, cloud.restDensity, nbrMode);
 }
 void launchCloudsFinish(const DeviceState& s, const GridParams& g, const rtp_cloud_params& cloud, const float4* pred, bool copyVel, cudaStream_t st)
 {
   if (s.N)
-    cloudsFinishKernel<<<ewBlocks(s.N), EW_THREADS, 0, st>>>(s, g, cloud, pred, copyVel ? 1 : 0);
+    launchPdl(cloudsFinishKernel, ewBlocks(s.N), EW_THREADS, st, s, g, cloud, pred, copyVel ? 1 : 0);
+}
+
+// ---- diagnostics: how the margin / hit lists of the last step would serve a sweep at the final predicted positions
+__global__ void __launch_bounds__(EW_THREADS) listStatsKernel(DeviceState s, GridParams g, SphConsts c, const float4* __restrict__ pred,
+    unsigned long long* __restrict__ out)
+{
+  RTP_PDL_PROLOGUE();
+  const u32 i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= s.N)
+    return;
+  const float4 pi = pred[i];
+  const int3 ci = cell3D(g, pi.x, pi.y, pi.z);
+  const u32 raw = s.nbrCount[i];
+  const float4 bp = s.nbrBuildPos[i];
+  const int3 cb = cell3D(g, bp.x, bp.y, bp.z);
+  atomicAdd(out + 0, 1ull);
+  if (raw == NBR_OVERFLOW)
+    atomicAdd(out + 1, 1ull);
+  else
+  {
+    atomicAdd(out + 4, (unsigned long long)raw);
+    atomicMax(out + 5, (unsigned long long)raw);
+  }
+  if (cb.x != ci.x || cb.y != ci.y || cb.z != ci.z)
+  {
+    atomicAdd(out + 2, 1ull);
+  }
+  if (s.hitCount[i] == NBR_OVERFLOW)
+    atomicAdd(out + 6, 1ull);
+  const float dx = pi.x - bp.x, dy = pi.y - bp.y, dz = pi.z - bp.z;
+  if (!(dx * dx + dy * dy + dz * dz <= c.nbrDmaxSq))
+    atomicAdd(out + 7, 1ull);
+}
+void launchListStats(const DeviceState& s, const GridParams& g, const SphConsts& c, const float4* pred, unsigned long long* out, cudaStream_t st)
+{
+  if (s.N)
+    launchPdl(listStatsKernel, ewBlocks(s.N), EW_THREADS, st, s, g, c, pred, out);
 }
 
 } // namespace rtp

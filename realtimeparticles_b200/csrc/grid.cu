@@ -11,6 +11,7 @@ static inline int ewBlocks(size_t n) { return (int)((n + EW_THREADS - 1) / EW_TH
 __global__ void __launch_bounds__(EW_THREADS) resetIdsKernel(u32* __restrict__ cellID, u32* __restrict__ cameraDist,
     u32* __restrict__ perm, u32* __restrict__ cameraPerm, u32 M, u32 numCells)
 {
+  RTP_PDL_PROLOGUE();
   const u32 i = blockIdx.x * EW_THREADS + threadIdx.x;
   if (i >= M)
     return;
@@ -23,6 +24,7 @@ __global__ void __launch_bounds__(EW_THREADS) resetIdsKernel(u32* __restrict__ c
 // adjustEndCell grid.cl:143-152
 __global__ void __launch_bounds__(EW_THREADS) adjustEndCellKernel(uint2* __restrict__ table, u32 numCells, u32 cap)
 {
+  RTP_PDL_PROLOGUE();
   const u32 c = blockIdx.x * EW_THREADS + threadIdx.x;
   if (c >= numCells)
     return;
@@ -35,6 +37,7 @@ __global__ void __launch_bounds__(EW_THREADS) adjustEndCellKernel(uint2* __restr
 __global__ void __launch_bounds__(EW_THREADS) fillCameraDistKernel(const float4* __restrict__ pos, float cx, float cy, float cz,
     u32* __restrict__ keys, u32 N)
 {
+  RTP_PDL_PROLOGUE();
   const u32 i = blockIdx.x * EW_THREADS + threadIdx.x;
   if (i >= N)
     return;
@@ -49,6 +52,7 @@ __global__ void __launch_bounds__(EW_THREADS) fillCameraDistKernel(const float4*
 __global__ void __launch_bounds__(EW_THREADS) cameraGatherKernel(DeviceState s, int model, const float4* __restrict__ pred,
     float4* __restrict__ predOut)
 {
+  RTP_PDL_PROLOGUE();
   const u32 i = blockIdx.x * EW_THREADS + threadIdx.x;
   if (i >= s.N)
     return;
@@ -77,6 +81,7 @@ __global__ void __launch_bounds__(EW_THREADS) cameraGatherKernel(DeviceState s, 
 // resetGridDetector / fillGridDetector grid.cl:43-60 (float8 per cell)
 __global__ void __launch_bounds__(EW_THREADS) resetGridDetectorKernel(float4* __restrict__ det, u32 n4)
 {
+  RTP_PDL_PROLOGUE();
   const u32 i = blockIdx.x * EW_THREADS + threadIdx.x;
   if (i < n4)
     det[i] = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -84,6 +89,7 @@ __global__ void __launch_bounds__(EW_THREADS) resetGridDetectorKernel(float4* __
 __global__ void __launch_bounds__(EW_THREADS) fillGridDetectorKernel(const float4* __restrict__ pos, GridParams g,
     float4* __restrict__ det, u32 N)
 {
+  RTP_PDL_PROLOGUE();
   const u32 i = blockIdx.x * EW_THREADS + threadIdx.x;
   if (i >= N)
     return;
@@ -100,6 +106,7 @@ __global__ void __launch_bounds__(EW_THREADS) fillGridDetectorKernel(const float
 __global__ void __launch_bounds__(EW_THREADS) fillFluidColorKernel(const float* __restrict__ density, float restDensity,
     float4* __restrict__ col, u32 N)
 {
+  RTP_PDL_PROLOGUE();
   const u32 i = blockIdx.x * EW_THREADS + threadIdx.x;
   if (i >= N)
     return;
@@ -128,6 +135,7 @@ __global__ void __launch_bounds__(EW_THREADS) fillFluidColorKernel(const float* 
 __global__ void __launch_bounds__(EW_THREADS) fillColorFloatKernel(const float* __restrict__ q, float minVal, float maxVal,
     float4* __restrict__ col, u32 N)
 {
+  RTP_PDL_PROLOGUE();
   const u32 i = blockIdx.x * EW_THREADS + threadIdx.x;
   if (i >= N)
     return;
@@ -141,6 +149,7 @@ __global__ void __launch_bounds__(EW_THREADS) fillColorFloatKernel(const float* 
 // bit pattern lies in [lo, hi]
 __global__ void __launch_bounds__(EW_THREADS) selftestMathKernel(u32 lo, u32 hi, unsigned long long* __restrict__ bad)
 {
+  RTP_PDL_PROLOGUE();
   unsigned long long badSqrt = 0, badRcp = 0;
   for (unsigned long long b = (unsigned long long)lo + blockIdx.x * (unsigned long long)EW_THREADS + threadIdx.x; b <= hi;
        b += (unsigned long long)gridDim.x * EW_THREADS)
@@ -156,19 +165,21 @@ __global__ void __launch_bounds__(EW_THREADS) selftestMathKernel(u32 lo, u32 hi,
 }
 void launchSelftestMath(u32 lo, u32 hi, unsigned long long* bad, cudaStream_t st)
 {
-  selftestMathKernel<<<148 * 8, EW_THREADS, 0, st>>>(lo, hi, bad);
+  launchPdl(selftestMathKernel, 148 * 8, EW_THREADS, st, lo, hi, bad);
 }
 
 // slab decomposition: drop the ghost copies after a step. Keys = "is ghost" (1 bit) -> one stable radix pass gives the
 // owned particles first, in their cell-sorted order; then the state is gathered through that permutation.
 __global__ void __launch_bounds__(EW_THREADS) ghostFlagKernel(const u32* __restrict__ perm, u32 nOwned, u32* __restrict__ keys, u32 N)
 {
+  RTP_PDL_PROLOGUE();
   const u32 i = blockIdx.x * EW_THREADS + threadIdx.x;
   if (i < N)
     keys[i] = perm[i] >= nOwned ? 1u : 0u;
 }
 __global__ void __launch_bounds__(EW_THREADS) compactGatherKernel(DeviceState s, const u32* __restrict__ order, u32 n)
 {
+  RTP_PDL_PROLOGUE();
   const u32 i = blockIdx.x * EW_THREADS + threadIdx.x;
   if (i >= n)
     return;
@@ -179,47 +190,47 @@ __global__ void __launch_bounds__(EW_THREADS) compactGatherKernel(DeviceState s,
 void launchGhostFlags(const DeviceState& s, u32* keysOut, cudaStream_t st)
 {
   if (s.N)
-    ghostFlagKernel<<<ewBlocks(s.N), EW_THREADS, 0, st>>>(s.perm, s.nOwned, keysOut, s.N);
+    launchPdl(ghostFlagKernel, ewBlocks(s.N), EW_THREADS, st, s.perm, s.nOwned, keysOut, s.N);
 }
 void launchCompactGather(const DeviceState& s, const u32* order, u32 n, cudaStream_t st)
 {
   if (n)
-    compactGatherKernel<<<ewBlocks(n), EW_THREADS, 0, st>>>(s, order, n);
+    launchPdl(compactGatherKernel, ewBlocks(n), EW_THREADS, st, s, order, n);
 }
 
 void launchResetIds(const DeviceState& s, u32 numCells, cudaStream_t st)
 {
-  resetIdsKernel<<<ewBlocks(s.M), EW_THREADS, 0, st>>>(s.cellID, s.cameraDist, s.perm, s.cameraPerm, s.M, numCells);
+  launchPdl(resetIdsKernel, ewBlocks(s.M), EW_THREADS, st, s.cellID, s.cameraDist, s.perm, s.cameraPerm, s.M, numCells);
 }
 void launchAdjustEndCell(const DeviceState& s, const GridParams& g, cudaStream_t st)
 {
-  adjustEndCellKernel<<<ewBlocks(g.numCells), EW_THREADS, 0, st>>>(s.table, g.numCells, g.maxPartsInCell);
+  launchPdl(adjustEndCellKernel, ewBlocks(g.numCells), EW_THREADS, st, s.table, g.numCells, g.maxPartsInCell);
 }
 void launchFillCameraDist(const DeviceState& s, const float cam[3], u32* keysOut, cudaStream_t st)
 {
   if (s.N)
-    fillCameraDistKernel<<<ewBlocks(s.N), EW_THREADS, 0, st>>>(s.posA, cam[0], cam[1], cam[2], keysOut, s.N);
+    launchPdl(fillCameraDistKernel, ewBlocks(s.N), EW_THREADS, st, s.posA, cam[0], cam[1], cam[2], keysOut, s.N);
 }
 void launchCameraGather(const DeviceState& s, int model, const float4* pred, float4* predOut, cudaStream_t st)
 {
   if (s.N)
-    cameraGatherKernel<<<ewBlocks(s.N), EW_THREADS, 0, st>>>(s, model, pred, predOut);
+    launchPdl(cameraGatherKernel, ewBlocks(s.N), EW_THREADS, st, s, model, pred, predOut);
 }
 void launchGridDetector(const DeviceState& s, const GridParams& g, cudaStream_t st)
 {
-  resetGridDetectorKernel<<<ewBlocks((size_t)g.numCells * 2), EW_THREADS, 0, st>>>((float4*)s.partDetector, g.numCells * 2);
+  launchPdl(resetGridDetectorKernel, ewBlocks((size_t)g.numCells * 2), EW_THREADS, st, (float4*)s.partDetector, g.numCells * 2);
   if (s.N)
-    fillGridDetectorKernel<<<ewBlocks(s.N), EW_THREADS, 0, st>>>(s.posA, g, (float4*)s.partDetector, s.N);
+    launchPdl(fillGridDetectorKernel, ewBlocks(s.N), EW_THREADS, st, s.posA, g, (float4*)s.partDetector, s.N);
 }
 void launchFillFluidColor(const DeviceState& s, float restDensity, cudaStream_t st)
 {
   if (s.N)
-    fillFluidColorKernel<<<ewBlocks(s.N), EW_THREADS, 0, st>>>(s.density, restDensity, s.col, s.N);
+    launchPdl(fillFluidColorKernel, ewBlocks(s.N), EW_THREADS, st, s.density, restDensity, s.col, s.N);
 }
 void launchFillColorFloat(const DeviceState& s, const float* quantity, float minVal, float maxVal, cudaStream_t st)
 {
   if (s.N)
-    fillColorFloatKernel<<<ewBlocks(s.N), EW_THREADS, 0, st>>>(quantity, minVal, maxVal, s.col, s.N);
+    launchPdl(fillColorFloatKernel, ewBlocks(s.N), EW_THREADS, st, quantity, minVal, maxVal, s.col, s.N);
 }
 
 } // namespace rtp

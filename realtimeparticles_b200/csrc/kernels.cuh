@@ -107,4 +107,5 @@ void launchCloudsLambdaTemp(const DeviceState& s, const GridParams& g, const Sph
 void launchCloudsCorrectTemp(const DeviceState& s, const GridParams& g, const SphConsts& c, const rtp_cloud_params& cloud, int nbrMode, cudaStream_t st);
 void launchCloudsFinish(const DeviceState& s, const GridParams& g, const rtp_cloud_params& cloud, const float4* pred, bool smoothing, cudaStream_t st);
 
+void launchListStats(const DeviceState& s, const GridParams& g, const SphConsts& c, const float4* pred, unsigned long long* out, cudaStream_t st);
 } // namespace rtp

@@ -38,7 +38,7 @@ struct rtp_handle
   SortPlan cellPlan, camPlan;
   float4* predFinal = nullptr;
   float4* shardCur = nullptr; // slab decomposition: prediction buffer the next stage reads
-  float nbrMargin = 0.2f; // RTP_NBR_MARGIN
+  float nbrMargin = 0.15f; // RTP_NBR_MARGIN
   bool nbrEnabled = true; // RTP_NBR_LISTS=0 disables the lists (plain 27-cell traversal in every sweep)
   std::vector<void*> allocs;
   std::string err;
@@ -296,6 +296,9 @@ extern "C" int rtp_create(const rtp_config* cfg, rtp_handle** out)
     CREATE_TRY(devAlloc(h, &s.lambda, M));
     CREATE_TRY(devAlloc(h, &s.vortNorm, M));
     h->predFinal = s.pred0;
+    // list entries keep 28 bits for the particle index (sweep.cuh)
+    if (M > (1u << 28))
+      h->nbrEnabled = false;
     if (h->nbrEnabled)
     {
       u32 cap = 256;
@@ -1064,6 +1067,25 @@ extern "C" int rtp_get_stage_times(rtp_handle* h, const char** names, float* ms,
       ms[i] = h->stageMs[i];
   }
   return n;
+}
+
+extern "C" int rtp_list_stats(rtp_handle* h, unsigned long long out[8])
+{
+  if (!h || !out)
+    return RTP_ERR_INVALID;
+  for (int k = 0; k < 8; ++k)
+    out[k] = 0ull;
+  if (!h->nbrEnabled || !h->s.nbrCount)
+    return RTP_OK;
+  unsigned long long* d = nullptr;
+  if (cudaMalloc(&d, 64) != cudaSuccess)
+    return RTP_ERR_CUDA;
+  cudaMemsetAsync(d, 0, 64, h->stream);
+  launchListStats(h->s, h->g, h->c, h->predFinal, d, h->stream);
+  cudaMemcpyAsync(out, d, 64, cudaMemcpyDeviceToHost, h->stream);
+  const cudaError_t e = cudaStreamSynchronize(h->stream);
+  cudaFree(d);
+  return e == cudaSuccess ? RTP_OK : RTP_ERR_CUDA;
 }
 
 extern "C" int rtp_last_launch_count(const rtp_handle* h) { return h ? h->lastLaunches : 0; }

@@ -21,6 +21,47 @@ namespace rtp
 {
 typedef uint32_t u32;
 
+// Programmatic dependent launch (sm_90+), compile-time option RTP_USE_PDL: 0 = plain stream order (default: measured
+// fastest on the 130k step), 1 = every kernel lets its successor start launching CTAs at once and
+// waits for its predecessor's memory (cudaGridDependencySynchronize), 2 = wait only (the successor is released when the
+// predecessor's CTAs have exited). All launches go through launchPdl(), also inside a captured CUDA graph.
+#ifndef RTP_USE_PDL
+#define RTP_USE_PDL 0
+#endif
+#if RTP_USE_PDL == 1
+#define RTP_PDL_PROLOGUE()                     \
+  do                                           \
+  {                                            \
+    cudaTriggerProgrammaticLaunchCompletion(); \
+    cudaGridDependencySynchronize();           \
+  } while (0)
+#elif RTP_USE_PDL == 2
+#define RTP_PDL_PROLOGUE() cudaGridDependencySynchronize()
+#else
+#define RTP_PDL_PROLOGUE() \
+  do                       \
+  {                        \
+  } while (0)
+#endif
+
+template <typename... P, typename... A>
+inline void launchPdl(void (*kernel)(P...), unsigned grid, unsigned block, cudaStream_t st, A&&... args)
+{
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(grid, 1, 1);
+  cfg.blockDim = dim3(block, 1, 1);
+  cfg.dynamicSmemBytes = 0;
+  cfg.stream = st;
+#if RTP_USE_PDL
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+#endif
+  cudaLaunchKernelEx(&cfg, kernel, static_cast<P>(args)...);
+}
+
 #define RTP_FLOAT_EPS 0.00000001f // define.cl:6
 #define RTP_ABS_GRAVITY_ACC_Y 9.81f // define.cl:8
 #define RTP_FAR_DIST 1000000.0f // define.cl:10

@@ -47,6 +47,7 @@ struct PassDesc
 __global__ void __launch_bounds__(SORT_THREADS) sortHistogramKernel(const u32* __restrict__ keys, u32 n, int passes,
     PassDesc desc, u32* __restrict__ ctrl, u32* __restrict__ status, size_t statusWords)
 {
+  RTP_PDL_PROLOGUE();
   __shared__ u32 sHist[SORT_MAX_PASSES * SORT_RADIX];
   const int tid = threadIdx.x, lane = tid & 31;
   for (int i = tid; i < passes * SORT_RADIX; i += SORT_THREADS)
@@ -80,6 +81,7 @@ __global__ void __launch_bounds__(SORT_THREADS) onesweepPassKernel(const u32* __
     u32* __restrict__ kout, u32* __restrict__ vout, u32 n, int shift, u32 mask, const u32* __restrict__ ghist,
     u32* __restrict__ status, u32* __restrict__ ticket)
 {
+  RTP_PDL_PROLOGUE();
   constexpr int TILE = SORT_THREADS * ITEMS;
   __shared__ u32 sWarpHist[SORT_WARPS][SORT_RADIX];
   __shared__ u32 sKeys[TILE];
@@ -234,7 +236,7 @@ int enqueueSort(const SortPlan& plan, u32* keys0, u32* vals0, u32* keys1, u32* v
       blocks = 148 * 8;
     if (blocks < 1)
       blocks = 1;
-    sortHistogramKernel<<<blocks, SORT_THREADS, 0, stream>>>(kbuf[first], plan.n, plan.passes, desc, ctrl, status,
+    launchPdl(sortHistogramKernel, blocks, SORT_THREADS, stream, kbuf[first], plan.n, plan.passes, desc, ctrl, status,
         sortStatusWords(plan));
     ++launches;
   }
@@ -247,10 +249,10 @@ int enqueueSort(const SortPlan& plan, u32* keys0, u32* vals0, u32* keys1, u32* v
     u32* ticket = ctrl + SORT_MAX_PASSES * SORT_RADIX + p;
     const u32* gh = ctrl + p * SORT_RADIX;
     if (plan.itemsPerThread == 4)
-      onesweepPassKernel<4><<<plan.tiles, SORT_THREADS, 0, stream>>>(kbuf[src], vin, kbuf[dst], vbuf[dst], plan.n,
+      launchPdl(onesweepPassKernel<4>, plan.tiles, SORT_THREADS, stream, kbuf[src], vin, kbuf[dst], vbuf[dst], plan.n,
           desc.shift[p], desc.mask[p], gh, st, ticket);
     else
-      onesweepPassKernel<16><<<plan.tiles, SORT_THREADS, 0, stream>>>(kbuf[src], vin, kbuf[dst], vbuf[dst], plan.n,
+      launchPdl(onesweepPassKernel<16>, plan.tiles, SORT_THREADS, stream, kbuf[src], vin, kbuf[dst], vbuf[dst], plan.n,
           desc.shift[p], desc.mask[p], gh, st, ticket);
     ++launches;
   }
