@@ -20,6 +20,9 @@
 // Numerics: bit-exact with the oracle everywhere. Hit tests, element-wise stages and the per-pair terms use the
 // canonical operation sequence (rtp_common.cuh, DESIGN.md "Canonical arithmetic"); sums run in the reference's
 // order (27 cells, ascending e, one fp32 accumulator per component).
+#include <algorithm>
+#include <cstdlib>
+
 #include "kernels.cuh"
 #include "sweep.cuh"
 
@@ -74,7 +77,11 @@ __global__ void __launch_bounds__(EW_THREADS) fluidPredictKernel(DeviceState s, 
   if (i < g.numCells)
     s.table[i] = make_uint2(1u, 0u);
   if (i < NBR_EPOCHS && s.nbrInvalid)
+  {
     s.nbrInvalid[i] = 0u;
+    s.stragCount[i] = 0u;
+    s.stragCursor[i] = 0u;
+  }
   if (i >= s.N)
     return;
   const float4 p = s.posA[i], v = s.velA[i];
@@ -172,7 +179,11 @@ __global__ void __launch_bounds__(EW_THREADS) cloudsThermoPredictKernel(DeviceSt
   if (i < g.numCells)
     s.table[i] = make_uint2(1u, 0u);
   if (i < NBR_EPOCHS && s.nbrInvalid)
+  {
     s.nbrInvalid[i] = 0u;
+    s.stragCount[i] = 0u;
+    s.stragCursor[i] = 0u;
+  }
   if (i >= s.N)
     return;
   const float4 p = s.posA[i], v = s.velA[i];
@@ -255,28 +266,35 @@ __global__ void __launch_bounds__(NB_THREADS, NB_MIN_BLOCKS) densityLambdaKernel
     const float4* __restrict__ pred, int nbrMode, int epoch)
 {
   RTP_PDL_PROLOGUE();
-  const u32 i = blockIdx.x * NB_THREADS + threadIdx.x;
-  if (i >= s.N)
-    return;
-  const float4 pi = pred[i];
-  float density = 0.f, gx = 0.f, gy = 0.f, gz = 0.f, sumG2 = 0.f;
-  sweepProducer<TRAV>(g, c, s, pred, pi, i, nbrMode, epoch,
-      [&](u32, float dx, float dy, float dz, float sq) -> float
+  producerLoop(s, nbrMode, epoch,
+      [&](const u32 i, const bool strag) -> int
       {
-        density = fadd(density, fmul(c.poly6, poly6nc(c, sq)));
-        const float cs = spikyCoefOrZero(c, sq);
-        gx = ffma(dx, cs, gx);
-        gy = ffma(dy, cs, gy);
-        gz = ffma(dz, cs, gz);
-        sumG2 = fadd(sumG2, fmul(fmul(cs, cs), sq));
-        return cs;
+        const float4 pi = pred[i];
+        float density = 0.f, gx = 0.f, gy = 0.f, gz = 0.f, sumG2 = 0.f;
+        const int r = sweepProducer<TRAV>(g, c, s, pred, pi, i, nbrMode, epoch, strag,
+            [&](u32, float dx, float dy, float dz, float sq)
+            {
+              const float cs = spikyCoefOrZero(c, sq);
+              return PairTerm<6> { { fmul(c.poly6, poly6nc(c, sq)), cs, dx, dy, dz, fmul(fmul(cs, cs), sq) } };
+            },
+            [&](const PairTerm<6>& t)
+            {
+              density = fadd(density, t.v[0]);
+              gx = ffma(t.v[2], t.v[1], gx);
+              gy = ffma(t.v[3], t.v[1], gy);
+              gz = ffma(t.v[4], t.v[1], gz);
+              sumG2 = fadd(sumG2, t.v[5]);
+            });
+        if (r != SWEEP_DONE)
+          return r;
+        s.density[i] = density;
+        // fluids.cl:189-192
+        const float densityC = fsub(fdiv(density, rho0), 1.0f);
+        float ssg = fadd(sumG2, dot3c(gx, gy, gz, gx, gy, gz));
+        ssg = fdiv(ssg, fmul(rho0, rho0));
+        s.lambda[i] = fdiv(-densityC, fadd(ssg, cfm));
+        return (int)SWEEP_DONE;
       });
-  s.density[i] = density;
-  // fluids.cl:189-192
-  const float densityC = fsub(fdiv(density, rho0), 1.0f);
-  float ssg = fadd(sumG2, dot3c(gx, gy, gz, gx, gy, gz));
-  ssg = fdiv(ssg, fmul(rho0, rho0));
-  s.lambda[i] = fdiv(-densityC, fadd(ssg, cfm));
 }
 
 template <int TRAV, bool LAST>
@@ -362,7 +380,12 @@ __global__ void __launch_bounds__(NB_THREADS, NB_MIN_BLOCKS) correctionKernel(De
     }
   }
   if (nbrMode != NBR_OFF)
+  {
     checkListValidity<TRAV>(g, c, s, i, np, epoch + 1);
+    // the next producer sweep (epoch + 1) cannot use this particle's margin list: straggler queue (sweep.cuh)
+    if (usableMarginList(g, s, cell3D(g, np.x, np.y, np.z), i, NBR_USE, false) == NBR_OVERFLOW)
+      pushStraggler(s, epoch + 1, i);
+  }
 }
 
 template <int TRAV>
@@ -370,27 +393,34 @@ __global__ void __launch_bounds__(NB_THREADS, NB_MIN_BLOCKS) vorticityKernel(Dev
     int nbrMode, int epoch)
 {
   RTP_PDL_PROLOGUE();
-  const u32 i = blockIdx.x * NB_THREADS + threadIdx.x;
-  if (i >= s.N)
-    return;
-  const float4 pi = pred[i];
   const float4* __restrict__ V = s.velB;
-  const float4 vi = V[i];
-  float wx = 0.f, wy = 0.f, wz = 0.f;
-  sweepProducer<TRAV>(g, c, s, pred, pi, i, nbrMode, epoch,
-      [&](u32 e, float dx, float dy, float dz, float sq) -> float
+  producerLoop(s, nbrMode, epoch,
+      [&](const u32 i, const bool strag) -> int
       {
-        const float cs = spikyCoefOrZero(c, sq);
-        const float4 vj = ld4(V, e);
-        const float ax = fsub(vj.x, vi.x), ay = fsub(vj.y, vi.y), az = fsub(vj.z, vi.z);
-        // cross(dv, vec * c) = cross(dv, vec) * c, cross(a,b).x = fma(a.y, b.z, -(a.z * b.y))
-        wx = ffma(ffma(ay, dz, -fmul(az, dy)), cs, wx);
-        wy = ffma(ffma(az, dx, -fmul(ax, dz)), cs, wy);
-        wz = ffma(ffma(ax, dy, -fmul(ay, dx)), cs, wz);
-        return cs;
+        const float4 pi = pred[i];
+        const float4 vi = V[i];
+        float wx = 0.f, wy = 0.f, wz = 0.f;
+        const int r = sweepProducer<TRAV>(g, c, s, pred, pi, i, nbrMode, epoch, strag,
+            [&](u32 e, float dx, float dy, float dz, float sq)
+            {
+              const float cs = spikyCoefOrZero(c, sq);
+              const float4 vj = ld4(V, e);
+              const float ax = fsub(vj.x, vi.x), ay = fsub(vj.y, vi.y), az = fsub(vj.z, vi.z);
+              // cross(dv, vec * c) = cross(dv, vec) * c, cross(a,b).x = fma(a.y, b.z, -(a.z * b.y))
+              return PairTerm<4> { { ffma(ay, dz, -fmul(az, dy)), ffma(az, dx, -fmul(ax, dz)), ffma(ax, dy, -fmul(ay, dx)), cs } };
+            },
+            [&](const PairTerm<4>& t)
+            {
+              wx = ffma(t.v[0], t.v[3], wx);
+              wy = ffma(t.v[1], t.v[3], wy);
+              wz = ffma(t.v[2], t.v[3], wz);
+            });
+        if (r != SWEEP_DONE)
+          return r;
+        s.vort[i] = make_float4(wx, wy, wz, 0.0f);
+        s.vortNorm[i] = fsqrt(dot3c(wx, wy, wz, wx, wy, wz)); // fast_length(vort[e]) of the next sweep
+        return (int)SWEEP_DONE;
       });
-  s.vort[i] = make_float4(wx, wy, wz, 0.0f);
-  s.vortNorm[i] = fsqrt(dot3c(wx, wy, wz, wx, wy, wz)); // fast_length(vort[e]) of the next sweep
 }
 
 template <int TRAV>
@@ -458,22 +488,26 @@ __global__ void __launch_bounds__(NB_THREADS, NB_MIN_BLOCKS) xsphKernel(DeviceSt
 __global__ void __launch_bounds__(NB_THREADS, NB_MIN_BLOCKS) laplacianTempKernel(DeviceState s, GridParams g, SphConsts c, float rho0, int nbrMode)
 {
   RTP_PDL_PROLOGUE();
-  const u32 i = blockIdx.x * NB_THREADS + threadIdx.x;
-  if (i >= s.N)
-    return;
-  const float4 pi = s.posB[i];
   const float* __restrict__ T = s.tempB;
-  const float Ti = T[i];
-  float lap = 0.f;
-  sweepProducer<TRAV_CLOUDS>(g, c, s, s.posB, pi, i, nbrMode, NBR_EPOCH_TEMP,
-      [&](u32 e, float, float, float, float sq) -> float
+  producerLoop(s, nbrMode, NBR_EPOCH_TEMP,
+      [&](const u32 i, const bool strag) -> int
       {
-        const float cs = spikyCoefOrZero(c, sq);
-        // dot(vec, grad) = c * sq ; x / d = x * (1/d)
-        lap = ffma(fmul(fsub(Ti, __ldg(T + e)), fmul(cs, sq)), rcpInRange(fadd(sq, RTP_FLOAT_EPS)), lap);
-        return cs;
+        const float4 pi = s.posB[i];
+        const float Ti = T[i];
+        float lap = 0.f;
+        const int r = sweepProducer<TRAV_CLOUDS>(g, c, s, s.posB, pi, i, nbrMode, NBR_EPOCH_TEMP, strag,
+            [&](u32 e, float, float, float, float sq)
+            {
+              const float cs = spikyCoefOrZero(c, sq);
+              // dot(vec, grad) = c * sq ; x / d = x * (1/d)
+              return PairTerm<2> { { fmul(fsub(Ti, __ldg(T + e)), fmul(cs, sq)), rcpInRange(fadd(sq, RTP_FLOAT_EPS)) } };
+            },
+            [&](const PairTerm<2>& t) { lap = ffma(t.v[0], t.v[1], lap); });
+        if (r != SWEEP_DONE)
+          return r;
+        s.lapTemp[i] = fdiv(lap, rho0);
+        return (int)SWEEP_DONE;
       });
-  s.lapTemp[i] = fdiv(lap, rho0);
 }
 
 // cld_computeConstraintFactorTemp clouds.cl:575-648

@@ -36,6 +36,7 @@ struct DeviceState
   u32 nbrStride = 0, nbrCap = 0;
   // per-epoch hit lists (sweep.cuh), same row layout
   u32 *hitList = nullptr, *hitCount = nullptr;
+  u32 *stragQueue = nullptr, *stragCount = nullptr, *stragCursor = nullptr; // straggler queue of the producer sweeps (sweep.cuh), counters per epoch
   u32 hitCap = 0;
 };
 

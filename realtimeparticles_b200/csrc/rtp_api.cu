@@ -318,6 +318,9 @@ extern "C" int rtp_create(const rtp_config* cfg, rtp_handle** out)
       s.hitCap = hcap;
       CREATE_TRY(devAlloc(h, &s.hitList, (size_t)hcap * M));
       CREATE_TRY(devAlloc(h, &s.hitCount, M));
+      CREATE_TRY(devAlloc(h, &s.stragQueue, M));
+      CREATE_TRY(devAlloc(h, &s.stragCount, (size_t)NBR_EPOCHS));
+      CREATE_TRY(devAlloc(h, &s.stragCursor, (size_t)NBR_EPOCHS));
     }
   }
   if (model == RTP_MODEL_CLOUDS)
