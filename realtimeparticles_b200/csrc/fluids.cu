@@ -32,7 +32,10 @@ namespace rtp
 #define RTP_NB_THREADS 128
 #endif
 constexpr int NB_THREADS = RTP_NB_THREADS; // neighbour kernels
-constexpr int NB_MIN_BLOCKS = 896 / RTP_NB_THREADS; // 28 resident warps per SM (72 registers per thread)
+#ifndef RTP_NB_WARPS_PER_SM
+#define RTP_NB_WARPS_PER_SM 28 // resident warps per SM the neighbour kernels are compiled for (28: 72 registers per thread)
+#endif
+constexpr int NB_MIN_BLOCKS = RTP_NB_WARPS_PER_SM * 32 / RTP_NB_THREADS;
 constexpr int EW_THREADS = 256; // element-wise kernels
 
 __device__ __forceinline__ void fillCellTable(const u32* __restrict__ keys, u32 i, u32 N, u32 numCells, uint2* __restrict__ table)

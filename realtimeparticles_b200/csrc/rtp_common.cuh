@@ -217,30 +217,21 @@ __device__ __forceinline__ void forEachNeighbourRun(const GridParams& g, const u
   }
 }
 
-// Run body(e, P[e]) for e = start..end in ascending order; positions are fetched one group of four ahead of the
-// group being processed (software pipeline), the bodies still execute strictly in order: sums stay bit-identical.
+// Run body(e, P[e]) for e = start..end in ascending order, four positions fetched per group. (A software pipeline
+// across groups was measured 2% slower: its rotating registers cost four MOVs per candidate in an issue-bound loop,
+// and the resident warps hide an L1 hit anyway.)
 template <typename Body>
 __device__ __forceinline__ void forRangeLoad4(const float4* __restrict__ P, u32 start, u32 end, Body&& body)
 {
   u32 e = start;
-  if (e + 3u <= end)
-  {
-    float4 a0 = __ldg(P + e), a1 = __ldg(P + e + 1), a2 = __ldg(P + e + 2), a3 = __ldg(P + e + 3);
 #pragma unroll 1
-    for (; e + 7u <= end; e += 4u)
-    {
-      const float4 b0 = __ldg(P + e + 4), b1 = __ldg(P + e + 5), b2 = __ldg(P + e + 6), b3 = __ldg(P + e + 7);
-      body(e, a0);
-      body(e + 1, a1);
-      body(e + 2, a2);
-      body(e + 3, a3);
-      a0 = b0; a1 = b1; a2 = b2; a3 = b3;
-    }
+  for (; e + 3u <= end; e += 4u)
+  {
+    const float4 a0 = __ldg(P + e), a1 = __ldg(P + e + 1), a2 = __ldg(P + e + 2), a3 = __ldg(P + e + 3);
     body(e, a0);
     body(e + 1, a1);
     body(e + 2, a2);
     body(e + 3, a3);
-    e += 4u;
   }
 #pragma unroll 1
   for (; e <= end; ++e)
