@@ -404,11 +404,17 @@ def run_ours(args):
                 "whole_step": {"algorithmic_bytes_per_particle": PBF_BYTES_PER_PARTICLE_STEP,
                                "achieved": round(value / world * PBF_BYTES_PER_PARTICLE_STEP / 1e9, 1),
                                "frac": round(value / world * PBF_BYTES_PER_PARTICLE_STEP / 1e9 / peak, 4)},
-                "note": "neighbour sweeps do ~460 pair evaluations per particle on 16-64 B of compulsory traffic: FP32-issue "
-                        "bound, far below the HBM line by construction (SURVEY 8d); traffic = ncu dram bytes, see profiles/"}
+                "note": "neighbour sweeps do ~460 pair evaluations per particle on 16-64 B of compulsory traffic: instruction-"
+                        "issue bound (64-68% of peak issue slots, math-pipe throttled), far below the HBM line by construction "
+                        "(SURVEY 8d); traffic = ncu dram bytes per launch, dominated by the neighbour lists the sweep writes "
+                        "once and later sweeps read instead of re-testing 460 candidates (DESIGN.md section 5)"}
     try:
         with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
-            roofline["traffic"] = json.load(f).get(dom)
+            tj = json.load(f)
+        roofline["traffic"] = tj.get(dom)
+        # what actually bounds the sweeps: warp-instruction issue (ncu smsp__issue_active, committed capture)
+        roofline["issue_active_pct_ncu"] = tj.get("issue_active_pct")
+        roofline["traffic_source"] = tj.get("source")
     except Exception:
         pass
 
