@@ -300,7 +300,8 @@ __global__ void __launch_bounds__(NB_THREADS, NB_MIN_BLOCKS) densityLambdaKernel
       });
 }
 
-template <int TRAV, bool LAST>
+// ART: artificial pressure compiled in as -1 = off, 4 = exponent 4 (the reference's default), 0 = as the parameters say
+template <int TRAV, bool LAST, int ART>
 __global__ void __launch_bounds__(NB_THREADS, NB_MIN_BLOCKS) correctionKernel(DeviceState s, GridParams g, SphConsts c, FluidStepParams fp,
     const float4* __restrict__ pred, float4* __restrict__ predOut, int writeCorr, int nbrMode, int epoch)
 {
@@ -311,8 +312,8 @@ __global__ void __launch_bounds__(NB_THREADS, NB_MIN_BLOCKS) correctionKernel(De
   const float4 pi = pred[i];
   const float* __restrict__ lambda = s.lambda;
   const float li = lambda[i];
-  const bool art = fp.f.isArtPressureEnabled != 0;
-  const u32 artExp = fp.f.artPressureExp;
+  const bool art = ART == 0 ? fp.f.isArtPressureEnabled != 0 : ART > 0;
+  const u32 artExp = ART > 0 ? (u32)ART : fp.f.artPressureExp;
   const float artCoeff = fp.f.artPressureCoeff, invDen = fp.invArtDenom;
   float cx = 0.f, cy = 0.f, cz = 0.f;
   sweepConsumer<TRAV>(g, c, s, pred, pi, i, nbrMode, epoch,
@@ -578,25 +579,37 @@ void launchDensityLambda(const DeviceState& s, int model, const GridParams& g, c
   else
     launchPdl(densityLambdaKernel<TRAV_FLUIDS>, nbBlocks(s.N), NB_THREADS, st, s, g, c, p.f.restDensity, p.f.relaxCFM, pred, nbrMode, epoch);
 }
+template <int TRAV, bool LAST>
+static void launchCorrectionArt(const DeviceState& s, const GridParams& g, const SphConsts& c, const FluidStepParams& p, const float4* pred,
+    float4* predOut, int wc, int nbrMode, int epoch, cudaStream_t st)
+{
+  const int nb = nbBlocks(s.N);
+  if (!p.f.isArtPressureEnabled)
+    launchPdl(correctionKernel<TRAV, LAST, -1>, nb, NB_THREADS, st, s, g, c, p, pred, predOut, wc, nbrMode, epoch);
+  else if (p.f.artPressureExp == 4u)
+    launchPdl(correctionKernel<TRAV, LAST, 4>, nb, NB_THREADS, st, s, g, c, p, pred, predOut, wc, nbrMode, epoch);
+  else
+    launchPdl(correctionKernel<TRAV, LAST, 0>, nb, NB_THREADS, st, s, g, c, p, pred, predOut, wc, nbrMode, epoch);
+}
 void launchCorrection(const DeviceState& s, int model, const GridParams& g, const SphConsts& c, const FluidStepParams& p,
     const rtp_cloud_params&, const float4* pred, float4* predOut, bool last, bool writeCorr, int nbrMode, int epoch, cudaStream_t st)
 {
   if (!s.N)
     return;
-  const int nb = nbBlocks(s.N), wc = writeCorr ? 1 : 0;
+  const int wc = writeCorr ? 1 : 0;
   if (model == RTP_MODEL_CLOUDS)
   {
     if (last)
-      launchPdl(correctionKernel<TRAV_CLOUDS, true>, nb, NB_THREADS, st, s, g, c, p, pred, predOut, wc, nbrMode, epoch);
+      launchCorrectionArt<TRAV_CLOUDS, true>(s, g, c, p, pred, predOut, wc, nbrMode, epoch, st);
     else
-      launchPdl(correctionKernel<TRAV_CLOUDS, false>, nb, NB_THREADS, st, s, g, c, p, pred, predOut, wc, nbrMode, epoch);
+      launchCorrectionArt<TRAV_CLOUDS, false>(s, g, c, p, pred, predOut, wc, nbrMode, epoch, st);
   }
   else
   {
     if (last)
-      launchPdl(correctionKernel<TRAV_FLUIDS, true>, nb, NB_THREADS, st, s, g, c, p, pred, predOut, wc, nbrMode, epoch);
+      launchCorrectionArt<TRAV_FLUIDS, true>(s, g, c, p, pred, predOut, wc, nbrMode, epoch, st);
     else
-      launchPdl(correctionKernel<TRAV_FLUIDS, false>, nb, NB_THREADS, st, s, g, c, p, pred, predOut, wc, nbrMode, epoch);
+      launchCorrectionArt<TRAV_FLUIDS, false>(s, g, c, p, pred, predOut, wc, nbrMode, epoch, st);
   }
 }
 void launchVorticity(const DeviceState& s, int model, const GridParams& g, const SphConsts& c, const float4* pred, int nbrMode,
