@@ -13,7 +13,7 @@ JSON keys (one line on stdout, rank 0):
   e2e        same metric through the public API (models.Fluids.update()) with HOST buffers: H2D of p_pos/p_vel from
              pinned memory and D2H of p_pos inside the timed region, every step
   roofline   dominant kernel: algorithmic bytes per launch / its event-timed duration vs MEASURED_PEAKS.json hbm_gbs
-  cpu_baseline  the CPU oracle (oracle/, a port of the reference kernels) timed on this box's host cores, bounded sample
+  cpu_baseline  the reference's kernels compiled for the CPU (oracle/_ref; else the oracle port) on this box's host cores, bounded sample
 --impl reference times that CPU port alone, all host threads, on the same workload and metric.
 """
 import argparse
@@ -103,42 +103,81 @@ def dist_env():
 
 # ------------------------------------------------------------------------------------------------ reference arm
 
-def run_reference(args):
-    """The reference's CPU implementation of the path: the OpenCL kernels cannot be built here (no OpenCL ICD/headers), so
-    this is the oracle port of them, all host threads, bounded to ~150 s."""
-    rank, _, world = dist_env()
-    if rank != 0:
-        return
+def cpu_world(pos, which):
+    """The 130k PBF workload on the host cores: which = "reference" -> the reference's OWN kernel sources compiled for the
+    CPU (oracle/_ref/libref_kernels.so, built by oracle/ref/Makefile where /root/reference exists; the .so travels),
+    "port" -> the oracle restatement (oracle/rtp_oracle.c). Returns (world, threads) or None when not available."""
+    import ctypes
     import numpy as np
     from oracle import oracle_py as O
-    pos = O.gen_box_grid((64, 64, 32), (-5.0, -5.0, -5.0), (5.0, 0.0, 0.0))
-    w = O.World(O.FLUIDS, N130K, N130K)
+    n_thr = os.cpu_count() or 1
+    if which == "reference":
+        from oracle import ref_py as R
+        if not R.available():
+            return None
+        mod = R
+        try:  # torchrun exports OMP_NUM_THREADS=1: use every host core anyway
+            ctypes.CDLL("libgomp.so.1").omp_set_num_threads(n_thr)
+        except OSError:
+            n_thr = int(os.environ.get("OMP_NUM_THREADS", n_thr))
+    else:
+        mod = O
+        O.lib().orc_set_threads(n_thr)
+        n_thr = O.max_threads()
+    w = mod.World(O.FLUIDS, N130K, N130K)
     w.set_fluid_params(O.default_fluid_params(), JACOBI)
     w.upload("POS", pos)
     w.upload("VEL", np.zeros((N130K, 4), np.float32))
     w.reset_ids()
-    O.lib().orc_set_threads(os.cpu_count() or 1)  # torchrun exports OMP_NUM_THREADS=1: use every host core anyway
-    cores = O.max_threads()
-    budget = 150.0
-    for _ in range(min(args.warmup, 2)):
+    return w, n_thr
+
+
+def time_cpu_world(w, warmup, steps, budget_s):
+    from oracle import oracle_py as O
+    for _ in range(warmup):
         w.step(O.STEP_PHYSICS)
     done, t0 = 0, time.perf_counter()
-    while done < args.steps and (time.perf_counter() - t0) < budget:
+    while done < steps and (time.perf_counter() - t0) < budget_s:
         w.step(O.STEP_PHYSICS)
         done += 1
-    dt = time.perf_counter() - t0
+    return done, time.perf_counter() - t0
+
+
+def run_reference(args):
+    """The reference's CPU implementation of the path. The OpenCL runtime it needs does not exist here, so its kernel
+    sources (physics/ocl/kernels/*.cl, unmodified) are compiled for the CPU through oracle/ref/ocl_shim.hpp into
+    oracle/_ref/libref_kernels.so and run over all host threads (one OpenMP work-item loop per kernel launch, the same
+    launch sequence as Fluids::update); when that library is absent the oracle port is timed instead. Bounded to ~150 s."""
+    rank, _, world = dist_env()
+    if rank != 0:
+        return
+    from oracle import oracle_py as O
+    pos = O.gen_box_grid((64, 64, 32), (-5.0, -5.0, -5.0), (5.0, 0.0, 0.0))
+    kind = "reference"
+    cw = cpu_world(pos, kind)
+    if cw is None:
+        kind = "port"
+        cw = cpu_world(pos, kind)
+    w, cores = cw
+    budget = 150.0
+    wu = min(args.warmup, 2)
+    done, dt = time_cpu_world(w, wu, args.steps, budget)
     value = N130K * done / dt
     sample = "%d of %d requested steps of the full 131072-particle PBF step (time-bounded to %ds)" % (done, args.steps, int(budget))
     out = {
         "impl": "reference", "metric": "particle-updates/sec", "value": value, "unit": "particle-updates/s",
-        "n_gpus": args.gpus, "steps": done, "warmup": min(args.warmup, 2), "ms_per_step": 1e3 * dt / max(done, 1),
+        "n_gpus": args.gpus, "steps": done, "warmup": wu, "ms_per_step": 1e3 * dt / max(done, 1),
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": "pbf_dam_130k_I3_vorticity_xsph", "particles": N130K, "jacobi_iterations": JACOBI,
                    "grid": [30, 30, 30], "box": [10, 10, 10]},
-        "cpu_baseline": {"value": value, "unit": "particle-updates/s", "cores": cores, "kind": "port", "sample": sample},
+        "cpu_baseline": {"value": value, "unit": "particle-updates/s", "cores": cores, "kind": kind, "sample": sample},
         "e2e": {"value": value, "unit": "particle-updates/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
+    if kind == "reference":  # for orientation: the fused restatement of the same kernels (the oracle) on the same cores
+        w2, c2 = cpu_world(pos, "port")
+        d2, t2 = time_cpu_world(w2, 1, max(2, min(done, 6)), 30.0)
+        out["oracle_port"] = {"value": N130K * d2 / t2, "unit": "particle-updates/s", "cores": c2, "steps": d2}
     print(json.dumps(out), flush=True)
 
 
@@ -448,24 +487,21 @@ def run_ours(args):
            "d2h_bytes_per_step": N130K * 16, "steps": ke, "ms_per_step": round(1e3 * e2e_dt / ke, 4),
            "api": "realtimeparticles_b200.models.Fluids: upload(p_pos,p_vel) + update() + download(p_pos), pinned host buffers"}
 
-    # ---- CPU baseline: the oracle port on this box's host cores, bounded sample
+    # ---- CPU baseline on this box's host cores, bounded sample: the reference's own kernels compiled for the CPU
+    # (oracle/_ref) when that library travelled here, and the oracle port beside it
     cpu = None
     if not args.no_cpu_baseline and world == 1:
-        from oracle import oracle_py as O
-        O.lib().orc_set_threads(os.cpu_count() or 1)
-        w = O.World(O.FLUIDS, N130K, N130K)
-        w.set_fluid_params(O.default_fluid_params(), JACOBI)
-        w.upload("POS", pos0)
-        w.upload("VEL", np.zeros((N130K, 4), np.float32))
-        w.reset_ids()
-        w.step(O.STEP_PHYSICS)
-        n, t0 = 0, time.perf_counter()
-        while n < 12 and time.perf_counter() - t0 < 20.0:
-            w.step(O.STEP_PHYSICS)
-            n += 1
-        dt = time.perf_counter() - t0
-        cpu = {"value": N130K * n / dt, "unit": "particle-updates/s", "cores": O.max_threads(), "kind": "port",
-               "sample": "%d full steps of the same 131072-particle PBF workload after 1 warm-up (%.1f s)" % (n, dt)}
+        for kind, (nsteps, budget) in (("reference", (8, 14.0)), ("port", (12, 14.0))):
+            cw = cpu_world(pos0, kind)
+            if cw is None:
+                continue
+            n, dt = time_cpu_world(cw[0], 1, nsteps, budget)
+            r = {"value": N130K * n / dt, "unit": "particle-updates/s", "cores": cw[1], "kind": kind,
+                 "sample": "%d full steps of the same 131072-particle PBF workload after 1 warm-up (%.1f s)" % (n, dt)}
+            if cpu is None:
+                cpu = r
+            else:
+                cpu["oracle_port"] = {k: r[k] for k in ("value", "cores", "sample")}
 
     others = {}
     if not args.no_other_workloads:
