@@ -233,6 +233,10 @@ RTP_API int rtp_list_stats(rtp_handle* h, unsigned long long out[8]);
 /* out: float4[res.x*res.y*res.z]; returns number of points or negative rtp_status */
 RTP_API int64_t rtp_gen_box_grid(float* out_xyzw, const int res[3], const float start[3], const float end[3]);
 RTP_API int64_t rtp_gen_sphere_grid(float* out_xyzw, const int res[3], const float start[3], const float end[3]);
+/* planar lattices of the 2D presets (utils/Geometry.cpp:8-196): plane 0 = XY, 1 = XZ, 2 = YZ; out: float4[res[0]*res[1]];
+ * rectangle: res points along the plane's two axes; circle: res[0] angles x res[1] radii around the centre of start..end */
+RTP_API int64_t rtp_gen_rectangle_grid(float* out_xyzw, int plane, const int res[2], const float start[3], const float end[3]);
+RTP_API int64_t rtp_gen_circle_grid(float* out_xyzw, int plane, const int res[2], const float start[3], const float end[3]);
 /* glibc rand()-driven uniform fill in (x,y,z) call order; seed<0 keeps the process' current rand() state */
 RTP_API int64_t rtp_gen_random_box(float* out_xyzw, int64_t n, const float start[3], const float end[3], int seed);
 /* the float a reference kernel sees for a -D constant: parse(FloatToStr(v)) (utils/Utils.cpp:24-29) */

@@ -25,6 +25,23 @@ long ref_generate_3d_grid(int shape /*0 box, 1 sphere*/, const int res[3], const
   return (long)verts.size();
 }
 
+long ref_generate_2d_grid(int shape /*0 rectangle, 1 circle*/, int plane /*0 XY, 1 XZ, 2 YZ*/, const int res[2], const float start[3],
+    const float end[3], int random, float* out_xyzw)
+{
+  const Geometry::Plane pl = plane == 0 ? Geometry::Plane::XY : (plane == 1 ? Geometry::Plane::XZ : Geometry::Plane::YZ);
+  const auto verts = Geometry::Generate2DGrid(shape == 0 ? Geometry::Shape2D::Rectangle : Geometry::Shape2D::Circle, pl,
+      Math::int2(res[0], res[1]), Math::float3(start[0], start[1], start[2]), Math::float3(end[0], end[1], end[2]),
+      random ? Geometry::Distribution::Random : Geometry::Distribution::Uniform);
+  for (size_t i = 0; i < verts.size(); ++i)
+  {
+    out_xyzw[4 * i + 0] = verts[i].x;
+    out_xyzw[4 * i + 1] = verts[i].y;
+    out_xyzw[4 * i + 2] = verts[i].z;
+    out_xyzw[4 * i + 3] = 0.0f;
+  }
+  return (long)verts.size();
+}
+
 // the float an OpenCL compiler reads back from "-DNAME=" << Utils::FloatToStr(v)
 float ref_baked_constant(float v)
 {

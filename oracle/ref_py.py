@@ -59,6 +59,9 @@ def glib():
         L.ref_generate_3d_grid.argtypes = [C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_float), C.POINTER(C.c_float), C.c_int,
                                            C.c_void_p]
         L.ref_generate_3d_grid.restype = C.c_long
+        L.ref_generate_2d_grid.argtypes = [C.c_int, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_float), C.POINTER(C.c_float), C.c_int,
+                                           C.c_void_p]
+        L.ref_generate_2d_grid.restype = C.c_long
         L.ref_baked_constant.argtypes = [C.c_float]
         L.ref_baked_constant.restype = C.c_float
         L.ref_float_to_str.argtypes = [C.c_float, C.c_char_p, C.c_size_t]
@@ -103,6 +106,19 @@ def generate_3d_grid(shape, res, start, end, random=False, seed=None):
         glib().ref_srand(seed)
     r = glib().ref_generate_3d_grid(shape, (C.c_int * 3)(*res), (C.c_float * 3)(*start), (C.c_float * 3)(*end), int(random),
                                     out.ctypes.data)
+    assert r == n
+    return out
+
+
+def generate_2d_grid(shape, plane, res, start, end, random=False, seed=None):
+    """Geometry::Generate2DGrid (utils/Geometry.cpp:8-38) of the reference itself; shape 0 = rectangle, 1 = circle;
+    plane 0 = XY, 1 = XZ, 2 = YZ."""
+    n = res[0] * res[1]
+    out = np.empty((n, 4), np.float32)
+    if seed is not None:
+        glib().ref_srand(seed)
+    r = glib().ref_generate_2d_grid(shape, plane, (C.c_int * 2)(*res), (C.c_float * 3)(*start), (C.c_float * 3)(*end),
+                                    int(random), out.ctypes.data)
     assert r == n
     return out
 

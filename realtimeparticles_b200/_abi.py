@@ -81,7 +81,7 @@ EXPORTS = ["rtp_abi_version", "rtp_device_count", "rtp_create", "rtp_destroy", "
            "rtp_set_displayed_quantity", "rtp_reset_ids", "rtp_init_clouds_fields", "rtp_step", "rtp_step_n",
            "rtp_sync", "rtp_get_stream", "rtp_sort_keys", "rtp_sort_keys_host", "rtp_selftest_math", "rtp_enable_profiling", "rtp_get_stage_times",
            "rtp_last_launch_count", "rtp_list_stats", "rtp_shard_set_owned", "rtp_shard_stage", "rtp_shard_buffer", "rtp_shard_list_dmax_sq",
-           "rtp_gen_box_grid", "rtp_gen_sphere_grid", "rtp_gen_random_box",
+           "rtp_gen_box_grid", "rtp_gen_sphere_grid", "rtp_gen_rectangle_grid", "rtp_gen_circle_grid", "rtp_gen_random_box",
            "rtp_baked_constant"]
 
 _lib = None
@@ -136,6 +136,9 @@ def lib():
     L.rtp_list_stats.argtypes = [vp, C.POINTER(C.c_ulonglong)]
     for g in ("rtp_gen_box_grid", "rtp_gen_sphere_grid"):
         getattr(L, g).argtypes = [vp, C.POINTER(C.c_int), fp, fp]
+        getattr(L, g).restype = C.c_int64
+    for g in ("rtp_gen_rectangle_grid", "rtp_gen_circle_grid"):
+        getattr(L, g).argtypes = [vp, C.c_int, C.POINTER(C.c_int), fp, fp]
         getattr(L, g).restype = C.c_int64
     L.rtp_gen_random_box.argtypes = [vp, C.c_int64, fp, fp, C.c_int]
     L.rtp_gen_random_box.restype = C.c_int64
@@ -335,6 +338,28 @@ def gen_sphere_grid(res, start, end):
     if r != n:
         raise RtpError("rtp_gen_sphere_grid failed: %d" % r)
     return out
+
+
+PLANE_XY, PLANE_XZ, PLANE_YZ = 0, 1, 2
+
+
+def _gen_planar(fn, plane, res, start, end):
+    n = res[0] * res[1]
+    out = np.empty((n, 4), np.float32)
+    r = getattr(lib(), fn)(out.ctypes.data, int(plane), (C.c_int * 2)(*res), _f3(start), _f3(end))
+    if r != n:
+        raise RtpError("%s failed: %d" % (fn, r))
+    return out
+
+
+def gen_rectangle_grid(res, start, end, plane=PLANE_YZ):
+    """Planar uniform lattice of the 2D presets (utils/Geometry.cpp:75-140); float4 rows."""
+    return _gen_planar("rtp_gen_rectangle_grid", plane, res, start, end)
+
+
+def gen_circle_grid(res, start, end, plane=PLANE_YZ):
+    """Planar polar lattice of the 2D presets (utils/Geometry.cpp:142-196); float4 rows."""
+    return _gen_planar("rtp_gen_circle_grid", plane, res, start, end)
 
 
 def gen_random_box(n, start, end, seed=1):

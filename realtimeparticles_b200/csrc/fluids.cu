@@ -24,6 +24,7 @@
 #include <cstdlib>
 
 #include "kernels.cuh"
+#include "sort.cuh"
 #include "sweep.cuh"
 
 namespace rtp
@@ -73,7 +74,11 @@ __device__ __forceinline__ float4 cloudBoundary(const GridParams& g, float4 np)
 
 // ------------------------------------------------------------------ element-wise kernels
 
-__global__ void __launch_bounds__(EW_THREADS) fluidPredictKernel(DeviceState s, GridParams g, float dt, u32* __restrict__ keys)
+// HIST: also build the digit histograms of the cell sort on the way and zero its look-back words (saves the sort's own
+// histogram kernel and one read of the keys; the caller has zeroed the sort control block before the launch)
+template <bool HIST>
+__global__ void __launch_bounds__(EW_THREADS) fluidPredictKernel(DeviceState s, GridParams g, float dt, u32* __restrict__ keys,
+    int passes, PassDesc desc, u32* __restrict__ sortCtrl, u32* __restrict__ sortStatus, size_t statusWords)
 {
   RTP_PDL_PROLOGUE();
   const u32 i = blockIdx.x * EW_THREADS + threadIdx.x;
@@ -85,14 +90,24 @@ __global__ void __launch_bounds__(EW_THREADS) fluidPredictKernel(DeviceState s, 
     s.stragCount[i] = 0u;
     s.stragCursor[i] = 0u;
   }
-  if (i >= s.N)
-    return;
-  const float4 p = s.posA[i], v = s.velA[i];
-  // newVel = vel + GRAVITY_ACC * dt ; predPos = pos + newVel * dt
-  const float nvx = fadd(v.x, fmul(0.0f, dt)), nvy = fadd(v.y, fmul(-RTP_ABS_GRAVITY_ACC_Y, dt)), nvz = fadd(v.z, fmul(0.0f, dt));
-  const float4 pr = make_float4(fadd(p.x, fmul(nvx, dt)), fadd(p.y, fmul(nvy, dt)), fadd(p.z, fmul(nvz, dt)), 0.0f);
-  s.pred0[i] = pr;
-  keys[i] = cell1D(g, pr.x, pr.y, pr.z);
+  const bool valid = i < s.N;
+  u32 key = 0u;
+  if (valid)
+  {
+    const float4 p = s.posA[i], v = s.velA[i];
+    // newVel = vel + GRAVITY_ACC * dt ; predPos = pos + newVel * dt
+    const float nvx = fadd(v.x, fmul(0.0f, dt)), nvy = fadd(v.y, fmul(-RTP_ABS_GRAVITY_ACC_Y, dt)), nvz = fadd(v.z, fmul(0.0f, dt));
+    const float4 pr = make_float4(fadd(p.x, fmul(nvx, dt)), fadd(p.y, fmul(nvy, dt)), fadd(p.z, fmul(nvz, dt)), 0.0f);
+    s.pred0[i] = pr;
+    key = cell1D(g, pr.x, pr.y, pr.z);
+    keys[i] = key;
+  }
+  if (HIST)
+  {
+    __shared__ u32 sHist[SORT_MAX_PASSES * SORT_RADIX];
+    sortStatusClear(sortStatus, statusWords);
+    sortHistogramAdd(sHist, key, valid, passes, desc, sortCtrl);
+  }
 }
 
 __global__ void __launch_bounds__(EW_THREADS) fluidGatherKernel(DeviceState s, GridParams g)
@@ -560,9 +575,17 @@ __global__ void __launch_bounds__(NB_THREADS, NB_MIN_BLOCKS) correctTempKernel(D
 static inline int ewBlocks(size_t n) { return (int)((n + EW_THREADS - 1) / EW_THREADS); }
 static inline int nbBlocks(size_t n) { return (int)((n + NB_THREADS - 1) / NB_THREADS); }
 
-void launchFluidPredict(const DeviceState& s, const GridParams& g, const FluidStepParams& p, u32* keysOut, cudaStream_t st)
+static_assert(EW_THREADS == SORT_THREADS, "fluidPredictKernel<true> builds the sort histograms with SORT_THREADS threads per block");
+void launchFluidPredict(const DeviceState& s, const GridParams& g, const FluidStepParams& p, u32* keysOut, const SortPlan* fusedSort,
+    u32* sortCtrl, u32* sortStatus, cudaStream_t st)
 {
-  launchPdl(fluidPredictKernel, ewBlocks(max(s.N, g.numCells)), EW_THREADS, st, s, g, p.f.timeStep, keysOut);
+  const int blocks = ewBlocks(max(s.N, g.numCells));
+  if (fusedSort && fusedSort->n)
+    launchPdl(fluidPredictKernel<true>, blocks, EW_THREADS, st, s, g, p.f.timeStep, keysOut, fusedSort->passes, makePassDesc(*fusedSort),
+        sortCtrl, sortStatus, sortStatusWords(*fusedSort));
+  else
+    launchPdl(fluidPredictKernel<false>, blocks, EW_THREADS, st, s, g, p.f.timeStep, keysOut, 0, PassDesc {}, (u32*)nullptr, (u32*)nullptr,
+        (size_t)0);
 }
 void launchFluidGather(const DeviceState& s, const GridParams& g, cudaStream_t st)
 {

@@ -86,7 +86,10 @@ void launchBoidsGather(const DeviceState& s, const GridParams& g, cudaStream_t s
 void launchBoidsRules(const DeviceState& s, const GridParams& g, const SphConsts& c, const BoidsStepParams& p, cudaStream_t st);
 
 // ---- fluids.cu (fluids + clouds)
-void launchFluidPredict(const DeviceState& s, const GridParams& g, const FluidStepParams& p, u32* keysOut, cudaStream_t st);
+struct SortPlan;
+// fusedSort != nullptr: the kernel also builds that sort's histograms (sort.cuh enqueueSortBegin / enqueueSortPasses around it)
+void launchFluidPredict(const DeviceState& s, const GridParams& g, const FluidStepParams& p, u32* keysOut, const SortPlan* fusedSort,
+    u32* sortCtrl, u32* sortStatus, cudaStream_t st);
 void launchFluidGather(const DeviceState& s, const GridParams& g, cudaStream_t st);
 void launchDensityLambda(const DeviceState& s, int model, const GridParams& g, const SphConsts& c, const FluidStepParams& p,
     const float4* pred, int nbrMode, int epoch, cudaStream_t st);

@@ -679,12 +679,19 @@ static int enqueueStep(rtp_handle* h, unsigned flags, const float cam[3], bool p
       const bool clouds = model == RTP_MODEL_CLOUDS;
       const bool lists = s.nbrList != nullptr && h->jacobi + 1 < NBR_EPOCH_TEMP;
       if (clouds)
+      {
         launchCloudsThermoPredict(s, g, h->cp, keysIn, st);
+        rec.mark("thermo+predict+boundary+fillCellIDs");
+        launches += 1 + enqueueSort(h->cellPlan, s.cellID, s.perm, s.keysTmp, s.permTmp, s.sortCtrl, s.sortStatus, st);
+      }
       else
-        launchFluidPredict(s, g, h->fp, keysIn, st);
-      ++launches;
-      rec.mark(clouds ? "thermo+predict+boundary+fillCellIDs" : "predictPosition+fillCellIDs");
-      launches += enqueueSort(h->cellPlan, s.cellID, s.perm, s.keysTmp, s.permTmp, s.sortCtrl, s.sortStatus, st);
+      {
+        // the predict kernel produces the keys: it builds the sort's digit histograms on the way
+        enqueueSortBegin(h->cellPlan, s.sortCtrl, st);
+        launchFluidPredict(s, g, h->fp, keysIn, &h->cellPlan, s.sortCtrl, s.sortStatus, st);
+        rec.mark("predictPosition+fillCellIDs");
+        launches += 1 + enqueueSortPasses(h->cellPlan, s.cellID, s.perm, s.keysTmp, s.permTmp, s.sortCtrl, s.sortStatus, st);
+      }
       rec.mark("radixSort(onesweep)");
       if (clouds)
         launchCloudsGather(s, g, st);
@@ -873,7 +880,7 @@ extern "C" int rtp_shard_stage(rtp_handle* h, int stage, int iter, int last)
   {
     DeviceState own = s;
     own.N = min(s.nOwned, s.N);
-    launchFluidPredict(own, g, h->fp, keysIn, st);
+    launchFluidPredict(own, g, h->fp, keysIn, nullptr, nullptr, nullptr, st);
     break;
   }
   case RTP_SHARD_GHOST_KEYS:
@@ -1143,6 +1150,67 @@ extern "C" int64_t rtp_gen_sphere_grid(float* out, const int res[3], const float
         o[2] = ctr[2] + r * cosf(ip * dphi);
         o[3] = 0.0f;
       }
+  return n;
+}
+
+// planar lattices of the 2D presets (utils/Geometry.cpp:8-196). plane: 0 = XY, 1 = XZ, 2 = YZ; res = points along the
+// plane's first / second axis (rectangle) or angular / radial subdivisions (circle). The off-plane coordinate is
+// start's (rectangle) or the centre's (circle).
+static bool planeAxes(int plane, int& a, int& b)
+{
+  if (plane < 0 || plane > 2)
+    return false;
+  a = plane == 2 ? 1 : 0;
+  b = plane == 0 ? 1 : 2;
+  return true;
+}
+extern "C" int64_t rtp_gen_rectangle_grid(float* out, int plane, const int res[2], const float start[3], const float end[3])
+{
+  int a, b;
+  if (!out || !res || !start || !end || res[0] <= 0 || res[1] <= 0 || !planeAxes(plane, a, b))
+    return RTP_ERR_INVALID;
+  const float da = (end[a] - start[a]) / res[0], db = (end[b] - start[b]) / res[1];
+  int64_t n = 0;
+  for (int ia = 0; ia < res[0]; ++ia)
+    for (int ib = 0; ib < res[1]; ++ib, ++n)
+    {
+      float* o = out + 4 * n;
+      // the reference adds index * spacing on every axis; off the plane that is start + 0 * 0
+      o[0] = start[0] + 0 * 0.0f;
+      o[1] = start[1] + 0 * 0.0f;
+      o[2] = start[2] + 0 * 0.0f;
+      o[3] = 0.0f;
+      o[a] = start[a] + ia * da;
+      o[b] = start[b] + ib * db;
+    }
+  return n;
+}
+extern "C" int64_t rtp_gen_circle_grid(float* out, int plane, const int res[2], const float start[3], const float end[3])
+{
+  int a, b;
+  if (!out || !res || !start || !end || res[0] <= 0 || res[1] <= 0 || !planeAxes(plane, a, b))
+    return RTP_ERR_INVALID;
+  const float PI_F = 3.1415927f;
+  float v[3], ctr[3];
+  for (int k = 0; k < 3; ++k)
+  {
+    v[k] = end[k] - start[k];
+    ctr[k] = start[k] + v[k] / 2.0f;
+  }
+  const float radius = sqrtf(v[0] * v[0] + v[1] * v[1] + v[2] * v[2]) / 2.0f;
+  const float dang = 2.0f * PI_F / res[0], dr = radius / res[1];
+  int64_t n = 0;
+  for (int io = 0; io < res[0]; ++io)
+    for (int ir = 0; ir < res[1]; ++ir, ++n)
+    {
+      float* o = out + 4 * n;
+      o[0] = ctr[0];
+      o[1] = ctr[1];
+      o[2] = ctr[2];
+      o[3] = 0.0f;
+      o[a] = ctr[a] + ((ir + 1) * dr) * cosf(io * dang);
+      o[b] = ctr[b] + ((ir + 1) * dr) * sinf(io * dang);
+    }
   return n;
 }
 

@@ -37,12 +37,6 @@ __device__ __forceinline__ u32 blockExclusiveScan256(u32 v, u32* sWarp)
   return base + incl - v;
 }
 
-struct PassDesc
-{
-  int shift[SORT_MAX_PASSES];
-  u32 mask[SORT_MAX_PASSES];
-};
-
 // One read of the keys builds the digit histogram of every pass; side job: zero the look-back status words.
 __global__ void __launch_bounds__(SORT_THREADS) sortHistogramKernel(const u32* __restrict__ keys, u32 n, int passes,
     PassDesc desc, u32* __restrict__ ctrl, u32* __restrict__ status, size_t statusWords)
@@ -214,32 +208,32 @@ SortPlan makeSortPlan(u32 n, int keyBits)
 
 size_t sortStatusWords(const SortPlan& plan) { return (size_t)plan.passes * plan.tiles * SORT_RADIX; }
 
-int enqueueSort(const SortPlan& plan, u32* keys0, u32* vals0, u32* keys1, u32* vals1, u32* ctrl, u32* status,
-    cudaStream_t stream)
+PassDesc makePassDesc(const SortPlan& plan)
 {
-  if (plan.n == 0)
-    return 0;
-  int launches = 0;
-  cudaMemsetAsync(ctrl, 0, SORT_CTRL_WORDS * sizeof(u32), stream); // memset node, not counted as a kernel
   PassDesc desc;
   for (int i = 0; i < SORT_MAX_PASSES; ++i)
   {
     desc.shift[i] = plan.shift[i];
     desc.mask[i] = plan.bits[i] ? ((1u << plan.bits[i]) - 1u) : 0u;
   }
+  return desc;
+}
+
+void enqueueSortBegin(const SortPlan& plan, u32* ctrl, cudaStream_t stream)
+{
+  if (plan.n)
+    cudaMemsetAsync(ctrl, 0, SORT_CTRL_WORDS * sizeof(u32), stream); // memset node, not counted as a kernel
+}
+
+int enqueueSortPasses(const SortPlan& plan, u32* keys0, u32* vals0, u32* keys1, u32* vals1, u32* ctrl, u32* status,
+    cudaStream_t stream)
+{
+  if (plan.n == 0)
+    return 0;
+  const PassDesc desc = makePassDesc(plan);
   u32* kbuf[2] = { keys0, keys1 };
   u32* vbuf[2] = { vals0, vals1 };
-  const int first = (plan.passes % 2 == 0) ? 0 : 1;
-  {
-    int blocks = (int)((plan.n + SORT_THREADS * 8 - 1) / (SORT_THREADS * 8));
-    if (blocks > 148 * 8)
-      blocks = 148 * 8;
-    if (blocks < 1)
-      blocks = 1;
-    launchPdl(sortHistogramKernel, blocks, SORT_THREADS, stream, kbuf[first], plan.n, plan.passes, desc, ctrl, status,
-        sortStatusWords(plan));
-    ++launches;
-  }
+  int launches = 0;
   for (int p = 0; p < plan.passes; ++p)
   {
     const int src = ((plan.passes - p) % 2 == 0) ? 0 : 1;
@@ -257,6 +251,25 @@ int enqueueSort(const SortPlan& plan, u32* keys0, u32* vals0, u32* keys1, u32* v
     ++launches;
   }
   return launches;
+}
+
+int enqueueSort(const SortPlan& plan, u32* keys0, u32* vals0, u32* keys1, u32* vals1, u32* ctrl, u32* status,
+    cudaStream_t stream)
+{
+  if (plan.n == 0)
+    return 0;
+  enqueueSortBegin(plan, ctrl, stream);
+  const PassDesc desc = makePassDesc(plan);
+  u32* kbuf[2] = { keys0, keys1 };
+  const int first = (plan.passes % 2 == 0) ? 0 : 1;
+  int blocks = (int)((plan.n + SORT_THREADS * 8 - 1) / (SORT_THREADS * 8));
+  if (blocks > 148 * 8)
+    blocks = 148 * 8;
+  if (blocks < 1)
+    blocks = 1;
+  launchPdl(sortHistogramKernel, blocks, SORT_THREADS, stream, kbuf[first], plan.n, plan.passes, desc, ctrl, status,
+      sortStatusWords(plan));
+  return 1 + enqueueSortPasses(plan, keys0, vals0, keys1, vals1, ctrl, status, stream);
 }
 
 } // namespace rtp

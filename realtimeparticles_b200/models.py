@@ -59,6 +59,10 @@ ALL_NB_PARTICLES = {
 }
 
 
+def GetNbParticlesSubdiv2D(nb):
+    return ALL_NB_PARTICLES.get(nb, ((0, 0), (0, 0, 0)))[0]
+
+
 def GetNbParticlesSubdiv3D(nb):
     return ALL_NB_PARTICLES.get(nb, ((0, 0), (0, 0, 0)))[1]
 
@@ -381,10 +385,12 @@ class Boids(Model):
         if self.m_currNbParticles > self.m_maxNbParticles:
             return
         bx, by, bz = [float(b) for b in self.m_boxSize]
-        if self.m_dimension == Dimension.dim2D:
-            raise NotImplementedError("2D circle preset: generate positions yourself and upload p_pos/p_vel")
-        sub = GetNbParticlesSubdiv3D(self.m_currNbParticles)
-        verts = _abi.gen_sphere_grid(sub, (bx / -6.0, by / -6.0, bz / -6.0), (bx / 6.0, by / 6.0, bz / 6.0))
+        if self.m_dimension == Dimension.dim2D:  # circle in the YZ plane, Boids.cpp:291-298
+            sub = GetNbParticlesSubdiv2D(self.m_currNbParticles)
+            verts = _abi.gen_circle_grid(sub, (0.0, by / -6.0, bz / -6.0), (0.0, by / 6.0, bz / 6.0), _abi.PLANE_YZ)
+        else:
+            sub = GetNbParticlesSubdiv3D(self.m_currNbParticles)
+            verts = _abi.gen_sphere_grid(sub, (bx / -6.0, by / -6.0, bz / -6.0), (bx / 6.0, by / 6.0, bz / 6.0))
         M = self.m_maxNbParticles
         pos = np.full((M, 4), np.inf, np.float32)
         pos[:, 3] = 0.0
@@ -429,10 +435,25 @@ class Fluids(Model):
         self.initFluidsParticles()
         self._h.reset_ids()
 
-    def initFluidsParticles(self):  # Fluids.cpp:273-398 (3D presets)
+    def initFluidsParticles(self):  # Fluids.cpp:273-398
         bx, by, bz = [float(b) for b in self.m_boxSize]
-        if self.m_dimension == Dimension.dim2D:
-            raise NotImplementedError("2D presets: generate positions yourself and upload p_pos")
+        if self.m_dimension == Dimension.dim2D:  # rectangles in the YZ plane, Fluids.cpp:287-335
+            if self.m_case == PhysicsCase.FLUIDS_DAM:
+                nb, start, end = P4K, (0.0, by / -2.0, bz / -2.0), (0.0, 0.0, 0.0)
+            elif self.m_case == PhysicsCase.FLUIDS_BOMB:
+                nb, start, end = P4K, (0.0, by / -6.0, bz / -6.0), (0.0, by / 6.0, bz / 6.0)
+            elif self.m_case == PhysicsCase.FLUIDS_DROP:
+                nb, start, end = P512, (0.0, 2.0 * by / 10.0, bz / -10.0), (0.0, 4.0 * by / 10.0, bz / 10.0)
+            else:
+                return
+            verts = _abi.gen_rectangle_grid(GetNbParticlesSubdiv2D(nb), start, end, _abi.PLANE_YZ)
+            if self.m_case == PhysicsCase.FLUIDS_DROP:  # + the pool it falls into
+                nb += P4K
+                pool = _abi.gen_rectangle_grid((64, 128), (0.0, by / -2.0, bz / -2.0), (0.0, 0.0, bz / 2.0), _abi.PLANE_YZ)
+                verts = np.concatenate([verts, pool])
+            self.setNbParticles(nb)
+            self._load_particles(verts, col=np.array([0.0, 0.1, 1.0, 0.0], np.float32))
+            return
         if self.m_case == PhysicsCase.FLUIDS_DAM:
             nb, box = P130K, True
             start, end = (bx / -2.0, by / -2.0, bz / -2.0), (bx / 2.0, 0.0, 0.0)
@@ -526,11 +547,16 @@ class Clouds(Model):
         self._push_displayed_quantity()
         self._h.reset_ids()
 
-    def initCloudsParticles(self):  # Clouds.cpp:401-501 (3D presets)
+    def initCloudsParticles(self):  # Clouds.cpp:401-501
         bx, by, bz = [float(b) for b in self.m_boxSize]
-        if self.m_dimension == Dimension.dim2D:
-            raise NotImplementedError("2D presets: generate positions yourself and upload the fields")
-        if self.m_case == PhysicsCase.CLOUDS_CUMULUS:
+        if self.m_dimension == Dimension.dim2D:  # random fill of a YZ rectangle (x extent 0), Clouds.cpp:414-444
+            if self.m_case == PhysicsCase.CLOUDS_CUMULUS:
+                nb, start, end = P8K, (0.0, by / -2.0, bz / -2.0), (0.0, 0.0, bz / 2.0)
+            elif self.m_case == PhysicsCase.CLOUDS_HOMOGENEOUS:
+                nb, start, end = P8K, (0.0, by / -2.0, bz / -2.0), (0.0, by / 2.0, bz / 2.0)
+            else:
+                return
+        elif self.m_case == PhysicsCase.CLOUDS_CUMULUS:
             nb, start, end = P65K, (bx / -2.0, by / -2.0, bz / -2.0), (bx / 2.0, by / -4.0, bz / 2.0)
         elif self.m_case == PhysicsCase.CLOUDS_HOMOGENEOUS:
             nb, start, end = P65K, (bx / -2.0, by / -2.0, bz / -2.0), (bx / 2.0, by / 2.0, bz / 2.0)

@@ -353,22 +353,27 @@ def _cpp_models():
     return L, C
 
 
-@pytest.mark.parametrize("kind", ["fluids", "boids", "clouds"])
+@pytest.mark.parametrize("kind", ["fluids", "boids", "clouds", "fluids2d", "boids2d"])
 def test_cpp_model_equals_python_model(kind):
     """Physics::CUDA::X driven through the reference's own Model interface == the Python mirror, bit for bit"""
     from realtimeparticles_b200 import models
     L, C = _cpp_models()
+    dim3 = not kind.endswith("2d")  # 2D: the presets live in the YZ plane (Generate2DGrid), same kernels
+    kind = kind[:-2] if not dim3 else kind
     t, case, box, grid = {"fluids": (1, models.PhysicsCase.FLUIDS_DAM, (10, 10, 10), (30, 30, 30)),
                           "boids": (0, models.PhysicsCase.BOIDS_LARGE, (10, 10, 10), (30, 30, 30)),
                           "clouds": (2, models.PhysicsCase.CLOUDS_CUMULUS, (10, 20, 10), (30, 60, 30))}[kind]
     M = 131072
-    m = L.rtpm_create(t, M, int(case), 1, (C.c_uint32 * 3)(*box), (C.c_uint32 * 3)(*grid))
+    m = L.rtpm_create(t, M, int(case), 1 if dim3 else 0, (C.c_uint32 * 3)(*box), (C.c_uint32 * 3)(*grid))
     assert m and L.rtpm_is_init(m)
     if kind != "boids":
         assert L.rtpm_update_input_json(m, b'{"Fluids": {"Nb Jacobi Iterations": [3, 1, 6]}}') == 0
         assert L.rtpm_update_input_json(m, b'{"Fluids": {"Nb Jacobi Iterations": "oops"}}') == -1  # "Wrong Json parsing"
         assert L.rtpm_update_input_json(m, b'{"Fluids": {"Nb Jacobi Iterations": [3, 1, 6]}}') == 0
-    py = models.CreateModel(t, models.ModelParams(currNbParticles=M, maxNbParticles=M, boxSize=box, gridRes=grid, pCase=case))
+    py = models.CreateModel(t, models.ModelParams(currNbParticles=M, maxNbParticles=M, boxSize=box, gridRes=grid, pCase=case,
+                                                  dimension=models.Dimension.dim3D if dim3 else models.Dimension.dim2D))
+    if not dim3 and kind == "fluids":
+        assert py.nbParticles() == 4096 and np.all(py.download("p_pos")[:4096, 0] == 0.0)
     if kind == "clouds":
         # the reference seeds nothing: both sides draw from glibc rand(); make the two draws identical
         verts = _abi.gen_random_box(65536, (-5.0, -10.0, -5.0), (5.0, -5.0, 5.0), 1)

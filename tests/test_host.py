@@ -52,6 +52,35 @@ def test_generators_product_equals_oracle():
     assert np.array_equal(a, b)
 
 
+def test_planar_generators_of_the_2d_presets():
+    # rectangle / circle lattices in a coordinate plane (utils/Geometry.cpp:8-196), used by the 2D presets of the models
+    f = np.float32
+    for plane, (a, b) in ((_abi.PLANE_XY, (0, 1)), (_abi.PLANE_XZ, (0, 2)), (_abi.PLANE_YZ, (1, 2))):
+        res, start, end = (7, 5), (-1.5, 0.25, -3.0), (2.5, 1.75, 0.5)
+        r = _abi.gen_rectangle_grid(res, start, end, plane)
+        assert r.shape == (35, 4) and np.all(r[:, 3] == 0)
+        off = 3 - a - b
+        assert np.all(r[:, off] == f(start[off]))  # off-plane coordinate: the start's
+        da, db = (f(end[a]) - f(start[a])) / f(res[0]), (f(end[b]) - f(start[b])) / f(res[1])
+        ia, ib = np.divmod(np.arange(35), res[1])
+        assert np.array_equal(r[:, a], f(start[a]) + ia.astype(f) * da) and np.array_equal(r[:, b], f(start[b]) + ib.astype(f) * db)
+        c = _abi.gen_circle_grid(res, start, end, plane)
+        ctr = [f(start[k]) + (f(end[k]) - f(start[k])) / f(2) for k in range(3)]
+        assert np.all(c[:, off] == ctr[off])
+        rad = np.hypot(c[:, a] - ctr[a], c[:, b] - ctr[b])
+        half_diag = np.sqrt(sum((end[k] - start[k]) ** 2 for k in range(3))) / 2
+        assert np.allclose(rad, (np.arange(35) % res[1] + 1) * half_diag / res[1], rtol=1e-5)
+    from oracle import ref_py as R
+    if R.available():  # bit for bit against the reference's own Geometry.cpp
+        for plane in (0, 1, 2):
+            for res, start, end in (((64, 64), (0.0, -5.0, -5.0), (0.0, 0.0, 0.0)), ((32, 16), (0.0, 2.0, -1.0), (0.0, 4.0, 1.0)),
+                                    ((256, 512), (0.0, -10 / 6, -10 / 6), (0.0, 10 / 6, 10 / 6))):
+                assert np.array_equal(_abi.gen_rectangle_grid(res, start, end, plane), R.generate_2d_grid(0, plane, res, start, end))
+                assert np.array_equal(_abi.gen_circle_grid(res, start, end, plane), R.generate_2d_grid(1, plane, res, start, end))
+        assert np.array_equal(_abi.gen_random_box(8192, (0.0, -10.0, -5.0), (0.0, 0.0, 5.0), 1),
+                              R.generate_2d_grid(0, 2, (128, 64), (0.0, -10.0, -5.0), (0.0, 0.0, 5.0), random=True, seed=1))
+
+
 def test_oracle_sort_is_stable():
     rng = np.random.default_rng(0)
     k = rng.integers(0, 500, size=10000).astype(np.uint32)
