@@ -491,7 +491,7 @@ def run_ours(args):
     # (oracle/_ref) when that library travelled here, and the oracle port beside it
     cpu = None
     if not args.no_cpu_baseline and world == 1:
-        for kind, (nsteps, budget) in (("reference", (8, 14.0)), ("port", (12, 14.0))):
+        for kind, (nsteps, budget) in (("reference", (40, 14.0)), ("port", (20, 8.0))):
             cw = cpu_world(pos0, kind)
             if cw is None:
                 continue

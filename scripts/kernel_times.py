@@ -15,4 +15,5 @@ for k, v in agg.items():
     if k.startswith('at::'):
         continue
     print("%-42s n=%3d mean=%8.2f us  min=%8.2f max=%8.2f share=%5.3f" % (k[:42], len(v), sum(v) / len(v), min(v), max(v), sum(v) / tot))
-print("sum of kernel time per step ~ %.1f us" % (tot / (len(agg.get('fluidPredictKernel', [1])) or 1)))
+steps = max([len(v) for k, v in agg.items() if k.startswith(('fluidPredictKernel', 'cloudsThermoPredictKernel', 'boidsCellIdsKernel'))] or [1])
+print("sum of kernel time per step ~ %.1f us (%d steps)" % (tot / steps, steps))
