@@ -4,8 +4,8 @@
 //
 // Launches per fluids step with I Jacobi iterations (reference: 3 + 5 I + 5 + buffer copies around two sorts):
 //   fluidPredictKernel      fld_predictPosition (fluids.cl:62-74) + fillCellIDs on p_predPos (grid.cl:76-86)
-//                           + resetStartEndCell (grid.cl:91-96)
-//   [sort]                  sort.cu
+//                           + resetStartEndCell (grid.cl:91-96) + the digit histograms of the cell sort
+//   [sort passes]           sort.cu
 //   fluidGatherKernel       payload permutation of p_pos, p_vel, p_predPos (radixSort.cl:179-190) + first
 //                           fld_applyBoundaryCondition (fluids.cl:435-439) + fillStartCell/fillEndCell (grid.cl:101-138)
 //   [adjustEndCell]         grid.cu
