@@ -59,6 +59,24 @@ def cases():
     }
 
 
+def generator_cases():
+    """name -> (product generator, reference generator, args): initial-state point sets of the presets (utils/Geometry.cpp)"""
+    from realtimeparticles_b200 import _abi
+    yz = _abi.PLANE_YZ
+    return {
+        "rect_yz_64x64_fluids2d_dam": (lambda: _abi.gen_rectangle_grid((64, 64), (0.0, -5.0, -5.0), (0.0, 0.0, 0.0), yz),
+                                       lambda: R.generate_2d_grid(0, 2, (64, 64), (0.0, -5.0, -5.0), (0.0, 0.0, 0.0))),
+        "circle_yz_32x16_boids2d": (lambda: _abi.gen_circle_grid((32, 16), (0.0, -10 / 6.0, -10 / 6.0), (0.0, 10 / 6.0, 10 / 6.0), yz),
+                                    lambda: R.generate_2d_grid(1, 2, (32, 16), (0.0, -10 / 6.0, -10 / 6.0), (0.0, 10 / 6.0, 10 / 6.0))),
+        "circle_xy_7x5": (lambda: _abi.gen_circle_grid((7, 5), (-1.5, 0.25, -3.0), (2.5, 1.75, 0.5), _abi.PLANE_XY),
+                          lambda: R.generate_2d_grid(1, 0, (7, 5), (-1.5, 0.25, -3.0), (2.5, 1.75, 0.5))),
+        "sphere_8x8x8_boids": (lambda: _abi.gen_sphere_grid((8, 8, 8), (-10 / 6.0,) * 3, (10 / 6.0,) * 3),
+                               lambda: R.generate_3d_grid(1, (8, 8, 8), (-10 / 6.0,) * 3, (10 / 6.0,) * 3)),
+        "random_yz_128x64_clouds2d": (lambda: _abi.gen_random_box(8192, (0.0, -10.0, -5.0), (0.0, 0.0, 5.0), 1),
+                                      lambda: R.generate_2d_grid(0, 2, (128, 64), (0.0, -10.0, -5.0), (0.0, 0.0, 5.0), random=True, seed=1)),
+    }
+
+
 def run_case(cls, name):
     make, steps, flags, fields = cases()[name]
     w = make(cls)
@@ -74,3 +92,5 @@ if __name__ == "__main__":
         init, out = run_case(R.World, name)
         np.savez_compressed(os.path.join(OUT, name + ".npz"), init_POS=init["POS"], init_VEL=init["VEL"], **out)
         print(name, {k: v.shape for k, v in out.items()})
+    np.savez_compressed(os.path.join(OUT, "generators.npz"), **{k: ref() for k, (_, ref) in generator_cases().items()})
+    print("generators", list(generator_cases()))

@@ -81,6 +81,17 @@ def test_planar_generators_of_the_2d_presets():
                               R.generate_2d_grid(0, 2, (128, 64), (0.0, -10.0, -5.0), (0.0, 0.0, 5.0), random=True, seed=1))
 
 
+def test_generators_match_reference_golden():
+    # point sets produced by the reference's own Geometry.cpp (tests/golden/make_golden.py), also where oracle/_ref is absent
+    import sys
+    gdir = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+    sys.path.insert(0, gdir)
+    import make_golden
+    gold = np.load(os.path.join(gdir, "generators.npz"))
+    for name, (product, _) in make_golden.generator_cases().items():
+        assert np.array_equal(product(), gold[name]), name
+
+
 def test_oracle_sort_is_stable():
     rng = np.random.default_rng(0)
     k = rng.integers(0, 500, size=10000).astype(np.uint32)
