@@ -187,12 +187,12 @@ __global__ void __launch_bounds__(BD_THREADS) boidsRulesKernel(DeviceState s, Gr
 void launchBoidsCellIds(const DeviceState& s, const GridParams& g, u32* keysOut, cudaStream_t st)
 {
   const u32 n = max(s.N, g.numCells);
-  launchPdl(boidsCellIdsKernel, (n + 255) / 256, 256, st, s.posA, g, keysOut, s.table, s.N);
+  launchKernel(boidsCellIdsKernel, (n + 255) / 256, 256, st, s.posA, g, keysOut, s.table, s.N);
 }
 void launchBoidsGather(const DeviceState& s, const GridParams& g, cudaStream_t st)
 {
   if (s.N)
-    launchPdl(boidsGatherKernel, (s.N + 255) / 256, 256, st, s, g);
+    launchKernel(boidsGatherKernel, (s.N + 255) / 256, 256, st, s, g);
 }
 void launchBoidsRules(const DeviceState& s, const GridParams& g, const SphConsts& c, const BoidsStepParams& p, cudaStream_t st)
 {
@@ -200,9 +200,9 @@ void launchBoidsRules(const DeviceState& s, const GridParams& g, const SphConsts
     return;
   const int blocks = (s.N + BD_THREADS - 1) / BD_THREADS;
   if (p.dim == 2)
-    launchPdl(boidsRulesKernel<true>, blocks, BD_THREADS, st, s, g, c, p);
+    launchKernel(boidsRulesKernel<true>, blocks, BD_THREADS, st, s, g, c, p);
   else
-    launchPdl(boidsRulesKernel<false>, blocks, BD_THREADS, st, s, g, c, p);
+    launchKernel(boidsRulesKernel<false>, blocks, BD_THREADS, st, s, g, c, p);
 }
 
 } // namespace rtp

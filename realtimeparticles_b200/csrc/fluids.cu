@@ -581,16 +581,16 @@ void launchFluidPredict(const DeviceState& s, const GridParams& g, const FluidSt
 {
   const int blocks = ewBlocks(max(s.N, g.numCells));
   if (fusedSort && fusedSort->n)
-    launchPdl(fluidPredictKernel<true>, blocks, EW_THREADS, st, s, g, p.f.timeStep, keysOut, fusedSort->passes, makePassDesc(*fusedSort),
+    launchKernel(fluidPredictKernel<true>, blocks, EW_THREADS, st, s, g, p.f.timeStep, keysOut, fusedSort->passes, makePassDesc(*fusedSort),
         sortCtrl, sortStatus, sortStatusWords(*fusedSort));
   else
-    launchPdl(fluidPredictKernel<false>, blocks, EW_THREADS, st, s, g, p.f.timeStep, keysOut, 0, PassDesc {}, (u32*)nullptr, (u32*)nullptr,
+    launchKernel(fluidPredictKernel<false>, blocks, EW_THREADS, st, s, g, p.f.timeStep, keysOut, 0, PassDesc {}, (u32*)nullptr, (u32*)nullptr,
         (size_t)0);
 }
 void launchFluidGather(const DeviceState& s, const GridParams& g, cudaStream_t st)
 {
   if (s.N)
-    launchPdl(fluidGatherKernel, ewBlocks(s.N), EW_THREADS, st, s, g);
+    launchKernel(fluidGatherKernel, ewBlocks(s.N), EW_THREADS, st, s, g);
 }
 void launchDensityLambda(const DeviceState& s, int model, const GridParams& g, const SphConsts& c, const FluidStepParams& p,
     const float4* pred, int nbrMode, int epoch, cudaStream_t st)
@@ -598,9 +598,9 @@ void launchDensityLambda(const DeviceState& s, int model, const GridParams& g, c
   if (!s.N)
     return;
   if (model == RTP_MODEL_CLOUDS)
-    launchPdl(densityLambdaKernel<TRAV_CLOUDS>, nbBlocks(s.N), NB_THREADS, st, s, g, c, p.f.restDensity, p.f.relaxCFM, pred, nbrMode, epoch);
+    launchKernel(densityLambdaKernel<TRAV_CLOUDS>, nbBlocks(s.N), NB_THREADS, st, s, g, c, p.f.restDensity, p.f.relaxCFM, pred, nbrMode, epoch);
   else
-    launchPdl(densityLambdaKernel<TRAV_FLUIDS>, nbBlocks(s.N), NB_THREADS, st, s, g, c, p.f.restDensity, p.f.relaxCFM, pred, nbrMode, epoch);
+    launchKernel(densityLambdaKernel<TRAV_FLUIDS>, nbBlocks(s.N), NB_THREADS, st, s, g, c, p.f.restDensity, p.f.relaxCFM, pred, nbrMode, epoch);
 }
 template <int TRAV, bool LAST>
 static void launchCorrectionArt(const DeviceState& s, const GridParams& g, const SphConsts& c, const FluidStepParams& p, const float4* pred,
@@ -608,11 +608,11 @@ static void launchCorrectionArt(const DeviceState& s, const GridParams& g, const
 {
   const int nb = nbBlocks(s.N);
   if (!p.f.isArtPressureEnabled)
-    launchPdl(correctionKernel<TRAV, LAST, -1>, nb, NB_THREADS, st, s, g, c, p, pred, predOut, wc, nbrMode, epoch);
+    launchKernel(correctionKernel<TRAV, LAST, -1>, nb, NB_THREADS, st, s, g, c, p, pred, predOut, wc, nbrMode, epoch);
   else if (p.f.artPressureExp == 4u)
-    launchPdl(correctionKernel<TRAV, LAST, 4>, nb, NB_THREADS, st, s, g, c, p, pred, predOut, wc, nbrMode, epoch);
+    launchKernel(correctionKernel<TRAV, LAST, 4>, nb, NB_THREADS, st, s, g, c, p, pred, predOut, wc, nbrMode, epoch);
   else
-    launchPdl(correctionKernel<TRAV, LAST, 0>, nb, NB_THREADS, st, s, g, c, p, pred, predOut, wc, nbrMode, epoch);
+    launchKernel(correctionKernel<TRAV, LAST, 0>, nb, NB_THREADS, st, s, g, c, p, pred, predOut, wc, nbrMode, epoch);
 }
 void launchCorrection(const DeviceState& s, int model, const GridParams& g, const SphConsts& c, const FluidStepParams& p,
     const rtp_cloud_params&, const float4* pred, float4* predOut, bool last, bool writeCorr, int nbrMode, int epoch, cudaStream_t st)
@@ -641,9 +641,9 @@ void launchVorticity(const DeviceState& s, int model, const GridParams& g, const
   if (!s.N)
     return;
   if (model == RTP_MODEL_CLOUDS)
-    launchPdl(vorticityKernel<TRAV_CLOUDS>, nbBlocks(s.N), NB_THREADS, st, s, g, c, pred, nbrMode, epoch);
+    launchKernel(vorticityKernel<TRAV_CLOUDS>, nbBlocks(s.N), NB_THREADS, st, s, g, c, pred, nbrMode, epoch);
   else
-    launchPdl(vorticityKernel<TRAV_FLUIDS>, nbBlocks(s.N), NB_THREADS, st, s, g, c, pred, nbrMode, epoch);
+    launchKernel(vorticityKernel<TRAV_FLUIDS>, nbBlocks(s.N), NB_THREADS, st, s, g, c, pred, nbrMode, epoch);
 }
 void launchConfinement(const DeviceState& s, int model, const GridParams& g, const SphConsts& c, const FluidStepParams& p,
     const float4* pred, int nbrMode, int epoch, cudaStream_t st)
@@ -651,9 +651,9 @@ void launchConfinement(const DeviceState& s, int model, const GridParams& g, con
   if (!s.N)
     return;
   if (model == RTP_MODEL_CLOUDS)
-    launchPdl(confinementKernel<TRAV_CLOUDS>, nbBlocks(s.N), NB_THREADS, st, s, g, c, p.f.vorticityConfCoeff, p.f.timeStep, pred, nbrMode, epoch);
+    launchKernel(confinementKernel<TRAV_CLOUDS>, nbBlocks(s.N), NB_THREADS, st, s, g, c, p.f.vorticityConfCoeff, p.f.timeStep, pred, nbrMode, epoch);
   else
-    launchPdl(confinementKernel<TRAV_FLUIDS>, nbBlocks(s.N), NB_THREADS, st, s, g, c, p.f.vorticityConfCoeff, p.f.timeStep, pred, nbrMode, epoch);
+    launchKernel(confinementKernel<TRAV_FLUIDS>, nbBlocks(s.N), NB_THREADS, st, s, g, c, p.f.vorticityConfCoeff, p.f.timeStep, pred, nbrMode, epoch);
 }
 void launchXsph(const DeviceState& s, int model, const GridParams& g, const SphConsts& c, const FluidStepParams& p,
     const rtp_cloud_params&, const float4* pred, int nbrMode, int epoch, cudaStream_t st)
@@ -661,42 +661,42 @@ void launchXsph(const DeviceState& s, int model, const GridParams& g, const SphC
   if (!s.N)
     return;
   if (model == RTP_MODEL_CLOUDS)
-    launchPdl(xsphKernel<TRAV_CLOUDS>, nbBlocks(s.N), NB_THREADS, st, s, g, c, p.f.xsphViscosityCoeff, pred, nbrMode, epoch);
+    launchKernel(xsphKernel<TRAV_CLOUDS>, nbBlocks(s.N), NB_THREADS, st, s, g, c, p.f.xsphViscosityCoeff, pred, nbrMode, epoch);
   else
-    launchPdl(xsphKernel<TRAV_FLUIDS>, nbBlocks(s.N), NB_THREADS, st, s, g, c, p.f.xsphViscosityCoeff, pred, nbrMode, epoch);
+    launchKernel(xsphKernel<TRAV_FLUIDS>, nbBlocks(s.N), NB_THREADS, st, s, g, c, p.f.xsphViscosityCoeff, pred, nbrMode, epoch);
 }
 void launchCloudsInitFields(const DeviceState& s, const GridParams& g, const rtp_cloud_params& cloud, cudaStream_t st)
 {
-  launchPdl(cloudsInitFieldsKernel, ewBlocks(s.M), EW_THREADS, st, s, g, cloud.initVaporDensityCoeff);
+  launchKernel(cloudsInitFieldsKernel, ewBlocks(s.M), EW_THREADS, st, s, g, cloud.initVaporDensityCoeff);
 }
 void launchCloudsThermoPredict(const DeviceState& s, const GridParams& g, const rtp_cloud_params& cloud, u32* keysOut, cudaStream_t st)
 {
-  launchPdl(cloudsThermoPredictKernel, ewBlocks(max(s.N, g.numCells)), EW_THREADS, st, s, g, cloud, keysOut);
+  launchKernel(cloudsThermoPredictKernel, ewBlocks(max(s.N, g.numCells)), EW_THREADS, st, s, g, cloud, keysOut);
 }
 void launchCloudsGather(const DeviceState& s, const GridParams& g, cudaStream_t st)
 {
   if (s.N)
-    launchPdl(cloudsGatherKernel, ewBlocks(s.N), EW_THREADS, st, s, g);
+    launchKernel(cloudsGatherKernel, ewBlocks(s.N), EW_THREADS, st, s, g);
 }
 void launchCloudsLaplacianTemp(const DeviceState& s, const GridParams& g, const SphConsts& c, const rtp_cloud_params& cloud, int nbrMode, cudaStream_t st)
 {
   if (s.N)
-    launchPdl(laplacianTempKernel, nbBlocks(s.N), NB_THREADS, st, s, g, c, cloud.restDensity, nbrMode);
+    launchKernel(laplacianTempKernel, nbBlocks(s.N), NB_THREADS, st, s, g, c, cloud.restDensity, nbrMode);
 }
 void launchCloudsLambdaTemp(const DeviceState& s, const GridParams& g, const SphConsts& c, const rtp_cloud_params& cloud, int nbrMode, cudaStream_t st)
 {
   if (s.N)
-    launchPdl(lambdaTempKernel, nbBlocks(s.N), NB_THREADS, st, s, g, c, cloud.restDensity, cloud.relaxCFM, nbrMode);
+    launchKernel(lambdaTempKernel, nbBlocks(s.N), NB_THREADS, st, s, g, c, cloud.restDensity, cloud.relaxCFM, nbrMode);
 }
 void launchCloudsCorrectTemp(const DeviceState& s, const GridParams& g, const SphConsts& c, const rtp_cloud_params& cloud, int nbrMode, cudaStream_t st)
 {
   if (s.N)
-    launchPdl(correctTempKernel, nbBlocks(s.N), NB_THREADS, st, s, g, c, cloud.restDensity, nbrMode);
+    launchKernel(correctTempKernel, nbBlocks(s.N), NB_THREADS, st, s, g, c, cloud.restDensity, nbrMode);
 }
 void launchCloudsFinish(const DeviceState& s, const GridParams& g, const rtp_cloud_params& cloud, const float4* pred, bool copyVel, cudaStream_t st)
 {
   if (s.N)
-    launchPdl(cloudsFinishKernel, ewBlocks(s.N), EW_THREADS, st, s, g, cloud, pred, copyVel ? 1 : 0);
+    launchKernel(cloudsFinishKernel, ewBlocks(s.N), EW_THREADS, st, s, g, cloud, pred, copyVel ? 1 : 0);
 }
 
 // ---- diagnostics: how the margin / hit lists of the last step would serve a sweep at the final predicted positions
@@ -733,7 +733,7 @@ __global__ void __launch_bounds__(EW_THREADS) listStatsKernel(DeviceState s, Gri
 void launchListStats(const DeviceState& s, const GridParams& g, const SphConsts& c, const float4* pred, unsigned long long* out, cudaStream_t st)
 {
   if (s.N)
-    launchPdl(listStatsKernel, ewBlocks(s.N), EW_THREADS, st, s, g, c, pred, out);
+    launchKernel(listStatsKernel, ewBlocks(s.N), EW_THREADS, st, s, g, c, pred, out);
 }
 
 } // namespace rtp

@@ -165,7 +165,7 @@ __global__ void __launch_bounds__(EW_THREADS) selftestMathKernel(u32 lo, u32 hi,
 }
 void launchSelftestMath(u32 lo, u32 hi, unsigned long long* bad, cudaStream_t st)
 {
-  launchPdl(selftestMathKernel, 148 * 8, EW_THREADS, st, lo, hi, bad);
+  launchKernel(selftestMathKernel, 148 * 8, EW_THREADS, st, lo, hi, bad);
 }
 
 // slab decomposition: drop the ghost copies after a step. Keys = "is ghost" (1 bit) -> one stable radix pass gives the
@@ -190,47 +190,47 @@ __global__ void __launch_bounds__(EW_THREADS) compactGatherKernel(DeviceState s,
 void launchGhostFlags(const DeviceState& s, u32* keysOut, cudaStream_t st)
 {
   if (s.N)
-    launchPdl(ghostFlagKernel, ewBlocks(s.N), EW_THREADS, st, s.perm, s.nOwned, keysOut, s.N);
+    launchKernel(ghostFlagKernel, ewBlocks(s.N), EW_THREADS, st, s.perm, s.nOwned, keysOut, s.N);
 }
 void launchCompactGather(const DeviceState& s, const u32* order, u32 n, cudaStream_t st)
 {
   if (n)
-    launchPdl(compactGatherKernel, ewBlocks(n), EW_THREADS, st, s, order, n);
+    launchKernel(compactGatherKernel, ewBlocks(n), EW_THREADS, st, s, order, n);
 }
 
 void launchResetIds(const DeviceState& s, u32 numCells, cudaStream_t st)
 {
-  launchPdl(resetIdsKernel, ewBlocks(s.M), EW_THREADS, st, s.cellID, s.cameraDist, s.perm, s.cameraPerm, s.M, numCells);
+  launchKernel(resetIdsKernel, ewBlocks(s.M), EW_THREADS, st, s.cellID, s.cameraDist, s.perm, s.cameraPerm, s.M, numCells);
 }
 void launchAdjustEndCell(const DeviceState& s, const GridParams& g, cudaStream_t st)
 {
-  launchPdl(adjustEndCellKernel, ewBlocks(g.numCells), EW_THREADS, st, s.table, g.numCells, g.maxPartsInCell);
+  launchKernel(adjustEndCellKernel, ewBlocks(g.numCells), EW_THREADS, st, s.table, g.numCells, g.maxPartsInCell);
 }
 void launchFillCameraDist(const DeviceState& s, const float cam[3], u32* keysOut, cudaStream_t st)
 {
   if (s.N)
-    launchPdl(fillCameraDistKernel, ewBlocks(s.N), EW_THREADS, st, s.posA, cam[0], cam[1], cam[2], keysOut, s.N);
+    launchKernel(fillCameraDistKernel, ewBlocks(s.N), EW_THREADS, st, s.posA, cam[0], cam[1], cam[2], keysOut, s.N);
 }
 void launchCameraGather(const DeviceState& s, int model, const float4* pred, float4* predOut, cudaStream_t st)
 {
   if (s.N)
-    launchPdl(cameraGatherKernel, ewBlocks(s.N), EW_THREADS, st, s, model, pred, predOut);
+    launchKernel(cameraGatherKernel, ewBlocks(s.N), EW_THREADS, st, s, model, pred, predOut);
 }
 void launchGridDetector(const DeviceState& s, const GridParams& g, cudaStream_t st)
 {
-  launchPdl(resetGridDetectorKernel, ewBlocks((size_t)g.numCells * 2), EW_THREADS, st, (float4*)s.partDetector, g.numCells * 2);
+  launchKernel(resetGridDetectorKernel, ewBlocks((size_t)g.numCells * 2), EW_THREADS, st, (float4*)s.partDetector, g.numCells * 2);
   if (s.N)
-    launchPdl(fillGridDetectorKernel, ewBlocks(s.N), EW_THREADS, st, s.posA, g, (float4*)s.partDetector, s.N);
+    launchKernel(fillGridDetectorKernel, ewBlocks(s.N), EW_THREADS, st, s.posA, g, (float4*)s.partDetector, s.N);
 }
 void launchFillFluidColor(const DeviceState& s, float restDensity, cudaStream_t st)
 {
   if (s.N)
-    launchPdl(fillFluidColorKernel, ewBlocks(s.N), EW_THREADS, st, s.density, restDensity, s.col, s.N);
+    launchKernel(fillFluidColorKernel, ewBlocks(s.N), EW_THREADS, st, s.density, restDensity, s.col, s.N);
 }
 void launchFillColorFloat(const DeviceState& s, const float* quantity, float minVal, float maxVal, cudaStream_t st)
 {
   if (s.N)
-    launchPdl(fillColorFloatKernel, ewBlocks(s.N), EW_THREADS, st, quantity, minVal, maxVal, s.col, s.N);
+    launchKernel(fillColorFloatKernel, ewBlocks(s.N), EW_THREADS, st, quantity, minVal, maxVal, s.col, s.N);
 }
 
 } // namespace rtp

@@ -24,7 +24,7 @@ typedef uint32_t u32;
 // Programmatic dependent launch (sm_90+), compile-time option RTP_USE_PDL: 0 = plain stream order (default: measured
 // fastest on the 130k step), 1 = every kernel lets its successor start launching CTAs at once and
 // waits for its predecessor's memory (cudaGridDependencySynchronize), 2 = wait only (the successor is released when the
-// predecessor's CTAs have exited). All launches go through launchPdl(), also inside a captured CUDA graph.
+// predecessor's CTAs have exited). All launches go through launchKernel(), also inside a captured CUDA graph.
 #ifndef RTP_USE_PDL
 #define RTP_USE_PDL 0
 #endif
@@ -45,7 +45,7 @@ typedef uint32_t u32;
 #endif
 
 template <typename... P, typename... A>
-inline void launchPdl(void (*kernel)(P...), unsigned grid, unsigned block, cudaStream_t st, A&&... args)
+inline void launchKernel(void (*kernel)(P...), unsigned grid, unsigned block, cudaStream_t st, A&&... args)
 {
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(grid, 1, 1);

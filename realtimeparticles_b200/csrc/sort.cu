@@ -243,10 +243,10 @@ int enqueueSortPasses(const SortPlan& plan, u32* keys0, u32* vals0, u32* keys1, 
     u32* ticket = ctrl + SORT_MAX_PASSES * SORT_RADIX + p;
     const u32* gh = ctrl + p * SORT_RADIX;
     if (plan.itemsPerThread == 4)
-      launchPdl(onesweepPassKernel<4>, plan.tiles, SORT_THREADS, stream, kbuf[src], vin, kbuf[dst], vbuf[dst], plan.n,
+      launchKernel(onesweepPassKernel<4>, plan.tiles, SORT_THREADS, stream, kbuf[src], vin, kbuf[dst], vbuf[dst], plan.n,
           desc.shift[p], desc.mask[p], gh, st, ticket);
     else
-      launchPdl(onesweepPassKernel<16>, plan.tiles, SORT_THREADS, stream, kbuf[src], vin, kbuf[dst], vbuf[dst], plan.n,
+      launchKernel(onesweepPassKernel<16>, plan.tiles, SORT_THREADS, stream, kbuf[src], vin, kbuf[dst], vbuf[dst], plan.n,
           desc.shift[p], desc.mask[p], gh, st, ticket);
     ++launches;
   }
@@ -267,7 +267,7 @@ int enqueueSort(const SortPlan& plan, u32* keys0, u32* vals0, u32* keys1, u32* v
     blocks = 148 * 8;
   if (blocks < 1)
     blocks = 1;
-  launchPdl(sortHistogramKernel, blocks, SORT_THREADS, stream, kbuf[first], plan.n, plan.passes, desc, ctrl, status,
+  launchKernel(sortHistogramKernel, blocks, SORT_THREADS, stream, kbuf[first], plan.n, plan.passes, desc, ctrl, status,
       sortStatusWords(plan));
   return 1 + enqueueSortPasses(plan, keys0, vals0, keys1, vals1, ctrl, status, stream);
 }
