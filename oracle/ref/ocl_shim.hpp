@@ -182,7 +182,12 @@ inline float dot(float3 a, float3 b) { return std::fma(a.z, b.z, std::fma(a.y, b
 inline float fast_length(float4 a) { return std::sqrt(dot(a, a)); }
 inline float length(float4 a) { return std::sqrt(dot(a, a)); }
 inline float length(float3 a) { return std::sqrt(dot(a, a)); }
-inline float4 fast_normalize(float4 a) { return a * (1.0f / std::sqrt(dot(a, a))); }
+// OpenCL 1.2 s6.12.5: a vector whose elements are all zero is returned unchanged (tested as dot == 0, like the oracle)
+inline float4 fast_normalize(float4 a)
+{
+  const float d = dot(a, a);
+  return d == 0.0f ? a : a * (1.0f / std::sqrt(d));
+}
 inline float4 normalize(float4 a)
 {
   const float l = std::sqrt(dot(a, a));

@@ -12,7 +12,8 @@
  *   (build with -ffp-contract=off). Element-wise stages follow the .cl expression order literally.
  *   dot(a,b)      = fma(a.z,b.z, fma(a.y,b.y, a.x*b.x))   (w is always 0 on this path)
  *   fast_length   = length = sqrtf(dot(v,v))
- *   fast_normalize(v) = v * (1.0f / sqrtf(dot(v,v)))        (0 -> NaN, as a native rsqrt would give)
+ *   fast_normalize(v) = v * (1.0f / sqrtf(dot(v,v))), fast_normalize(0) = 0   (OpenCL 1.2 s6.12.5: "if all elements
+ *                   of x are zero, returns x"; tested as dot(v,v) == 0)
  *   normalize(v)  = v / sqrtf(dot(v,v)), normalize(0) = 0
  *   step(e,x)     = x < e ? 0 : 1 ; clamp(x,lo,hi) = fmin(fmax(x,lo),hi) ; convert_uint = truncation
  *   exp           = canon_expf / canon_exp below: Cody-Waite reduction by ln2 (hi+lo) and a Taylor-Horner polynomial
@@ -107,7 +108,10 @@ static inline float dotc(f4 a, f4 b) { return fmaf(a.z, b.z, fmaf(a.y, b.y, a.x 
 static inline float lengthc(f4 v) { return sqrtf(dotc(v, v)); }
 static inline f4 fast_normalizec(f4 v)
 {
-  const float r = 1.0f / sqrtf(dotc(v, v));
+  const float d = dotc(v, v);
+  if (d == 0.0f)
+    return v;
+  const float r = 1.0f / sqrtf(d);
   return mul4s(v, r);
 }
 static inline f4 normalizec(f4 v)

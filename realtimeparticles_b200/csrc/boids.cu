@@ -16,6 +16,17 @@ namespace rtp
 {
 constexpr int BD_THREADS = 128;
 
+// fast_normalize(v) = v * (1 / sqrt(dot(v, v))), and a zero vector is returned unchanged (OpenCL 1.2 s6.12.5; the test is
+// dot == 0, as in the oracle)
+__device__ __forceinline__ float4 fastNormalize(const float4 v)
+{
+  const float d = dot3c(v.x, v.y, v.z, v.x, v.y, v.z);
+  if (d == 0.0f)
+    return v;
+  const float r = fdiv(1.0f, fsqrt(d));
+  return make_float4(fmul(v.x, r), fmul(v.y, r), fmul(v.z, r), fmul(v.w, r));
+}
+
 __device__ __forceinline__ void fillCellTable(const u32* __restrict__ keys, u32 i, u32 N, u32 numCells, uint2* __restrict__ table)
 {
   const u32 id = keys[i];
@@ -56,8 +67,7 @@ __global__ void __launch_bounds__(256) boidsGatherKernel(DeviceState s, GridPara
   const float4 v = s.velA[j];
   s.velB[i] = v;
   // fast_normalize(velocity[e]) (boids.cl:104) depends on e only: do it once per particle, exactly
-  const float r = fdiv(1.0f, fsqrt(dot3c(v.x, v.y, v.z, v.x, v.y, v.z)));
-  s.velC[i] = make_float4(fmul(v.x, r), fmul(v.y, r), fmul(v.z, r), fmul(v.w, r));
+  s.velC[i] = fastNormalize(v);
   fillCellTable(s.cellID, i, s.N, g.numCells, s.table);
 }
 
@@ -117,28 +127,21 @@ __global__ void __launch_bounds__(BD_THREADS) boidsRulesKernel(DeviceState s, Gr
       }
   }
 
-  // From here on the w lane is carried like the reference's float4 arithmetic does: it is 0 unless a
-  // fast_normalize() of a zero vector poisons it (0 * inf = NaN), and the oracle reproduces exactly that.
+  // The w lane is carried like the reference's float4 arithmetic does (it stays 0 on this path).
   float ax = 0.f, ay = 0.f, az = 0.f, aw = 0.f;
   if (count != 0)
   {
     // boids.cl:115-131
     const float fc = (float)count;
     const float vs = p.rules.velocityScale;
-    apx = fsub(fdiv(apx, fc), pi.x); apy = fsub(fdiv(apy, fc), pi.y); apz = fsub(fdiv(apz, fc), pi.z);
-    float r = fdiv(1.0f, fsqrt(dot3c(apx, apy, apz, apx, apy, apz)));
-    apx = fmul(fmul(apx, r), vs); apy = fmul(fmul(apy, r), vs); apz = fmul(fmul(apz, r), vs);
-    const float apw = fmul(fmul(0.0f, r), vs);
-    r = fdiv(1.0f, fsqrt(dot3c(avx, avy, avz, avx, avy, avz)));
-    avx = fmul(fmul(avx, r), vs); avy = fmul(fmul(avy, r), vs); avz = fmul(fmul(avz, r), vs);
-    const float avw = fmul(fmul(0.0f, r), vs);
-    r = fdiv(1.0f, fsqrt(dot3c(rpx, rpy, rpz, rpx, rpy, rpz)));
-    rpx = fmul(fmul(rpx, r), vs); rpy = fmul(fmul(rpy, r), vs); rpz = fmul(fmul(rpz, r), vs);
-    const float rpw = fmul(fmul(0.0f, r), vs);
-    ax = fadd(fadd(fmul(avx, p.rules.alignmentScale), fmul(rpx, p.rules.separationScale)), fmul(apx, p.rules.cohesionScale));
-    ay = fadd(fadd(fmul(avy, p.rules.alignmentScale), fmul(rpy, p.rules.separationScale)), fmul(apy, p.rules.cohesionScale));
-    az = fadd(fadd(fmul(avz, p.rules.alignmentScale), fmul(rpz, p.rules.separationScale)), fmul(apz, p.rules.cohesionScale));
-    aw = fadd(fadd(fmul(avw, p.rules.alignmentScale), fmul(rpw, p.rules.separationScale)), fmul(apw, p.rules.cohesionScale));
+    const float4 ap = fastNormalize(make_float4(fsub(fdiv(apx, fc), pi.x), fsub(fdiv(apy, fc), pi.y), fsub(fdiv(apz, fc), pi.z), 0.0f));
+    const float4 av = fastNormalize(make_float4(avx, avy, avz, 0.0f));
+    const float4 rp = fastNormalize(make_float4(rpx, rpy, rpz, 0.0f));
+    const float al = p.rules.alignmentScale, se = p.rules.separationScale, co = p.rules.cohesionScale;
+    ax = fadd(fadd(fmul(fmul(av.x, vs), al), fmul(fmul(rp.x, vs), se)), fmul(fmul(ap.x, vs), co));
+    ay = fadd(fadd(fmul(fmul(av.y, vs), al), fmul(fmul(rp.y, vs), se)), fmul(fmul(ap.y, vs), co));
+    az = fadd(fadd(fmul(fmul(av.z, vs), al), fmul(fmul(rp.z, vs), se)), fmul(fmul(ap.z, vs), co));
+    aw = fadd(fadd(fmul(fmul(av.w, vs), al), fmul(fmul(rp.w, vs), se)), fmul(fmul(ap.w, vs), co));
   }
 
   // bd_addTargetRule boids.cl:226-241
@@ -164,8 +167,8 @@ __global__ void __launch_bounds__(BD_THREADS) boidsRulesKernel(DeviceState s, Gr
   const float nvx = fadd(vi.x, fmul(ax, p.dt)), nvy = fadd(vi.y, fmul(ay, p.dt)), nvz = fadd(vi.z, fmul(az, p.dt)), nvw = fadd(vi.w, fmul(aw, p.dt));
   const float len = fsqrt(dot3c(nvx, nvy, nvz, nvx, nvy, nvz));
   const float norm = fclamp(len, fmul(0.2f, maxV), maxV);
-  const float rn = fdiv(1.0f, len);
-  float vx = fmul(fmul(nvx, rn), norm), vy = fmul(fmul(nvy, rn), norm), vz = fmul(fmul(nvz, rn), norm), vw = fmul(fmul(nvw, rn), norm);
+  const float4 nn = fastNormalize(make_float4(nvx, nvy, nvz, nvw));
+  float vx = fmul(nn.x, norm), vy = fmul(nn.y, norm), vz = fmul(nn.z, norm), vw = fmul(nn.w, norm);
 
   // bd_updatePosAndApplyWallBC boids.cl:264-284 / bd_updatePosAndApplyPeriodicBC :289-315
   const float npx = fadd(pi.x, fmul(vx, p.dt)), npy = fadd(pi.y, fmul(vy, p.dt)), npz = fadd(pi.z, fmul(vz, p.dt));

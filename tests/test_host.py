@@ -163,3 +163,30 @@ def test_cpp_dropin_library_exports():
     for name in ("rtpm_create", "rtpm_destroy", "rtpm_update", "rtpm_reset", "rtpm_update_input_json", "rtpm_get_input_json",
                  "rtpm_handle", "rtpm_nb_particles", "rtpm_is_init", "rtpm_pause", "rtpm_set_boundary", "rtpm_set_step_flags"):
         assert hasattr(L, name), name
+
+
+def test_oracle_boids_config1_loses_no_boid():
+    # BASELINE config 1 on the oracle: with fast_normalize(0) = 0 (OpenCL 1.2 s6.12.5) no boid turns NaN over 300 steps
+    # (the NaN-propagating variant had lost 9 % of them by step 200); the CUDA path runs the full 1000 steps bit-exact
+    # against this in tests/test_gpu_parity.py
+    from scenarios import make_boids
+    p = make_boids(M=131072, N=512, gpu=False)
+    for _ in range(300):
+        p.w.step(O.STEP_PHYSICS)
+    pos, vel = p.w.download("POS")[:512], p.w.download("VEL")[:512]
+    assert np.isfinite(pos).all() and np.isfinite(vel).all()
+    assert (np.abs(pos[:, :3] + 5.0).max(axis=1) < 1e-6).sum() == 0
+
+
+def test_oracle_fast_normalize_zero_vector():
+    # one boid pair placed symmetrically so that a rule sum cancels exactly: acceleration stays finite
+    verts = np.array([[0.1, 0.0, 0.0, 0.0], [-0.1, 0.0, 0.0, 0.0], [0.0, 0.1, 0.0, 0.0]], np.float32)
+    w = O.World(O.BOIDS, 1024, 3)
+    pos = np.full((1024, 4), np.inf, np.float32)
+    pos[:, 3] = 0
+    pos[:3] = verts
+    w.upload("POS", pos)
+    w.upload("VEL", np.zeros((1024, 4), np.float32))  # fast_normalize(velocity[e]) of zero velocities
+    w.reset_ids()
+    w.step(O.STEP_PHYSICS)
+    assert np.isfinite(w.download("ACC")[:3]).all() and np.isfinite(w.download("VEL")[:3]).all()
