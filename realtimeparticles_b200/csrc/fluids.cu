@@ -315,6 +315,42 @@ __global__ void __launch_bounds__(NB_THREADS, NB_MIN_BLOCKS) densityLambdaKernel
       });
 }
 
+// The same sweep as the list BUILD of a step (first Jacobi iteration): block-cooperative, candidates from shared-memory
+// tiles staged by TMA (tilebuild.cuh)
+template <int TRAV>
+__global__ void __launch_bounds__(NB_THREADS, NB_MIN_BLOCKS) densityLambdaBuildKernel(DeviceState s, GridParams g, SphConsts c, float rho0, float cfm,
+    const float4* __restrict__ pred, int epoch)
+{
+  RTP_PDL_PROLOGUE();
+  __shared__ TileSmem sm;
+  const u32 i = blockIdx.x * NB_THREADS + threadIdx.x;
+  const bool active = i < s.N;
+  const float4 pi = active ? pred[i] : make_float4(0.f, 0.f, 0.f, 0.f);
+  float density = 0.f, gx = 0.f, gy = 0.f, gz = 0.f, sumG2 = 0.f;
+  const bool done = sweepProducerBuildTiled<TRAV>(sm, g, c, s, pred, pi, i, active, epoch,
+      [&](u32, float dx, float dy, float dz, float sq)
+      {
+        const float cs = spikyCoefOrZero(c, sq);
+        return PairTerm<6> { { fmul(c.poly6, poly6nc(c, sq)), cs, dx, dy, dz, fmul(fmul(cs, cs), sq) } };
+      },
+      [&](const PairTerm<6>& t)
+      {
+        density = fadd(density, t.v[0]);
+        gx = ffma(t.v[2], t.v[1], gx);
+        gy = ffma(t.v[3], t.v[1], gy);
+        gz = ffma(t.v[4], t.v[1], gz);
+        sumG2 = fadd(sumG2, t.v[5]);
+      });
+  if (!done)
+    return;
+  s.density[i] = density;
+  // fluids.cl:189-192
+  const float densityC = fsub(fdiv(density, rho0), 1.0f);
+  float ssg = fadd(sumG2, dot3c(gx, gy, gz, gx, gy, gz));
+  ssg = fdiv(ssg, fmul(rho0, rho0));
+  s.lambda[i] = fdiv(-densityC, fadd(ssg, cfm));
+}
+
 // ART: artificial pressure compiled in as -1 = off, 4 = exponent 4 (the reference's default), 0 = as the parameters say
 template <int TRAV, bool LAST, int ART>
 __global__ void __launch_bounds__(NB_THREADS, NB_MIN_BLOCKS) correctionKernel(DeviceState s, GridParams g, SphConsts c, FluidStepParams fp,
@@ -529,6 +565,28 @@ __global__ void __launch_bounds__(NB_THREADS, NB_MIN_BLOCKS) laplacianTempKernel
       });
 }
 
+// the same sweep as the block-cooperative list build of the temperature epoch (tilebuild.cuh)
+__global__ void __launch_bounds__(NB_THREADS, NB_MIN_BLOCKS) laplacianTempBuildKernel(DeviceState s, GridParams g, SphConsts c, float rho0)
+{
+  RTP_PDL_PROLOGUE();
+  __shared__ TileSmem sm;
+  const float* __restrict__ T = s.tempB;
+  const u32 i = blockIdx.x * NB_THREADS + threadIdx.x;
+  const bool active = i < s.N;
+  const float4 pi = active ? s.posB[i] : make_float4(0.f, 0.f, 0.f, 0.f);
+  const float Ti = active ? T[i] : 0.f;
+  float lap = 0.f;
+  const bool done = sweepProducerBuildTiled<TRAV_CLOUDS>(sm, g, c, s, s.posB, pi, i, active, NBR_EPOCH_TEMP,
+      [&](u32 e, float, float, float, float sq)
+      {
+        const float cs = spikyCoefOrZero(c, sq);
+        return PairTerm<2> { { fmul(fsub(Ti, __ldg(T + e)), fmul(cs, sq)), rcpInRange(fadd(sq, RTP_FLOAT_EPS)) } };
+      },
+      [&](const PairTerm<2>& t) { lap = ffma(t.v[0], t.v[1], lap); });
+  if (done)
+    s.lapTemp[i] = fdiv(lap, rho0);
+}
+
 // cld_computeConstraintFactorTemp clouds.cl:575-648
 __global__ void __launch_bounds__(NB_THREADS, NB_MIN_BLOCKS) lambdaTempKernel(DeviceState s, GridParams g, SphConsts c, float rho0, float cfm, int nbrMode)
 {
@@ -597,6 +655,15 @@ void launchDensityLambda(const DeviceState& s, int model, const GridParams& g, c
 {
   if (!s.N)
     return;
+  static_assert(NB_THREADS == TB_THREADS, "tilebuild.cuh is written for the neighbour kernels' block size");
+  if (nbrMode == NBR_BUILD && s.tiledBuild)
+  {
+    if (model == RTP_MODEL_CLOUDS)
+      launchKernel(densityLambdaBuildKernel<TRAV_CLOUDS>, nbBlocks(s.N), NB_THREADS, st, s, g, c, p.f.restDensity, p.f.relaxCFM, pred, epoch);
+    else
+      launchKernel(densityLambdaBuildKernel<TRAV_FLUIDS>, nbBlocks(s.N), NB_THREADS, st, s, g, c, p.f.restDensity, p.f.relaxCFM, pred, epoch);
+    return;
+  }
   if (model == RTP_MODEL_CLOUDS)
     launchKernel(densityLambdaKernel<TRAV_CLOUDS>, nbBlocks(s.N), NB_THREADS, st, s, g, c, p.f.restDensity, p.f.relaxCFM, pred, nbrMode, epoch);
   else
@@ -680,7 +747,9 @@ void launchCloudsGather(const DeviceState& s, const GridParams& g, cudaStream_t 
 }
 void launchCloudsLaplacianTemp(const DeviceState& s, const GridParams& g, const SphConsts& c, const rtp_cloud_params& cloud, int nbrMode, cudaStream_t st)
 {
-  if (s.N)
+  if (s.N && nbrMode == NBR_BUILD && s.tiledBuild)
+    launchKernel(laplacianTempBuildKernel, nbBlocks(s.N), NB_THREADS, st, s, g, c, cloud.restDensity);
+  else if (s.N)
     launchKernel(laplacianTempKernel, nbBlocks(s.N), NB_THREADS, st, s, g, c, cloud.restDensity, nbrMode);
 }
 void launchCloudsLambdaTemp(const DeviceState& s, const GridParams& g, const SphConsts& c, const rtp_cloud_params& cloud, int nbrMode, cudaStream_t st)

@@ -38,6 +38,8 @@ struct DeviceState
   u32 *hitList = nullptr, *hitCount = nullptr;
   u32 *stragQueue = nullptr, *stragCount = nullptr, *stragCursor = nullptr; // straggler queue of the producer sweeps (sweep.cuh), counters per epoch
   u32 hitCap = 0;
+  int tiledBuild = 0; // the list build of a step runs block-cooperatively (tilebuild.cuh)
+  u32* buildStats = nullptr; // tilebuild.cuh counters: { warps on the per-thread build, -, CTAs over the tile capacity }
 };
 
 // how a neighbour sweep treats the per-step neighbour lists

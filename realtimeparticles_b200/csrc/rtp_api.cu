@@ -321,6 +321,12 @@ extern "C" int rtp_create(const rtp_config* cfg, rtp_handle** out)
       CREATE_TRY(devAlloc(h, &s.stragQueue, M));
       CREATE_TRY(devAlloc(h, &s.stragCount, (size_t)NBR_EPOCHS));
       CREATE_TRY(devAlloc(h, &s.stragCursor, (size_t)NBR_EPOCHS));
+      CREATE_TRY(devAlloc(h, &s.buildStats, (size_t)4));
+      // block-cooperative list build (tilebuild.cuh): word descriptors keep 27 bits for the index, the slot logic needs
+      // >= 4 cells per axis; RTP_TILED_BUILD=0 selects the per-thread build (bit-identical lists, slower)
+      s.tiledBuild = (M <= (1u << 27) && cfg->grid[0] >= 4 && cfg->grid[1] >= 4 && cfg->grid[2] >= 4) ? 1 : 0;
+      if (const char* e = getenv("RTP_TILED_BUILD"))
+        s.tiledBuild = s.tiledBuild && atoi(e) != 0;
     }
   }
   if (model == RTP_MODEL_CLOUDS)

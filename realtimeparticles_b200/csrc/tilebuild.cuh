@@ -1,0 +1,542 @@
+// tilebuild.cuh -- block-cooperative, shared-memory-staged build of the per-step neighbour lists (sweep.cuh).
+//
+// The first sweep of a step visits, per particle, the 27 cells around the particle's current cell (fluids.cl:101-123):
+// ~460 candidates of which ~110 are within the list radius (1 + margin) h and ~70 inside the support. One thread walking
+// its own ragged runs with a gather and two divergent appends per candidate needed ~40 thread instructions per candidate
+// at 20 of 32 lanes (round 1: 185 us of a 650 us step). Here a CTA of 128 consecutive cell-sorted particles works as a team:
+//
+//  WINDOWS. For a particle, the three z cells of one (iX, iY) neighbour column are one contiguous index run of the
+//   cell-sorted position array (ids are z-fastest); a z wrap splits it into "pre | main | post" runs, so a particle has
+//   27 SLOTS = 9 columns x {pre, main, post}, visited in the reference's order (pre/post are almost always empty). The
+//   lanes of a warp that sit in the same (x, y) column have overlapping runs: per slot and lane GROUP (lanes of one
+//   column, found by leader election) the warp WINDOW is the union [min start, max end].
+//  STAGING. Per neighbour column the windows of the CTA's warps are merged into disjoint index segments; consecutive
+//   columns are packed into STAGES that fit the tile (usually three stages of three columns), and a stage is copied into
+//   shared memory with 1-D TMA bulk copies (cp.async.bulk, one per segment, completion on an mbarrier). The resident
+//   CTAs of an SM are in different phases, so the copies of one run under the filter of the others.
+//  FILTER. Every lane tests ALL candidates of its warp's window in lock step: the candidate is one broadcast LDS.128 for
+//   the whole warp, the test the squared distance against the list radius (3 FADD, FMUL, 2 FFMA, FSETP), the result one
+//   bit of a 32-candidate mask word. No divergence, no per-lane addresses. Candidates of the window outside the lane's
+//   own run (another lane's cell) are removed per word with a range mask, so a lane keeps exactly the reference's
+//   candidate set; words no lane needs (a hole between two families of runs) are skipped.
+//  WALK. After each stage every lane walks the set bits of its buffered words in order (= the reference's order: slots
+//   ascending, index ascending) and hands each candidate (entry, position from the tile) to the caller, which appends it
+//   to the margin list, applies the exact support test and runs the sweep's pair term (sweep.cuh).
+//  FALLBACK. A warp whose lanes cannot be described this way (a cap or start = 1 quirk breaks a run, more than NGROUP
+//   columns in one warp, windows larger than the tile) builds its lists with the per-thread 27-cell traversal. Both
+//   paths emit the same candidates in the same order.
+#pragma once
+
+#include "kernels.cuh"
+
+namespace rtp
+{
+constexpr int TB_THREADS = 128; // == the neighbour kernels' block size
+constexpr int TB_WARPS = TB_THREADS / 32;
+constexpr u32 TILE_STAGE_CAP = 1088; // positions one stage may hold: 128 + 2 x 101 (cell cap) per column, x 3
+constexpr u32 TILE_PAD = 32; // the filter reads whole 32-candidate words: over-read room behind the last window
+constexpr int WORD_BUF = 12; // mask words a warp buffers between two walks
+constexpr int NSLOT = 27;
+constexpr int NGROUP = 4; // lane groups of a warp (lanes with the same centre column)
+constexpr int SEG_MAX = TB_WARPS * NGROUP + 4; // staged index segments of one column
+constexpr int WIN_MAX = 6; // non-empty windows of one warp in one column (usually 1)
+constexpr u32 TB_INDEX_BITS = 27; // word descriptor = global index of bit 0 | slot << 27
+constexpr u32 TB_INDEX_MASK = (1u << TB_INDEX_BITS) - 1u;
+
+struct __align__(16) TileSmem
+{
+  float4 tile[TILE_STAGE_CAP + TILE_PAD];
+  u32 words[TB_WARPS][WORD_BUF][32];
+  u32 wordDesc[TB_WARPS][WORD_BUF]; // global index of bit 0 | slot << 27
+  u32 wordTile[TB_WARPS][WORD_BUF]; // tile index of bit 0
+  // per warp and neighbour column: its non-empty windows in slot order: (first index, last index, slot | group << 8, -)
+  uint4 winList[TB_WARPS][9][WIN_MAX];
+  u32 winCount[TB_WARPS][9];
+  // per neighbour column: the windows the warps registered, then the directory of its staged segments (sorted, disjoint)
+  uint2 ranges[9][SEG_MAX];
+  u32 rangeCount[9];
+  u32 segStart[9][SEG_MAX], segEnd[9][SEG_MAX], segOff[9][SEG_MAX]; // segOff: offset inside the column's part of the tile
+  u32 segCount[9];
+  u32 colLen[9], colOff[9]; // positions staged for the column; offset of the column's part inside the tile of its stage
+  u32 stageFirst[10]; // stage k covers the columns stageFirst[k] .. stageFirst[k + 1] - 1
+  u32 nStages;
+  u32 stageHasData;
+  u32 overflow;
+  unsigned long long bar;
+};
+
+// image code of a list entry: bits 28-29 x image, bits 30-31 z image (0: none, 1: +2W, 2: -2W); same encoding as sweep.cuh
+__device__ __forceinline__ u32 imageCode(float sx, float sz)
+{
+  const u32 cx = sx > 0.0f ? 1u : (sx < 0.0f ? 2u : 0u), cz = sz > 0.0f ? 1u : (sz < 0.0f ? 2u : 0u);
+  return (cx << 28) | (cz << 30);
+}
+
+// ---------------------------------------------------------------- slots
+
+// image shift of a wrapped neighbour cell (clouds.cl:334-347): raw index beyond the grid -> +2W, below -> -2W
+__device__ __forceinline__ float wrapShift(int raw, int res, float absW) { return raw >= res ? 2.0f * absW : (raw < 0 ? -2.0f * absW : 0.0f); }
+
+struct LaneShifts
+{
+  float sx[3]; // by iX + 1
+  float sz[3]; // by kind: pre, main, post
+};
+// (v + R) % R for v in [-R, 2R): the neighbour-cell indices are in [-1, R + 1]
+__device__ __forceinline__ int wrapIndex(int v, int R) { return v < 0 ? v + R : (v >= R ? v - R : v); }
+
+template <int TRAV>
+__device__ __forceinline__ LaneShifts laneShifts(const GridParams& g, const int3 ci)
+{
+  LaneShifts r;
+#pragma unroll
+  for (int k = 0; k < 3; ++k)
+  {
+    r.sx[k] = TRAV == TRAV_CLOUDS ? wrapShift(ci.x + k - 1, g.res[0], g.absW[0]) : 0.0f;
+    r.sz[k] = 0.0f;
+  }
+  if (TRAV == TRAV_CLOUDS)
+  {
+    const int RZ = g.res[2];
+    const int z0 = wrapIndex(ci.z - 1, RZ), z1 = wrapIndex(ci.z, RZ), z2 = wrapIndex(ci.z + 1, RZ);
+    const bool break01 = z1 != z0 + 1, break12 = z2 != z1 + 1;
+    r.sz[1] = wrapShift(ci.z, RZ, g.absW[2]);
+    r.sz[0] = break01 ? wrapShift(ci.z - 1, RZ, g.absW[2]) : r.sz[1];
+    r.sz[2] = break12 ? wrapShift(ci.z + 1, RZ, g.absW[2]) : r.sz[1];
+  }
+  return r;
+}
+
+// The runs of one lane in the neighbour column (iX, iY): rs/re[kind] (kind 0 = pre, 1 = main, 2 = post), inclusive
+// global indices, empty = (0xFFFFFFFF, 0). Returns false when the column cannot be described by at most one ascending
+// run per kind (a capped or start = 1 cell breaks the contiguity): the warp then takes the fallback path.
+template <int TRAV>
+__device__ __forceinline__ bool laneColumn(const GridParams& g, const uint2* __restrict__ table, const int3 ci, const int iX, const int iY,
+    const bool active, u32 (&rs)[3], u32 (&re)[3])
+{
+#pragma unroll
+  for (int k = 0; k < 3; ++k)
+  {
+    rs[k] = 0xFFFFFFFFu;
+    re[k] = 0u;
+  }
+  if (!active)
+    return true;
+  const int RX = g.res[0], RY = g.res[1], RZ = g.res[2];
+  int cx = ci.x + iX, cy = ci.y + iY;
+  if (TRAV == TRAV_BOIDS)
+  {
+    if (cx < 0 || cx >= RX)
+      return true;
+  }
+  else
+    cx = wrapIndex(cx, RX);
+  if (TRAV == TRAV_FLUIDS)
+    cy = wrapIndex(cy, RY);
+  else if (cy < 0 || cy >= RY)
+    return true;
+  const uint2* __restrict__ row = table + (cx * RY + cy) * RZ;
+  int zm[3];
+  uint2 se[3];
+#pragma unroll
+  for (int k = 0; k < 3; ++k)
+  {
+    const int zr = ci.z + k - 1;
+    bool skip = false;
+    if (TRAV == TRAV_BOIDS)
+    {
+      skip = zr < 0 || zr >= RZ;
+      zm[k] = zr;
+    }
+    else
+      zm[k] = wrapIndex(zr, RZ);
+    se[k] = skip ? make_uint2(1u, 0u) : __ldg(row + zm[k]);
+  }
+  const bool break01 = TRAV != TRAV_BOIDS && zm[1] != zm[0] + 1, break12 = TRAV != TRAV_BOIDS && zm[2] != zm[1] + 1;
+  bool ok = true;
+#pragma unroll
+  for (int k = 0; k < 3; ++k)
+  {
+    if (se[k].x > se[k].y)
+      continue;
+    const int kind = k == 0 ? (break01 ? 0 : 1) : (k == 2 ? (break12 ? 2 : 1) : 1);
+    // (kind is a compile-time function of k and two predicates: select the slot with predicated moves)
+#pragma unroll
+    for (int q = 0; q < 3; ++q)
+      if (q == kind)
+      {
+        if (rs[q] > re[q])
+        {
+          rs[q] = se[k].x;
+          re[q] = se[k].y;
+        }
+        else if (re[q] + 1u == se[k].x)
+          re[q] = se[k].y;
+        else
+          ok = false;
+      }
+  }
+  return ok;
+}
+
+// ---------------------------------------------------------------- TMA / mbarrier primitives (sm_90+)
+
+__device__ __forceinline__ u32 smemAddr(const void* p) { return (u32)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbarInit(unsigned long long* bar, u32 count)
+{
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smemAddr(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbarExpectTx(unsigned long long* bar, u32 bytes)
+{
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smemAddr(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbarWait(unsigned long long* bar, u32 parity)
+{
+  u32 ok = 0u;
+  do
+  {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+        "selp.u32 %0, 1, 0, p;\n"
+        "}\n"
+        : "=r"(ok)
+        : "r"(smemAddr(bar)), "r"(parity)
+        : "memory");
+  } while (ok == 0u);
+}
+// 1-D bulk copy global -> shared, bytes a multiple of 16, both addresses 16-byte aligned; completes on the mbarrier
+__device__ __forceinline__ void tmaLoad1D(void* dstSmem, const void* srcGlobal, u32 bytes, unsigned long long* bar)
+{
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smemAddr(dstSmem)),
+               "l"(srcGlobal), "r"(bytes), "r"(smemAddr(bar))
+               : "memory");
+}
+
+// ---------------------------------------------------------------- the builder
+
+// Stream, in the reference's order, every candidate of particle i (position pi) that is closer than sqrt(radiusSq) to
+// it: onCandidate(entry, pj) with entry = index | image code (sweep.cuh) and pj = the candidate's position. Every thread
+// of the CTA must call (inactive threads: active = false). Returns false -- before any candidate has been handed out --
+// when this warp has to build with the per-thread traversal instead. stats: optional counters { irregular warps, -,
+// CTAs over the tile capacity }.
+template <int TRAV, typename CandF>
+__device__ __forceinline__ bool tileBuildCandidates(TileSmem& sm, const GridParams& g, const float radiusSq, const uint2* __restrict__ table,
+    const float4* __restrict__ P, const float4 pi, const bool active, u32* __restrict__ stats, CandF&& onCandidate)
+{
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int3 ci = cell3D(g, pi.x, pi.y, pi.z);
+  const LaneShifts sh = laneShifts<TRAV>(g, ci);
+
+  if (tid < 9)
+    sm.rangeCount[tid] = 0u;
+  if (tid == 0)
+  {
+    sm.overflow = 0u;
+    mbarInit(&sm.bar, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  // lane groups: the runs of lanes with the same centre column overlap or touch (the lanes are consecutive in the sorted
+  // order); lanes in different columns have runs that can be far apart (columns of different height), hence one window
+  // per group. Groups are formed by leader election; a warp with more than NGROUP columns (very sparse particles) is
+  // irregular.
+  bool regular = true;
+  int grp = NGROUP;
+  {
+    unsigned todo = __ballot_sync(0xFFFFFFFFu, active);
+#pragma unroll
+    for (int gq = 0; gq < NGROUP; ++gq)
+    {
+      if (todo == 0u)
+        break;
+      const int leader = __ffs(todo) - 1;
+      const int lx = __shfl_sync(0xFFFFFFFFu, ci.x, leader), ly = __shfl_sync(0xFFFFFFFFu, ci.y, leader);
+      const bool same = active && grp == NGROUP && ci.x == lx && ci.y == ly;
+      if (same)
+        grp = gq;
+      todo &= ~__ballot_sync(0xFFFFFFFFu, same);
+    }
+    if (todo != 0u)
+      regular = false;
+  }
+  __syncthreads();
+
+  // ---- pass A: the windows of this warp (27 slots x NGROUP groups; only the non-empty ones are kept), registered with the CTA
+  if (lane < 9)
+    sm.winCount[warp][lane] = 0u;
+  __syncwarp();
+#pragma unroll 1
+  for (int col = 0; col < 9; ++col)
+  {
+    u32 rs[3], re[3];
+    regular &= laneColumn<TRAV>(g, table, ci, col / 3 - 1, col % 3 - 1, active, rs, re);
+#pragma unroll
+    for (int kind = 0; kind < 3; ++kind)
+    {
+      const bool mine = rs[kind] <= re[kind];
+      if (!__any_sync(0xFFFFFFFFu, mine))
+        continue;
+#pragma unroll
+      for (int gq = 0; gq < NGROUP; ++gq)
+      {
+        const bool in = mine && grp == gq;
+        if (!__any_sync(0xFFFFFFFFu, in))
+          continue;
+        const u32 ws = __reduce_min_sync(0xFFFFFFFFu, in ? rs[kind] : 0xFFFFFFFFu), we = __reduce_max_sync(0xFFFFFFFFu, in ? re[kind] : 0u);
+        if (lane == 0)
+        {
+          const u32 kw = sm.winCount[warp][col];
+          if (kw < (u32)WIN_MAX)
+          {
+            sm.winList[warp][col][kw] = make_uint4(ws, we, (u32)(col * 3 + kind) | ((u32)gq << 8), 0u);
+            sm.winCount[warp][col] = kw + 1u;
+          }
+          const u32 k = atomicAdd(&sm.rangeCount[col], 1u);
+          if (kw >= (u32)WIN_MAX || k >= (u32)SEG_MAX)
+            sm.overflow = 1u;
+          else
+            sm.ranges[col][k] = make_uint2(ws, we);
+        }
+      }
+    }
+  }
+  const bool warpRegular = __all_sync(0xFFFFFFFFu, regular);
+  if (!warpRegular && lane == 0 && stats)
+    atomicAdd(stats + 0, 1u);
+  __syncthreads();
+
+  // ---- the tile directory: per column, sort the registered windows and merge overlapping / touching ones
+  if (sm.overflow == 0u)
+  {
+#pragma unroll 1
+    for (int col = warp; col < 9; col += TB_WARPS)
+    {
+      const u32 n = sm.rangeCount[col];
+      uint2 r = (u32)lane < n ? sm.ranges[col][lane] : make_uint2(0xFFFFFFFFu, 0u);
+      u32 rank = 0u;
+      for (u32 j = 0; j < n; ++j)
+      {
+        const u32 sj = __shfl_sync(0xFFFFFFFFu, r.x, j);
+        rank += (sj < r.x || (sj == r.x && j < (u32)lane)) ? 1u : 0u;
+      }
+      __syncwarp();
+      if ((u32)lane < n)
+        sm.ranges[col][rank] = r;
+      __syncwarp();
+      r = (u32)lane < n ? sm.ranges[col][lane] : make_uint2(0xFFFFFFFFu, 0u);
+      u32 pm = (u32)lane < n ? r.y : 0u; // inclusive prefix maximum of the ends
+#pragma unroll
+      for (int off = 1; off < SEG_MAX; off <<= 1)
+      {
+        const u32 t = __shfl_up_sync(0xFFFFFFFFu, pm, off);
+        if (lane >= off)
+          pm = max(pm, t);
+      }
+      const u32 prevMax = __shfl_up_sync(0xFFFFFFFFu, pm, 1);
+      const bool head = (u32)lane < n && (lane == 0 || r.x > prevMax + 1u);
+      const unsigned hb = __ballot_sync(0xFFFFFFFFu, head);
+      const unsigned above = lane == 31 ? 0u : (hb & (0xFFFFFFFFu << (lane + 1)));
+      const int lastLane = above ? (__ffs(above) - 2) : (int)n - 1;
+      const u32 segEnd = __shfl_sync(0xFFFFFFFFu, pm, lastLane < 0 ? 0 : lastLane);
+      const u32 len = head ? segEnd - r.x + 1u : 0u;
+      u32 incl = len;
+#pragma unroll
+      for (int off = 1; off < SEG_MAX; off <<= 1)
+      {
+        const u32 t = __shfl_up_sync(0xFFFFFFFFu, incl, off);
+        if (lane >= off)
+          incl += t;
+      }
+      if (head)
+      {
+        const u32 k = __popc(hb & ((1u << lane) - 1u));
+        sm.segStart[col][k] = r.x;
+        sm.segEnd[col][k] = segEnd;
+        sm.segOff[col][k] = incl - len;
+      }
+      const u32 total = __shfl_sync(0xFFFFFFFFu, incl, SEG_MAX - 1);
+      if (lane == 0)
+      {
+        sm.segCount[col] = __popc(hb);
+        sm.colLen[col] = total;
+        if (total > TILE_STAGE_CAP)
+          sm.overflow = 1u;
+      }
+    }
+  }
+  __syncthreads();
+  if (tid == 0 && sm.overflow == 0u)
+  {
+    // pack consecutive columns into stages that fit the tile
+    u32 ns = 0u, fill = 0u;
+    sm.stageFirst[0] = 0u;
+    for (u32 col = 0; col < 9u; ++col)
+    {
+      if (fill + sm.colLen[col] > TILE_STAGE_CAP)
+      {
+        sm.stageFirst[++ns] = col;
+        fill = 0u;
+      }
+      sm.colOff[col] = fill;
+      fill += sm.colLen[col];
+    }
+    sm.stageFirst[++ns] = 9u;
+    sm.nStages = ns;
+  }
+  __syncthreads();
+  const bool useTiles = sm.overflow == 0u;
+  if (!useTiles && tid == 0 && stats)
+    atomicAdd(stats + 2, 1u);
+  if (!useTiles)
+    return false; // (uniform for the CTA: nobody is left behind at a barrier)
+
+  // one thread: one bulk copy per staged segment of the stage's columns behind one mbarrier phase; false: nothing to stage
+  auto issueStage = [&](u32 stage) -> bool
+  {
+    u32 total = 0u;
+    for (u32 col = sm.stageFirst[stage]; col < sm.stageFirst[stage + 1]; ++col)
+      total += sm.colLen[col];
+    if (total == 0u)
+      return false;
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    mbarExpectTx(&sm.bar, total * (u32)sizeof(float4));
+    for (u32 col = sm.stageFirst[stage]; col < sm.stageFirst[stage + 1]; ++col)
+      for (u32 k = 0; k < sm.segCount[col]; ++k)
+        tmaLoad1D(&sm.tile[sm.colOff[col] + sm.segOff[col][k]], P + sm.segStart[col][k],
+            (sm.segEnd[col][k] - sm.segStart[col][k] + 1u) * (u32)sizeof(float4), &sm.bar);
+    return true;
+  };
+  // tile index of global index `idx` of column `col` (the whole warp asks for the same idx, which lies inside a staged segment)
+  auto tileIndex = [&](int col, u32 idx) -> u32
+  {
+    const bool hit = (u32)lane < sm.segCount[col] && sm.segStart[col][lane] <= idx && idx <= sm.segEnd[col][lane];
+    const int k = __ffs(__ballot_sync(0xFFFFFFFFu, hit)) - 1;
+    return sm.colOff[col] + sm.segOff[col][k] + (idx - sm.segStart[col][k]);
+  };
+
+  // (clouds: the filter uses the shifted centre pi - shift, one rounding away from the canonical (pi - pj) - shift; the
+  //  list radius has 12 % of slack and the caller applies the exact support test)
+  const float filterSq = radiusSq;
+
+  // hand the candidates of the buffered words to the caller: per lane, set bits in word order
+  auto flush = [&](u32& used, const float4* tileBuf)
+  {
+    __syncwarp();
+    u32 nz = 0u;
+    for (u32 w = 0; w < used; ++w)
+      nz |= (sm.words[warp][w][lane] != 0u ? 1u : 0u) << w;
+    // one candidate per lane and iteration; moving on to the lane's next non-empty word is a find-first-set on nz (lanes
+    // reach the end of a word at different iterations: a per-word loop would run with a handful of lanes)
+    u32 m = 0u, base = 0u, tb = 0u;
+    for (;;)
+    {
+      if (m == 0u)
+      {
+        if (nz == 0u)
+          break;
+        const u32 j = __ffs(nz) - 1u;
+        nz &= nz - 1u;
+        m = sm.words[warp][j][lane];
+        const u32 desc = sm.wordDesc[warp][j];
+        tb = sm.wordTile[warp][j];
+        u32 code = 0u;
+        if (TRAV == TRAV_CLOUDS)
+        {
+          const u32 slot = desc >> TB_INDEX_BITS;
+          const u32 col = slot / 3u, kind = slot - col * 3u, ix = col / 3u;
+          code = imageCode(ix == 0u ? sh.sx[0] : (ix == 1u ? sh.sx[1] : sh.sx[2]), kind == 0u ? sh.sz[0] : (kind == 1u ? sh.sz[1] : sh.sz[2]));
+        }
+        base = (desc & TB_INDEX_MASK) | code;
+      }
+      const u32 b = __ffs(m) - 1u;
+      m &= m - 1u;
+      onCandidate(base + b, tileBuf[tb + b]);
+    }
+    used = 0u;
+    __syncwarp();
+  };
+
+  {
+    u32 phase = 0u;
+    const u32 nStages = sm.nStages;
+#pragma unroll 1
+    for (u32 stage = 0; stage < nStages; ++stage)
+    {
+      __syncthreads(); // every warp is through with the previous stage's tile
+      if (tid == 0)
+        sm.stageHasData = issueStage(stage) ? 1u : 0u;
+      __syncthreads();
+      if (sm.stageHasData == 0u)
+        continue;
+      mbarWait(&sm.bar, phase);
+      phase ^= 1u;
+      if (!warpRegular)
+        continue;
+      const float4* tileBuf = sm.tile;
+      u32 used = 0u;
+#pragma unroll 1
+      for (int col = (int)sm.stageFirst[stage]; col < (int)sm.stageFirst[stage + 1]; ++col)
+      {
+        const u32 nWin = sm.winCount[warp][col];
+        if (nWin == 0u)
+          continue;
+        const int ix = col / 3;
+        u32 rs[3], re[3];
+        laneColumn<TRAV>(g, table, ci, ix - 1, col - ix * 3 - 1, active, rs, re);
+        const float px = TRAV == TRAV_CLOUDS ? pi.x - (ix == 0 ? sh.sx[0] : (ix == 1 ? sh.sx[1] : sh.sx[2])) : pi.x, py = pi.y;
+#pragma unroll 1
+        for (u32 kw = 0; kw < nWin; ++kw)
+        {
+          const uint4 wl = sm.winList[warp][col][kw];
+          const int slot = (int)(wl.z & 0xFFu), gq = (int)(wl.z >> 8), kind = slot - col * 3;
+          const float pz = TRAV == TRAV_CLOUDS ? pi.z - (kind == 0 ? sh.sz[0] : (kind == 1 ? sh.sz[1] : sh.sz[2])) : pi.z;
+          // this lane's own run, if it belongs to the group
+          const bool in = grp == gq;
+          const u32 s0 = !in ? 0xFFFFFFFFu : (kind == 0 ? rs[0] : (kind == 1 ? rs[1] : rs[2]));
+          const u32 e0 = !in ? 0u : (kind == 0 ? re[0] : (kind == 1 ? re[1] : re[2]));
+          const u32 tileBase = tileIndex(col, wl.x);
+          const u32 nW = ((wl.y - wl.x) >> 5) + 1u;
+#pragma unroll 1
+          for (u32 w = 0; w < nW; ++w)
+          {
+            const u32 B = wl.x + 32u * w;
+            // the candidates of this word that are in the lane's own run [s0, e0]
+            u32 rm = 0u;
+            if (s0 <= e0 && s0 <= B + 31u && e0 >= B)
+            {
+              const u32 lo = s0 > B ? s0 - B : 0u, hi = e0 < B + 31u ? e0 - B : 31u;
+              rm = (0xFFFFFFFFu >> (31u - hi)) & (0xFFFFFFFFu << lo);
+            }
+            if (!__any_sync(0xFFFFFFFFu, rm != 0u))
+              continue; // nobody's run reaches into this word (a hole between two families of runs)
+            if (used == (u32)WORD_BUF)
+              flush(used, tileBuf);
+            const float4* __restrict__ tp = tileBuf + tileBase + 32u * w;
+            u32 m = 0u;
+#pragma unroll
+            for (int k = 0; k < 32; ++k)
+            {
+              const float4 q = tp[k];
+              const float dx = px - q.x, dy = py - q.y, dz = pz - q.z;
+              const float sq = dot3c(dx, dy, dz, dx, dy, dz);
+              if (sq < filterSq)
+                m |= 1u << k;
+            }
+            sm.words[warp][used][lane] = m & rm;
+            if (lane == 0)
+            {
+              sm.wordDesc[warp][used] = B | ((u32)slot << TB_INDEX_BITS);
+              sm.wordTile[warp][used] = tileBase + 32u * w;
+            }
+            ++used;
+          }
+        }
+      }
+      flush(used, tileBuf);
+    }
+  }
+  return warpRegular;
+}
+
+} // namespace rtp

@@ -160,8 +160,9 @@ def test_lists_on_off_bit_identical(monkeypatch):
     # also when the margin is so small that the lists are invalidated and rebuilt inside the step
     outs = []
     for env in ({"RTP_NBR_LISTS": "0"}, {"RTP_NBR_LISTS": "1"}, {"RTP_NBR_LISTS": "1", "RTP_NBR_MARGIN": "0.02"},
-                {"RTP_NBR_LISTS": "1", "RTP_NBR_CAP": "64", "RTP_HIT_CAP": "48"}):
-        for k in ("RTP_NBR_LISTS", "RTP_NBR_MARGIN", "RTP_NBR_CAP", "RTP_HIT_CAP"):
+                {"RTP_NBR_LISTS": "1", "RTP_NBR_CAP": "64", "RTP_HIT_CAP": "48"}, {"RTP_NBR_LISTS": "1", "RTP_TILED_BUILD": "0"},
+                {"RTP_NBR_LISTS": "1", "RTP_TILED_BUILD": "0", "RTP_NBR_MARGIN": "0.02"}):
+        for k in ("RTP_NBR_LISTS", "RTP_NBR_MARGIN", "RTP_NBR_CAP", "RTP_HIT_CAP", "RTP_TILED_BUILD"):
             monkeypatch.delenv(k, raising=False)
         for k, v in env.items():
             monkeypatch.setenv(k, v)
