@@ -242,6 +242,15 @@ RTP_API int64_t rtp_gen_random_box(float* out_xyzw, int64_t n, const float start
 /* the float a reference kernel sees for a -D constant: parse(FloatToStr(v)) (utils/Utils.cpp:24-29) */
 RTP_API float rtp_baked_constant(float v);
 
+/* ---- boids target trajectory (host side; replaces Physics::Target, physics/utils/Target.cpp:11-50 with its three
+ * PerlinNoise channels, physics/utils/PerlinNoise.cpp:10-85). The reference moves the target once per frame on the CPU
+ * (Boids.cpp:351-358) and hands the position to bd_addTargetRule; a host does the same with rtp_target_update() and
+ * rtp_set_boids_params(). dim: 2 or 3. */
+typedef struct rtp_target rtp_target;
+RTP_API rtp_target* rtp_target_create(uint32_t box_size);
+RTP_API void rtp_target_destroy(rtp_target* t);
+RTP_API int rtp_target_update(rtp_target* t, int dim, float particles_velocity, float out_pos[3]);
+
 /* ---- multi-GPU slab decomposition (new design; fluids model) ----
  * One handle per GPU over the GLOBAL box/grid (cell ids stay global); it holds the rank's owned particles followed by
  * ghost copies of its slab neighbours' boundary layers. The kernels are the single-GPU ones; the caller

@@ -3,6 +3,7 @@
 // baked -D constants used by the oracle and by the product's generators.
 #include "Geometry.hpp"
 #include "Utils.hpp"
+#include "Target.hpp" // physics/utils/Target.hpp (+ PerlinNoise), unmodified
 
 #include <cstdlib>
 #include <cstring>
@@ -55,4 +56,17 @@ void ref_float_to_str(float v, char* out, size_t cap)
   out[cap - 1] = 0;
 }
 void ref_srand(unsigned seed) { srand(seed); }
+
+// the reference's boids target trajectory (physics/utils/Target.cpp + PerlinNoise.cpp)
+void* ref_target_create(unsigned boxSize) { return new Physics::Target(boxSize); }
+void ref_target_destroy(void* t) { delete (Physics::Target*)t; }
+void ref_target_update(void* t, int dim, float vel, float out[3])
+{
+  Physics::Target* tg = (Physics::Target*)t;
+  tg->updatePos(dim == 3 ? Geometry::Dimension::dim3D : Geometry::Dimension::dim2D, vel);
+  const auto p = tg->pos();
+  out[0] = p.x;
+  out[1] = p.y;
+  out[2] = p.z;
+}
 }

@@ -131,3 +131,20 @@ def float_to_str(v):
     buf = C.create_string_buffer(64)
     glib().ref_float_to_str(float(v), buf, 64)
     return buf.value.decode()
+
+
+def target_trajectory(box_size, dim, velocity, steps):
+    """positions of the reference's own Physics::Target (physics/utils/Target.cpp + PerlinNoise.cpp) over `steps` updates"""
+    L = glib()
+    L.ref_target_create.restype = C.c_void_p
+    L.ref_target_create.argtypes = [C.c_uint]
+    L.ref_target_destroy.argtypes = [C.c_void_p]
+    L.ref_target_update.argtypes = [C.c_void_p, C.c_int, C.c_float, C.POINTER(C.c_float)]
+    t = C.c_void_p(L.ref_target_create(int(box_size)))
+    out = np.empty((steps, 3), np.float32)
+    buf = (C.c_float * 3)()
+    for k in range(steps):
+        L.ref_target_update(t, int(dim), float(velocity), buf)
+        out[k] = (buf[0], buf[1], buf[2])
+    L.ref_target_destroy(t)
+    return out

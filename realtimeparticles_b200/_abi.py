@@ -82,7 +82,7 @@ EXPORTS = ["rtp_abi_version", "rtp_device_count", "rtp_create", "rtp_destroy", "
            "rtp_sync", "rtp_get_stream", "rtp_sort_keys", "rtp_sort_keys_host", "rtp_selftest_math", "rtp_enable_profiling", "rtp_get_stage_times",
            "rtp_last_launch_count", "rtp_list_stats", "rtp_shard_set_owned", "rtp_shard_stage", "rtp_shard_buffer", "rtp_shard_list_dmax_sq",
            "rtp_gen_box_grid", "rtp_gen_sphere_grid", "rtp_gen_rectangle_grid", "rtp_gen_circle_grid", "rtp_gen_random_box",
-           "rtp_baked_constant"]
+           "rtp_baked_constant", "rtp_target_create", "rtp_target_destroy", "rtp_target_update"]
 
 _lib = None
 
@@ -318,6 +318,29 @@ class Handle:
         self._check(self.L.rtp_list_stats(self.h, out), "rtp_list_stats")
         keys = ("particles", "margin_overflow", "cell_changed", "reserved", "sum_len", "max_len", "hit_overflow", "moved_beyond_bound")
         return dict(zip(keys, [int(v) for v in out]))
+
+
+class Target:
+    """Host-side boids target trajectory (rtp_target_*; replaces Physics::Target, physics/utils/Target.cpp)."""
+
+    def __init__(self, box_size):
+        L = lib()
+        L.rtp_target_create.restype = C.c_void_p
+        L.rtp_target_create.argtypes = [C.c_uint32]
+        L.rtp_target_destroy.argtypes = [C.c_void_p]
+        L.rtp_target_update.argtypes = [C.c_void_p, C.c_int, C.c_float, C.POINTER(C.c_float)]
+        self.L, self.t = L, C.c_void_p(L.rtp_target_create(int(box_size)))
+
+    def update(self, dim, velocity):
+        out = (C.c_float * 3)()
+        if self.L.rtp_target_update(self.t, int(dim), float(velocity), out) != 0:
+            raise RtpError("rtp_target_update failed")
+        return (float(out[0]), float(out[1]), float(out[2]))
+
+    def __del__(self):
+        if getattr(self, "t", None):
+            self.L.rtp_target_destroy(self.t)
+            self.t = None
 
 
 def gen_box_grid(res, start, end):

@@ -9,6 +9,9 @@
 #include <stdlib.h>
 #include <string.h>
 
+#include <algorithm>
+#include <numeric>
+#include <random>
 #include <string>
 #include <vector>
 
@@ -47,6 +50,7 @@ struct rtp_handle
   unsigned graphFlags = 0;
   float graphCam[3] = { 0, 0, 0 };
   bool graphValid = false;
+  float4* graphPredFinal = nullptr; // p_predPos buffer at the start of the captured step
   int lastLaunches = 0;
   // profiling
   bool profiling = false;
@@ -299,35 +303,61 @@ extern "C" int rtp_create(const rtp_config* cfg, rtp_handle** out)
     // list entries keep 28 bits for the particle index (sweep.cuh)
     if (M > (1u << 28))
       h->nbrEnabled = false;
+    // The lists are an optimisation ((nbrCap + hitCap) * 4 B = 1.66 kB per particle of max_particles): when they cannot be
+    // allocated the sweeps run the plain 27-cell traversal, which is bit-identical.
+#define LIST_TRY(expr)                       \
+  do                                         \
+  {                                          \
+    if (listsOk && (expr) != cudaSuccess)    \
+    {                                        \
+      (void)cudaGetLastError();              \
+      listsOk = false;                       \
+    }                                        \
+  } while (0)
     if (h->nbrEnabled)
     {
+      bool listsOk = true;
+      const size_t firstListAlloc = h->allocs.size();
       u32 cap = 256;
       if (const char* e = getenv("RTP_NBR_CAP"))
         cap = (u32)atoi(e);
       cap = (cap + 3u) & ~3u;
       s.nbrCap = cap;
       s.nbrStride = (u32)M;
-      CREATE_TRY(devAlloc(h, &s.nbrList, (size_t)cap * M));
-      CREATE_TRY(devAlloc(h, &s.nbrCount, M));
-      CREATE_TRY(devAlloc(h, &s.nbrBuildPos, M));
-      CREATE_TRY(devAlloc(h, &s.nbrInvalid, (size_t)NBR_EPOCHS));
+      LIST_TRY(devAlloc(h, &s.nbrList, (size_t)cap * M));
+      LIST_TRY(devAlloc(h, &s.nbrCount, M));
+      LIST_TRY(devAlloc(h, &s.nbrBuildPos, M));
+      LIST_TRY(devAlloc(h, &s.nbrInvalid, (size_t)NBR_EPOCHS));
       u32 hcap = 160;
       if (const char* e = getenv("RTP_HIT_CAP"))
         hcap = (u32)atoi(e);
       hcap = (hcap + 3u) & ~3u;
       s.hitCap = hcap;
-      CREATE_TRY(devAlloc(h, &s.hitList, (size_t)hcap * M));
-      CREATE_TRY(devAlloc(h, &s.hitCount, M));
-      CREATE_TRY(devAlloc(h, &s.stragQueue, M));
-      CREATE_TRY(devAlloc(h, &s.stragCount, (size_t)NBR_EPOCHS));
-      CREATE_TRY(devAlloc(h, &s.stragCursor, (size_t)NBR_EPOCHS));
-      CREATE_TRY(devAlloc(h, &s.buildStats, (size_t)4));
+      LIST_TRY(devAlloc(h, &s.hitList, (size_t)hcap * M));
+      LIST_TRY(devAlloc(h, &s.hitCount, M));
+      LIST_TRY(devAlloc(h, &s.stragQueue, M));
+      LIST_TRY(devAlloc(h, &s.stragCount, (size_t)NBR_EPOCHS));
+      LIST_TRY(devAlloc(h, &s.stragCursor, (size_t)NBR_EPOCHS));
+      LIST_TRY(devAlloc(h, &s.buildStats, (size_t)4));
       // block-cooperative list build (tilebuild.cuh): word descriptors keep 27 bits for the index, the slot logic needs
       // >= 4 cells per axis; RTP_TILED_BUILD=0 selects the per-thread build (bit-identical lists, slower)
       s.tiledBuild = (M <= (1u << 27) && cfg->grid[0] >= 4 && cfg->grid[1] >= 4 && cfg->grid[2] >= 4) ? 1 : 0;
       if (const char* e = getenv("RTP_TILED_BUILD"))
         s.tiledBuild = s.tiledBuild && atoi(e) != 0;
+      if (getenv("RTP_TEST_FAIL_LIST_ALLOC")) // (tests: exercise the out-of-memory path)
+        listsOk = false;
+      if (!listsOk)
+      {
+        for (size_t k = firstListAlloc; k < h->allocs.size(); ++k)
+          cudaFree(h->allocs[k]);
+        h->allocs.resize(firstListAlloc);
+        s.nbrList = s.nbrCount = s.nbrInvalid = s.hitList = s.hitCount = s.stragQueue = s.stragCount = s.stragCursor = s.buildStats = nullptr;
+        s.nbrBuildPos = nullptr;
+        s.tiledBuild = 0;
+        h->nbrEnabled = false;
+      }
     }
+#undef LIST_TRY
   }
   if (model == RTP_MODEL_CLOUDS)
   {
@@ -484,7 +514,14 @@ extern "C" int rtp_set_fluid_params(rtp_handle* h, const rtp_fluid_params* fluid
   if (h->cfg.model == RTP_MODEL_BOIDS)
     return fail(h, RTP_ERR_STATE, "not a fluids/clouds model");
   if (fluid)
+  {
+    // the ranges of the reference's UI (Fluids.cpp:52-74): the exponent is an unrolled product of 1..6 factors, and a
+    // radius factor >= 1 puts the reference distance outside the kernel support (division by poly6 = 0)
+    if (fluid->isArtPressureEnabled
+        && (fluid->artPressureExp < 1u || fluid->artPressureExp > 6u || !(fluid->artPressureRadius > 0.0f && fluid->artPressureRadius < 1.0f)))
+      return fail(h, RTP_ERR_INVALID, "artificial pressure: exponent must be in [1, 6] and the radius factor in (0, 1)");
     h->fp.f = *fluid;
+  }
   if (nb_jacobi_iters > 0)
     h->jacobi = nb_jacobi_iters;
   updateDerivedFluidParams(h);
@@ -813,21 +850,35 @@ extern "C" int rtp_step_n(rtp_handle* h, unsigned flags, const float camera_pos[
     return RTP_OK;
   const float* cam = camera_pos ? camera_pos : kDefaultCam;
   CUDA_TRY(h, cudaSetDevice(h->cfg.device));
-  if (!h->graphValid || h->graphFlags != flags || memcmp(h->graphCam, cam, sizeof h->graphCam) != 0)
+  // the captured graph bakes in the flags, the camera and the buffer p_predPos currently lives in (the camera sort reads it)
+  if (!h->graphValid || h->graphFlags != flags || memcmp(h->graphCam, cam, sizeof h->graphCam) != 0 || h->graphPredFinal != h->predFinal)
   {
     if (h->graphExec)
     {
       cudaGraphExecDestroy(h->graphExec);
       h->graphExec = nullptr;
     }
+    h->graphValid = false;
     cudaGraph_t graph = nullptr;
+    float4* const predBefore = h->predFinal;
     CUDA_TRY(h, cudaStreamBeginCapture(h->stream, cudaStreamCaptureModeThreadLocal));
     h->lastLaunches = enqueueStep(h, flags, cam, false);
-    CUDA_TRY(h, cudaStreamEndCapture(h->stream, &graph));
-    CUDA_TRY(h, cudaGraphInstantiate(&h->graphExec, graph, 0));
-    cudaGraphDestroy(graph);
+    cudaError_t e = cudaStreamEndCapture(h->stream, &graph); // always ends the capture, also after a failed launch
+    if (e == cudaSuccess)
+      e = cudaGraphInstantiate(&h->graphExec, graph, 0);
+    if (graph)
+      cudaGraphDestroy(graph);
+    if (e != cudaSuccess)
+    {
+      (void)cudaGetLastError();
+      h->graphExec = nullptr;
+      h->predFinal = predBefore;
+      h->err = std::string("rtp_step_n: graph capture failed: ") + cudaGetErrorString(e);
+      return RTP_ERR_CUDA;
+    }
     h->graphFlags = flags;
     memcpy(h->graphCam, cam, sizeof h->graphCam);
+    h->graphPredFinal = predBefore;
     h->graphValid = true;
   }
   for (int i = 0; i < n; ++i)
@@ -991,17 +1042,26 @@ extern "C" int rtp_sort_keys(rtp_handle* h, const uint32_t* d_keys_in, uint32_t*
   CUDA_TRY(h, cudaSetDevice(h->cfg.device));
   const SortPlan plan = makeSortPlan((u32)n, key_bits);
   u32 *k1 = nullptr, *v1 = nullptr, *ctrl = nullptr, *status = nullptr;
-  CUDA_TRY(h, cudaMalloc(&k1, n * 4));
-  CUDA_TRY(h, cudaMalloc(&v1, n * 4));
-  CUDA_TRY(h, cudaMalloc(&ctrl, SORT_CTRL_WORDS * 4));
-  CUDA_TRY(h, cudaMalloc(&status, sortStatusWords(plan) * 4));
-  u32* start = (plan.passes % 2 == 0) ? d_keys_out : k1;
-  cudaMemcpyAsync(start, d_keys_in, n * 4, cudaMemcpyDeviceToDevice, h->stream);
-  enqueueSort(plan, d_keys_out, d_perm_out, k1, v1, ctrl, status, h->stream);
-  cudaError_t e = cudaStreamSynchronize(h->stream);
+  cudaError_t e = cudaMalloc(&k1, n * 4);
   if (e == cudaSuccess)
-    e = cudaGetLastError();
-  cudaFree(k1);
+    e = cudaMalloc(&v1, n * 4);
+  if (e == cudaSuccess)
+    e = cudaMalloc(&ctrl, SORT_CTRL_WORDS * 4);
+  if (e == cudaSuccess)
+    e = cudaMalloc(&status, sortStatusWords(plan) * 4);
+  if (e == cudaSuccess)
+  {
+    u32* start = (plan.passes % 2 == 0) ? d_keys_out : k1;
+    e = cudaMemcpyAsync(start, d_keys_in, n * 4, cudaMemcpyDeviceToDevice, h->stream);
+  }
+  if (e == cudaSuccess)
+  {
+    enqueueSort(plan, d_keys_out, d_perm_out, k1, v1, ctrl, status, h->stream);
+    e = cudaStreamSynchronize(h->stream);
+    if (e == cudaSuccess)
+      e = cudaGetLastError();
+  }
+  cudaFree(k1); // (cudaFree(nullptr) is a no-op: every path releases what it got)
   cudaFree(v1);
   cudaFree(ctrl);
   cudaFree(status);
@@ -1018,16 +1078,20 @@ extern "C" int rtp_sort_keys_host(rtp_handle* h, const uint32_t* keys_in, uint32
     return RTP_OK;
   CUDA_TRY(h, cudaSetDevice(h->cfg.device));
   u32 *din = nullptr, *dk = nullptr, *dp = nullptr;
-  CUDA_TRY(h, cudaMalloc(&din, n * 4));
-  CUDA_TRY(h, cudaMalloc(&dk, n * 4));
-  CUDA_TRY(h, cudaMalloc(&dp, n * 4));
-  cudaMemcpyAsync(din, keys_in, n * 4, cudaMemcpyHostToDevice, h->stream);
-  int rc = rtp_sort_keys(h, din, dk, dp, n, key_bits);
+  int rc = RTP_OK;
+  if (cudaMalloc(&din, n * 4) != cudaSuccess || cudaMalloc(&dk, n * 4) != cudaSuccess || cudaMalloc(&dp, n * 4) != cudaSuccess
+      || cudaMemcpyAsync(din, keys_in, n * 4, cudaMemcpyHostToDevice, h->stream) != cudaSuccess)
+  {
+    (void)cudaGetLastError();
+    rc = fail(h, RTP_ERR_CUDA, "rtp_sort_keys_host: device scratch allocation or upload failed");
+  }
+  if (rc == RTP_OK)
+    rc = rtp_sort_keys(h, din, dk, dp, n, key_bits);
   if (rc == RTP_OK)
   {
-    cudaMemcpyAsync(keys_out, dk, n * 4, cudaMemcpyDeviceToHost, h->stream);
-    cudaMemcpyAsync(perm_out, dp, n * 4, cudaMemcpyDeviceToHost, h->stream);
-    if (cudaStreamSynchronize(h->stream) != cudaSuccess)
+    if (cudaMemcpyAsync(keys_out, dk, n * 4, cudaMemcpyDeviceToHost, h->stream) != cudaSuccess
+        || cudaMemcpyAsync(perm_out, dp, n * 4, cudaMemcpyDeviceToHost, h->stream) != cudaSuccess
+        || cudaStreamSynchronize(h->stream) != cudaSuccess)
       rc = fail(h, RTP_ERR_CUDA, "rtp_sort_keys_host: copy back failed");
   }
   cudaFree(din);
@@ -1231,4 +1295,84 @@ extern "C" int64_t rtp_gen_random_box(float* out, int64_t n, const float start[3
     for (int k = 0; k < 4; ++k)
       out[4 * i + k] = (k < 3) ? (float)rand() / (float)RAND_MAX * (end[k] - start[k]) + start[k] : 0.0f;
   return n;
+}
+
+// ------------------------------------------------------------------ boids target trajectory (host)
+
+// The boids target wanders on a pseudo-random path driven by three Perlin-noise channels (physics/utils/Target.cpp:11-50,
+// physics/utils/PerlinNoise.cpp:10-85); the reference evaluates it on the CPU once per frame (Boids.cpp:351-358) and so
+// does this backend. The permutation tables come from std::shuffle over std::default_random_engine(seed), like the
+// reference's: the same C++ library gives the same tables.
+namespace
+{
+struct NoiseChannel
+{
+  std::vector<int> perm;
+  explicit NoiseChannel(int seed) : perm(256)
+  {
+    std::iota(perm.begin(), perm.end(), 0);
+    std::default_random_engine engine(seed);
+    std::shuffle(perm.begin(), perm.end(), engine);
+    perm.insert(perm.end(), perm.begin(), perm.end());
+  }
+  static float fade(float t) { return t * t * t * (t * (t * 6 - 15) + 10); }
+  static float mix(float t, float a, float b) { return a + t * (b - a); }
+  static float gradient(int hash, float x, float y, float z)
+  {
+    const int h = hash & 15;
+    const float u = h < 8 ? x : y;
+    const float v = h < 4 ? y : ((h == 12 || h == 14) ? x : z);
+    return ((h & 1) == 0 ? u : -u) + ((h & 2) == 0 ? v : -v);
+  }
+  float value(float x, float y, float z) const
+  {
+    const int X = (int)floor(x) & 255, Y = (int)floor(y) & 255, Z = (int)floor(z) & 255;
+    x -= floor(x);
+    y -= floor(y);
+    z -= floor(z);
+    const float u = fade(x), v = fade(y), w = fade(z);
+    const int A = perm[X] + Y, AA = perm[A] + Z, AB = perm[A + 1] + Z;
+    const int B = perm[X + 1] + Y, BA = perm[B] + Z, BB = perm[B + 1] + Z;
+    const float lo = mix(v, mix(u, gradient(perm[AA], x, y, z), gradient(perm[BA], x - 1, y, z)),
+        mix(u, gradient(perm[AB], x, y - 1, z), gradient(perm[BB], x - 1, y - 1, z)));
+    const float hi = mix(v, mix(u, gradient(perm[AA + 1], x, y, z - 1), gradient(perm[BA + 1], x - 1, y, z - 1)),
+        mix(u, gradient(perm[AB + 1], x, y - 1, z - 1), gradient(perm[BB + 1], x - 1, y - 1, z - 1)));
+    return (mix(w, lo, hi) + 1.0f) / 2.0f;
+  }
+};
+} // namespace
+
+struct rtp_target
+{
+  NoiseChannel theta { 1 }, beta { 29 }, radial { 246 };
+  float walker[3] = { 0.0f, 0.0f, 0.0f };
+  float pos[3] = { 0.0f, 0.0f, 0.0f };
+  float maxRadius = 0.0f;
+};
+
+extern "C" rtp_target* rtp_target_create(uint32_t box_size)
+{
+  rtp_target* t = new rtp_target();
+  t->maxRadius = 0.48f * box_size;
+  return t;
+}
+extern "C" void rtp_target_destroy(rtp_target* t) { delete t; }
+extern "C" int rtp_target_update(rtp_target* t, int dim, float particles_velocity, float out_pos[3])
+{
+  if (!t || !out_pos)
+    return RTP_ERR_INVALID;
+  const float PI_T = 3.14f; // Target.cpp:25
+  t->walker[0] += 0.001f;
+  t->walker[1] += 0.002f;
+  t->walker[2] += 0.01f;
+  const float nTheta = t->theta.value(t->walker[0], t->walker[1], t->walker[2]);
+  const float nBeta = t->beta.value(t->walker[0], t->walker[1], t->walker[2]);
+  const float nR = t->radial.value(t->walker[0], t->walker[1], t->walker[2]);
+  const float velRatio = particles_velocity / 9.5f;
+  const float radius = t->maxRadius * cos(12 * velRatio * PI_T * nR);
+  t->pos[0] = dim == 3 ? (radius * cos(5 * velRatio * PI_T * nBeta)) : 0.0f;
+  t->pos[1] = radius * sin(5 * velRatio * PI_T * nBeta) * cos(4 * velRatio * PI_T * nTheta);
+  t->pos[2] = radius * sin(5 * velRatio * PI_T * nBeta) * sin(4 * velRatio * PI_T * nTheta);
+  memcpy(out_pos, t->pos, sizeof t->pos);
+  return RTP_OK;
 }

@@ -320,8 +320,8 @@ def _fluid_inputs_from_json(fluidsJson, dim, k):
 
 
 class Boids(Model):
-    """Physics::CL::Boids, physics/ocl/Boids.{hpp,cpp}. The Perlin-noise target trajectory (physics/utils/Target.cpp)
-    stays on the host: feed its position with setTargetPos()."""
+    """Physics::CL::Boids, physics/ocl/Boids.{hpp,cpp}. The Perlin-noise target trajectory (physics/utils/Target.cpp) is
+    evaluated on the host once per update(), like the reference (Boids.cpp:351-358): rtp_target_update()."""
 
     _TYPE = ModelType.BOIDS
     _MAX_PARTS_IN_CELL = 3000  # Boids.cpp:78
@@ -333,8 +333,17 @@ class Boids(Model):
         self.m_targetActive = False
         self.m_targetVisible = False
         self.m_targetPos = (0.0, 0.0, 0.0)
+        self.m_target = _abi.Target(int(params.boxSize[0]))
         self.m_init = True
         self.reset()
+
+    def update(self):  # Boids.cpp:323-384
+        if not self.m_init:
+            return
+        if not self.m_pause and self.m_targetActive:
+            self.m_targetPos = self.m_target.update(3 if self.m_dimension == Dimension.dim3D else 2, self.m_rules.velocityScale)
+            self.transferKernelInputsToGPU()
+        super().update()
 
     def transferJsonInputsToModel(self, inputJson):  # Boids.cpp:177-210
         if not self.m_init:
@@ -348,7 +357,7 @@ class Boids(Model):
             self.m_targetActive = bool(b["Target"]["Enable##Target"])
             self.m_targetVisible = bool(b["Target"]["Show"])
             self.m_targetInputs.targetRadiusEffect = float(b["Target"]["Radius"][0])
-            self.m_targetInputs.targetSignEffect = 1 if b["Target"]["Attract"] else -1
+            self.m_targetInputs.targetSignEffect = int(bool(b["Target"]["Attract"]))  # (int)bool, Boids.cpp:201: "repel" is 0
         except (KeyError, TypeError, IndexError):
             raise RuntimeError("Wrong Json parsing")
 

@@ -94,3 +94,7 @@ if __name__ == "__main__":
         print(name, {k: v.shape for k, v in out.items()})
     np.savez_compressed(os.path.join(OUT, "generators.npz"), **{k: ref() for k, (_, ref) in generator_cases().items()})
     print("generators", list(generator_cases()))
+    # boids target trajectory of the reference (Physics::Target): 3D at the default velocity scale, 2D at a faster one
+    np.savez_compressed(os.path.join(OUT, "target_trajectory.npz"), dim3_v05=R.target_trajectory(10, 3, 0.5, 400),
+                        dim2_v20=R.target_trajectory(10, 2, 2.0, 400))
+    print("target_trajectory")

@@ -201,6 +201,49 @@ def test_stragglers_occur_and_stay_exact(monkeypatch):
     assert q.h.list_stats()["particles"] == 0  # lists disabled: nothing to report
 
 
+def test_list_allocation_failure_falls_back_to_plain_traversal(monkeypatch):
+    # the lists cost 1.66 kB per particle of max_particles; when they cannot be allocated rtp_create must not fail: the
+    # sweeps take the plain 27-cell traversal (bit-identical)
+    monkeypatch.setenv("RTP_TEST_FAIL_LIST_ALLOC", "1")
+    p = make_fluids(M=16384, res=(32, 32, 16), jacobi=3)
+    monkeypatch.delenv("RTP_TEST_FAIL_LIST_ALLOC")
+    q = make_fluids(M=16384, res=(32, 32, 16), jacobi=3)
+    for _ in range(5):
+        p.step(O.STEP_PHYSICS, oracle=False)
+        q.step(O.STEP_PHYSICS, oracle=False)
+    assert p.h.list_stats()["particles"] == 0 and q.h.list_stats()["particles"] == 16384
+    for f in ("p_pos", "p_vel", "p_density"):
+        assert np.array_equal(p.h.download(f), q.h.download(f)), f
+
+
+def test_fluid_params_are_validated():
+    # artPressureExp outside [1, 6] or a radius factor outside (0, 1) would silently change the arithmetic (the exponent
+    # is an unrolled product; radius >= 1 divides by poly6 = 0): rejected like the reference's UI ranges (Fluids.cpp:52-74)
+    h = _abi.Handle(_abi.FLUIDS, 1024, 0)
+    for exp, radius in ((0, 0.006), (7, 0.006), (4, 1.0), (4, 0.0)):
+        with pytest.raises(_abi.RtpError):
+            h.set_fluid_params(_abi.FluidParams(450.0, 600.0, 0.010, 3, 1, radius, 0.001, exp, 1, 0.0004, 0.0001), 3)
+    h.set_fluid_params(_abi.FluidParams(450.0, 600.0, 0.010, 3, 0, 1.0, 0.001, 9, 1, 0.0004, 0.0001), 3)  # disabled: not looked at
+    h.set_fluid_params(_abi.FluidParams(450.0, 600.0, 0.010, 3, 1, 0.015, 0.001, 6, 1, 0.0004, 0.0001), 3)
+
+
+@pytest.mark.parametrize("case", ["FLUIDS_BOMB", "FLUIDS_DROP"])
+def test_fluid_presets_bomb_and_drop_vs_oracle(case):
+    # the remaining fluids presets (Fluids.cpp:339-380): 65k sphere "bomb"; 4k drop over a 65k floor layer
+    from realtimeparticles_b200 import models
+    M = 131072
+    py = models.CreateModel(1, models.ModelParams(currNbParticles=M, maxNbParticles=M, boxSize=(10, 10, 10), gridRes=(30, 30, 30),
+                                                  pCase=getattr(models.PhysicsCase, case), dimension=models.Dimension.dim3D))
+    N = py.nbParticles()
+    assert N == (65536 if case == "FLUIDS_BOMB" else 4096 + 65536)
+    verts = py.download("p_pos")[:N]
+    p = make_fluids(M=M, N=N, verts=verts, jacobi=2)
+    for _ in range(3):
+        p.step(O.STEP_PHYSICS)
+    assert_ids_exact(p)
+    assert_close(p, ("POS", "VEL", "PRED_POS", "DENSITY", "VORT"), N=N)
+
+
 def test_step_n_graph_replay_equals_single_steps():
     a = make_fluids(M=16384, res=(32, 32, 16), jacobi=3)
     b = make_fluids(M=16384, res=(32, 32, 16), jacobi=3)
@@ -361,16 +404,28 @@ def _cpp_models():
     return L, C
 
 
-@pytest.mark.parametrize("kind", ["fluids", "boids", "clouds", "fluids2d", "boids2d"])
+@pytest.mark.parametrize("kind", ["fluids", "boids", "clouds", "fluids2d", "boids2d", "fluids_bomb", "fluids_drop",
+                                  "clouds_homogeneous", "boids_target", "boids_target2d"])
 def test_cpp_model_equals_python_model(kind):
-    """Physics::CUDA::X driven through the reference's own Model interface == the Python mirror, bit for bit"""
+    """Physics::CUDA::X driven through the reference's own Model interface == the Python mirror, bit for bit.
+    Covers every preset (Fluids.cpp:339-380 Dam / Bomb / Drop, Clouds.cpp:449-471 Cumulus / Homogeneous, Boids.cpp:235-257)
+    and the boids target rule with its Perlin-noise trajectory (Boids.cpp:351-358: the C++ host runs the reference's own
+    Physics::Target, the Python host rtp_target_update)."""
     from realtimeparticles_b200 import models
     L, C = _cpp_models()
+    variant = kind
     dim3 = not kind.endswith("2d")  # 2D: the presets live in the YZ plane (Generate2DGrid), same kernels
     kind = kind[:-2] if not dim3 else kind
-    t, case, box, grid = {"fluids": (1, models.PhysicsCase.FLUIDS_DAM, (10, 10, 10), (30, 30, 30)),
-                          "boids": (0, models.PhysicsCase.BOIDS_LARGE, (10, 10, 10), (30, 30, 30)),
-                          "clouds": (2, models.PhysicsCase.CLOUDS_CUMULUS, (10, 20, 10), (30, 60, 30))}[kind]
+    target = kind == "boids_target"
+    PC = models.PhysicsCase
+    t, case, box, grid = {"fluids": (1, PC.FLUIDS_DAM, (10, 10, 10), (30, 30, 30)),
+                          "fluids_bomb": (1, PC.FLUIDS_BOMB, (10, 10, 10), (30, 30, 30)),
+                          "fluids_drop": (1, PC.FLUIDS_DROP, (10, 10, 10), (30, 30, 30)),
+                          "boids": (0, PC.BOIDS_LARGE, (10, 10, 10), (30, 30, 30)),
+                          "boids_target": (0, PC.BOIDS_MEDIUM, (10, 10, 10), (30, 30, 30)),
+                          "clouds": (2, PC.CLOUDS_CUMULUS, (10, 20, 10), (30, 60, 30)),
+                          "clouds_homogeneous": (2, PC.CLOUDS_HOMOGENEOUS, (10, 20, 10), (30, 60, 30))}[kind]
+    kind = kind.split("_")[0]
     M = 131072
     m = L.rtpm_create(t, M, int(case), 1 if dim3 else 0, (C.c_uint32 * 3)(*box), (C.c_uint32 * 3)(*grid))
     assert m and L.rtpm_is_init(m)
@@ -384,7 +439,8 @@ def test_cpp_model_equals_python_model(kind):
         assert py.nbParticles() == 4096 and np.all(py.download("p_pos")[:4096, 0] == 0.0)
     if kind == "clouds":
         # the reference seeds nothing: both sides draw from glibc rand(); make the two draws identical
-        verts = _abi.gen_random_box(65536, (-5.0, -10.0, -5.0), (5.0, -5.0, 5.0), 1)
+        region = ((-5.0, -10.0, -5.0), (5.0, -5.0, 5.0)) if case == PC.CLOUDS_CUMULUS else ((-5.0, -10.0, -5.0), (5.0, 10.0, 5.0))
+        verts = _abi.gen_random_box(65536, region[0], region[1], 1)
         py.loadCloudsState(verts)
         h = _abi.Handle.__new__(_abi.Handle)  # borrowed view of the C++ model's handle: never let it destroy it
         h.L, h.h, h.model, h.M, h.N = _abi.lib(), C.c_void_p(L.rtpm_handle(m, t)), t, M, 65536
@@ -398,10 +454,22 @@ def test_cpp_model_equals_python_model(kind):
         js = py.getInputJson()
         js["Fluids"]["Nb Jacobi Iterations"][0] = 3
         py.updateInputJson(js)
+    if target:
+        tj = b'{"Boids": {"Target": {"Enable##Target": true, "Radius": [3.0, 1.0, 20.0], "Attract": false}}}'
+        assert L.rtpm_update_input_json(m, tj) == 0
+        js = py.getInputJson()
+        js["Boids"]["Target"].update({"Enable##Target": True, "Radius": [3.0, 1.0, 20.0], "Attract": False})
+        py.updateInputJson(js)
+        assert py.isTargetActivated()
     assert L.rtpm_nb_particles(m) == py.nbParticles()
-    for _ in range(3):
+    expect = {"fluids_bomb": 65536, "fluids_drop": 4096 + 65536, "clouds_homogeneous": 65536, "boids_target": 16384}
+    if variant in expect:
+        assert py.nbParticles() == expect[variant], py.nbParticles()
+    for _ in range(12 if target else 3):
         L.rtpm_update(m)
         py.update()
+    if target:
+        assert np.abs(np.array(py.targetPos())).max() > 0.1  # the target has left the origin
     h = _abi.Handle.__new__(_abi.Handle)
     h.L, h.h, h.model, h.M, h.N = _abi.lib(), C.c_void_p(L.rtpm_handle(m, t)), t, M, py.nbParticles()
     h.sync()

@@ -190,3 +190,17 @@ def test_oracle_fast_normalize_zero_vector():
     w.reset_ids()
     w.step(O.STEP_PHYSICS)
     assert np.isfinite(w.download("ACC")[:3]).all() and np.isfinite(w.download("VEL")[:3]).all()
+
+
+def test_target_trajectory_matches_reference():
+    # rtp_target_* (host code of the library) against Physics::Target of the reference itself: golden positions generated
+    # through oracle/_ref (tests/golden/make_golden.py), and live when oracle/_ref is built
+    gold = np.load(os.path.join(ROOT, "tests", "golden", "target_trajectory.npz"))
+    for key, dim, vel in (("dim3_v05", 3, 0.5), ("dim2_v20", 2, 2.0)):
+        t = _abi.Target(10)
+        got = np.array([t.update(dim, vel) for _ in range(400)], np.float32)
+        assert np.array_equal(got, gold[key]), key
+        assert np.abs(got).max() <= 4.8 + 1e-5 and (dim == 3 or np.all(got[:, 0] == 0.0))
+    from oracle import ref_py as R
+    if R.available():
+        assert np.array_equal(R.target_trajectory(10, 3, 0.5, 50), gold["dim3_v05"][:50])
