@@ -264,7 +264,9 @@ def run_slab_16m(args, torch, abi, rank, local_rank, world, steps=10, warmup=8):
     decomposed over `world` GPUs with halo exchange + migration (realtimeparticles_b200/sharded.py). Strong scaling:
     the total problem is fixed; value = 2^24 * steps / max-over-ranks device time. 8 warm-up steps: the first step in
     which particles migrate (step 7 of this initial state) pays a one-off ~90 ms set-up; the same step window
-    (steps 10-19) is timed for every N."""
+    (steps 10-19) is timed for every N, N = 1 included (same code path with no neighbour), so the driver can form
+    strong-scaling efficiencies from like-for-like numbers; `invariants` lets it check that every N computed the same
+    physics."""
     import numpy as np
     import torch.distributed as dist
     from realtimeparticles_b200 import sharded
@@ -273,11 +275,13 @@ def run_slab_16m(args, torch, abi, rank, local_rank, world, steps=10, warmup=8):
     x0 = -40.0 + rank * (80.0 / world)
     pos = abi.gen_box_grid((nx, 256, 128), (x0, -20.0, -20.0), (x0 + 80.0 / world, 0.0, 0.0))
     n_own = len(pos)
-    ghost_cap = 2 * sharded.GHOST_LAYERS * 120 * 120 * 40 if world > 1 else 0
-    capacity = int(n_own * 1.15) + ghost_cap
+    # fixed capacities per slab face: a ghost region of 2 x-layers (120 x 120 cells each, 4.9 particles per cell in the
+    # initial lattice; room for 16) and a migration message
+    ghost_cap = sharded.GHOST_LAYERS * 120 * 120 * 16 if world > 1 else 0
+    capacity = int(n_own * 1.15) + 2 * ghost_cap
     dev = torch.device("cuda", local_rank)
     eng = sharded.CudaSlabEngine(capacity, box, grid, local_rank, jacobi=JACOBI)
-    sd = sharded.SlabDecomposition(eng, grid, rank, world)
+    sd = sharded.SlabDecomposition(eng, grid, rank, world, ghost_cap=ghost_cap, migrate_cap=1 << 16)
     sd.load_owned(torch.from_numpy(pos).to(dev), torch.zeros((n_own, 4), device=dev))
     sd.warm_up_code_paths()
     for _ in range(warmup):
@@ -317,12 +321,25 @@ def run_slab_16m(args, torch, abi, rank, local_rank, world, steps=10, warmup=8):
         dist.all_reduce(owned, op=dist.ReduceOp.SUM)
     ms = float(t[0].item())
     per_step = [a.elapsed_time(b) for a, b in zip([e0] + marks[:-1], marks)]
+    # aggregate invariants of the state after the timed window (north_star: mean PBF density error and kinetic energy must
+    # agree between decompositions within 1 %): sums over the OWNED particles of every rank
+    with eng.stream_context():
+        n_loc = sd.n_owned + sd.ghost_rows
+        own = eng.field("RadixSortIndices", u32=True)[:n_loc] < sd.n_owned  # rows of the last sort that are not ghosts
+        dens = eng.field("p_density")[:n_loc][own].double()
+        v = eng.vel()[:sd.n_owned, :3].double()
+        inv = torch.stack([(dens / 450.0 - 1.0).abs().sum(), 0.5 * (v * v).sum(), torch.tensor(float(sd.n_owned), dtype=torch.float64, device=dev)])
+    eng.sync()
+    if world > 1:
+        dist.all_reduce(inv, op=dist.ReduceOp.SUM)
+    invariants = {"mean_abs_density_error": float(inv[0] / inv[2]), "kinetic_energy": float(inv[1]), "after_step": warmup + 1 + steps}
     bpp = WORKLOADS["pbf_dam_16m_I3_vorticity_xsph"][1]
     peak, _ = measured_peak()
     out = {"workload": "pbf_dam_16m_I3_vorticity_xsph, x-slab decomposition (2 ghost layers, 2I+3 halo refreshes + migration per step)",
            "particles": total, "particles_owned_sum": int(owned.item()), "n_gpus": world, "steps": steps, "warmup": warmup,
            "scaling": "strong", "ms_per_step": ms / steps, "steps_per_s": steps / (ms * 1e-3),
            "value": total * steps / (ms * 1e-3), "unit": "particle-updates/s", "wall_ms_per_step": float(t[1].item()) / steps,
+           "invariants": invariants, "ghost_capacity_rows_per_face": ghost_cap,
            "per_step_ms_rank0": [round(x, 2) for x in per_step], "per_rank": {k: v for k, v in sd.stats.items() if k != "phases"}, "phases_ms_per_rank": phases, "algorithmic_bytes_per_particle": bpp,
            "whole_step_frac_of_hbm_per_gpu": round(total * steps / (ms * 1e-3) * bpp / 1e9 / peak / world, 4)}
     eng.h.close()

@@ -280,13 +280,26 @@ typedef enum rtp_shard_buffer_id
   RTP_SHARD_BUF_VORT_NORM = 5, /* f[M] */
   RTP_SHARD_BUF_VEL_CONFINED = 6, /* f4[M] velocity after vorticity confinement (input of the XSPH sweep) */
   RTP_SHARD_BUF_LIST_BUILD_POS = 7, /* f4[M] positions the neighbour lists were built from */
-  RTP_SHARD_BUF_LIST_INVALID = 8 /* u32[16] per-epoch "lists invalid" flags */
+  RTP_SHARD_BUF_LIST_INVALID = 8, /* u32[16] per-epoch "lists invalid" flags */
+  RTP_SHARD_BUF_POS = 9, /* f4[M] p_pos (unsorted between steps: migration) */
+  RTP_SHARD_BUF_VEL = 10 /* f4[M] p_vel */
 } rtp_shard_buffer_id;
 
 /* number of leading (unsorted) particles this rank owns; the rest of nb_particles are ghosts */
 RTP_API int rtp_shard_set_owned(rtp_handle* h, uint64_t n_owned);
 RTP_API int rtp_shard_stage(rtp_handle* h, int stage, int iter, int last);
 RTP_API int rtp_shard_buffer(rtp_handle* h, int which, void** dptr, size_t* bytes);
+/* The exchange kernels of the slab data plane (the transport between ranks -- NCCL / gloo send-recv -- stays with the
+ * caller). All pointers are DEVICE pointers, everything is enqueued on the handle's stream, nothing synchronises.
+ *  pack:   d_out[k] = buffer[d_idx[k]], k < n; an index 0xFFFFFFFF ("no particle": fixed-capacity exchanges are padded)
+ *          packs a +inf position (f4 rows) or 0 (scalar rows);  unpack: buffer[d_idx[k]] = d_in[k], padding skipped.
+ *  inverse_perm: d_inv[perm[i]] = i for the nb_particles cell-sorted rows (where did unsorted row j go).
+ *  check_ghosts: raise the "lists invalid" flag of next_epoch when a ghost row (sorted indices d_sorted_idx) has been moved
+ *          further than the list validity bound from its position at the list build (its owner moves it, not this rank). */
+RTP_API int rtp_shard_pack(rtp_handle* h, int buffer, const uint32_t* d_idx, uint64_t n, void* d_out);
+RTP_API int rtp_shard_unpack(rtp_handle* h, int buffer, const uint32_t* d_idx, uint64_t n, const void* d_in);
+RTP_API int rtp_shard_inverse_perm(rtp_handle* h, uint32_t* d_inv);
+RTP_API int rtp_shard_check_ghosts(rtp_handle* h, const uint32_t* d_sorted_idx, uint64_t n, int next_epoch);
 /* neighbour-list validity: radius^2 a particle may move from its list-build position (see sweep.cuh) */
 RTP_API float rtp_shard_list_dmax_sq(const rtp_handle* h);
 

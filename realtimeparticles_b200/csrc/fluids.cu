@@ -284,6 +284,7 @@ __global__ void __launch_bounds__(NB_THREADS, NB_MIN_BLOCKS) densityLambdaKernel
     const float4* __restrict__ pred, int nbrMode, int epoch)
 {
   RTP_PDL_PROLOGUE();
+  recordGhostBuildPos(s, pred, nbrMode, epoch);
   producerLoop(s, nbrMode, epoch,
       [&](const u32 i, const bool strag) -> int
       {
@@ -324,7 +325,8 @@ __global__ void __launch_bounds__(NB_THREADS, NB_MIN_BLOCKS) densityLambdaBuildK
   RTP_PDL_PROLOGUE();
   __shared__ TileSmem sm;
   const u32 i = blockIdx.x * NB_THREADS + threadIdx.x;
-  const bool active = i < s.N;
+  recordGhostBuildPos(s, pred, NBR_BUILD, epoch);
+  const bool active = i < s.N && !isGhostRow(s, i);
   const float4 pi = active ? pred[i] : make_float4(0.f, 0.f, 0.f, 0.f);
   float density = 0.f, gx = 0.f, gy = 0.f, gz = 0.f, sumG2 = 0.f;
   const bool done = sweepProducerBuildTiled<TRAV>(sm, g, c, s, pred, pi, i, active, epoch,
@@ -358,7 +360,7 @@ __global__ void __launch_bounds__(NB_THREADS, NB_MIN_BLOCKS) correctionKernel(De
 {
   RTP_PDL_PROLOGUE();
   const u32 i = blockIdx.x * NB_THREADS + threadIdx.x;
-  if (i >= s.N)
+  if (i >= s.N || isGhostRow(s, i))
     return;
   const float4 pi = pred[i];
   const float* __restrict__ lambda = s.lambda;
@@ -449,6 +451,7 @@ __global__ void __launch_bounds__(NB_THREADS, NB_MIN_BLOCKS) vorticityKernel(Dev
 {
   RTP_PDL_PROLOGUE();
   const float4* __restrict__ V = s.velB;
+  recordGhostBuildPos(s, pred, nbrMode, epoch);
   producerLoop(s, nbrMode, epoch,
       [&](const u32 i, const bool strag) -> int
       {
@@ -484,7 +487,7 @@ __global__ void __launch_bounds__(NB_THREADS, NB_MIN_BLOCKS) confinementKernel(D
 {
   RTP_PDL_PROLOGUE();
   const u32 i = blockIdx.x * NB_THREADS + threadIdx.x;
-  if (i >= s.N)
+  if (i >= s.N || isGhostRow(s, i))
     return;
   const float4 pi = pred[i];
   const float* __restrict__ wn = s.vortNorm;
@@ -519,7 +522,7 @@ __global__ void __launch_bounds__(NB_THREADS, NB_MIN_BLOCKS) xsphKernel(DeviceSt
 {
   RTP_PDL_PROLOGUE();
   const u32 i = blockIdx.x * NB_THREADS + threadIdx.x;
-  if (i >= s.N)
+  if (i >= s.N || isGhostRow(s, i))
     return;
   const float4 pi = pred[i];
   const float4* __restrict__ V = s.velC;

@@ -1,4 +1,6 @@
 // grid.cu -- reset / cell-table / camera / render-side kernels shared by the three models.
+#include <math.h>
+
 #include "kernels.cuh"
 #include "sweep.cuh"
 
@@ -196,6 +198,81 @@ void launchCompactGather(const DeviceState& s, const u32* order, u32 n, cudaStre
 {
   if (n)
     launchKernel(compactGatherKernel, ewBlocks(n), EW_THREADS, st, s, order, n);
+}
+
+// ---- slab decomposition: exchange buffers. out[k] = buf[idx[k]] (idx 0xFFFFFFFF = no particle: `fill`), and back.
+template <typename T>
+__global__ void __launch_bounds__(EW_THREADS) packRowsKernel(const T* __restrict__ buf, const u32* __restrict__ idx, u32 n, T* __restrict__ out, T fill)
+{
+  RTP_PDL_PROLOGUE();
+  const u32 k = blockIdx.x * EW_THREADS + threadIdx.x;
+  if (k >= n)
+    return;
+  const u32 j = idx[k];
+  out[k] = j == 0xFFFFFFFFu ? fill : buf[j];
+}
+template <typename T>
+__global__ void __launch_bounds__(EW_THREADS) unpackRowsKernel(T* __restrict__ buf, const u32* __restrict__ idx, u32 n, const T* __restrict__ in)
+{
+  RTP_PDL_PROLOGUE();
+  const u32 k = blockIdx.x * EW_THREADS + threadIdx.x;
+  if (k >= n)
+    return;
+  const u32 j = idx[k];
+  if (j != 0xFFFFFFFFu)
+    buf[j] = in[k];
+}
+__global__ void __launch_bounds__(EW_THREADS) inversePermKernel(const u32* __restrict__ perm, u32 n, u32* __restrict__ inv)
+{
+  RTP_PDL_PROLOGUE();
+  const u32 i = blockIdx.x * EW_THREADS + threadIdx.x;
+  if (i < n)
+    inv[perm[i]] = i;
+}
+// list validity across slabs: a ghost moved by its owner further than the bound invalidates the lists of the next epoch
+__global__ void __launch_bounds__(EW_THREADS) ghostDisplacementKernel(const float4* __restrict__ pred, const float4* __restrict__ buildPos,
+    const u32* __restrict__ idx, u32 n, float dmaxSq, u32* __restrict__ invalid)
+{
+  RTP_PDL_PROLOGUE();
+  const u32 k = blockIdx.x * EW_THREADS + threadIdx.x;
+  if (k >= n)
+    return;
+  const u32 i = idx[k];
+  if (i == 0xFFFFFFFFu)
+    return;
+  const float4 p = pred[i], b = buildPos[i];
+  const float dx = p.x - b.x, dy = p.y - b.y, dz = p.z - b.z;
+  if (!(dx * dx + dy * dy + dz * dz <= dmaxSq) && isfinite(p.x))
+    *invalid = 1u;
+}
+void launchPackRows(const void* buf, int rowBytes, const u32* idx, u32 n, void* out, cudaStream_t st)
+{
+  if (!n)
+    return;
+  const float inf = INFINITY;
+  if (rowBytes == 16)
+    launchKernel(packRowsKernel<float4>, ewBlocks(n), EW_THREADS, st, (const float4*)buf, idx, n, (float4*)out, make_float4(inf, inf, inf, 0.0f));
+  else
+    launchKernel(packRowsKernel<float>, ewBlocks(n), EW_THREADS, st, (const float*)buf, idx, n, (float*)out, 0.0f);
+}
+void launchUnpackRows(void* buf, int rowBytes, const u32* idx, u32 n, const void* in, cudaStream_t st)
+{
+  if (!n)
+    return;
+  if (rowBytes == 16)
+    launchKernel(unpackRowsKernel<float4>, ewBlocks(n), EW_THREADS, st, (float4*)buf, idx, n, (const float4*)in);
+  else
+    launchKernel(unpackRowsKernel<float>, ewBlocks(n), EW_THREADS, st, (float*)buf, idx, n, (const float*)in);
+}
+void launchInversePerm(const DeviceState& s, u32* inv, cudaStream_t st)
+{
+  if (s.N)
+    launchKernel(inversePermKernel, ewBlocks(s.N), EW_THREADS, st, s.perm, s.N, inv);
+}
+void launchGhostDisplacement(const DeviceState& s, const float4* pred, const u32* idx, u32 n, float dmaxSq, u32* invalid, cudaStream_t st)
+{
+  if (n)
+    launchKernel(ghostDisplacementKernel, ewBlocks(n), EW_THREADS, st, pred, (const float4*)s.nbrBuildPos, idx, n, dmaxSq, invalid);
 }
 
 void launchResetIds(const DeviceState& s, u32 numCells, cudaStream_t st)

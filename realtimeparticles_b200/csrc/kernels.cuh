@@ -72,6 +72,10 @@ struct FluidStepParams
 
 // ---- grid.cu
 void launchSelftestMath(u32 lo, u32 hi, unsigned long long* bad, cudaStream_t st);
+void launchPackRows(const void* buf, int rowBytes, const u32* idx, u32 n, void* out, cudaStream_t st);
+void launchUnpackRows(void* buf, int rowBytes, const u32* idx, u32 n, const void* in, cudaStream_t st);
+void launchInversePerm(const DeviceState& s, u32* inv, cudaStream_t st);
+void launchGhostDisplacement(const DeviceState& s, const float4* pred, const u32* idx, u32 n, float dmaxSq, u32* invalid, cudaStream_t st);
 void launchGhostFlags(const DeviceState& s, u32* keysOut, cudaStream_t st);
 void launchCompactGather(const DeviceState& s, const u32* order, u32 n, cudaStream_t st);
 void launchResetIds(const DeviceState& s, u32 numCells, cudaStream_t st);

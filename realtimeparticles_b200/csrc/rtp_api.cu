@@ -1018,6 +1018,8 @@ extern "C" int rtp_shard_buffer(rtp_handle* h, int which, void** dptr, size_t* b
   case RTP_SHARD_BUF_VEL_SORTED: p = s.velB; b = 16 * M; break;
   case RTP_SHARD_BUF_VORT_NORM: p = s.vortNorm; b = 4 * M; break;
   case RTP_SHARD_BUF_VEL_CONFINED: p = s.velC; b = 16 * M; break;
+  case RTP_SHARD_BUF_POS: p = s.posA; b = 16 * M; break;
+  case RTP_SHARD_BUF_VEL: p = s.velA; b = 16 * M; break;
   case RTP_SHARD_BUF_LIST_BUILD_POS: p = s.nbrBuildPos; b = 16 * M; break;
   case RTP_SHARD_BUF_LIST_INVALID: p = s.nbrInvalid; b = 4 * (size_t)NBR_EPOCHS; break;
   default: return fail(h, RTP_ERR_INVALID, "unknown shard buffer");
@@ -1027,6 +1029,68 @@ extern "C" int rtp_shard_buffer(rtp_handle* h, int which, void** dptr, size_t* b
   *dptr = p;
   if (bytes)
     *bytes = b;
+  return RTP_OK;
+}
+
+static int shardRows(rtp_handle* h, int buffer, void** p, int* rowBytes)
+{
+  size_t bytes = 0;
+  const int rc = rtp_shard_buffer(h, buffer, p, &bytes);
+  if (rc != RTP_OK)
+    return rc;
+  *rowBytes = (buffer == RTP_SHARD_BUF_LAMBDA || buffer == RTP_SHARD_BUF_VORT_NORM || buffer == RTP_SHARD_BUF_KEYS_IN) ? 4 : 16;
+  return RTP_OK;
+}
+
+extern "C" int rtp_shard_pack(rtp_handle* h, int buffer, const uint32_t* d_idx, uint64_t n, void* d_out)
+{
+  if (!h || (n && (!d_idx || !d_out)) || n > h->s.M)
+    return RTP_ERR_INVALID;
+  void* p;
+  int rb;
+  const int rc = shardRows(h, buffer, &p, &rb);
+  if (rc != RTP_OK)
+    return rc;
+  CUDA_TRY(h, cudaSetDevice(h->cfg.device));
+  launchPackRows(p, rb, d_idx, (u32)n, d_out, h->stream);
+  CUDA_TRY(h, cudaGetLastError());
+  return RTP_OK;
+}
+
+extern "C" int rtp_shard_unpack(rtp_handle* h, int buffer, const uint32_t* d_idx, uint64_t n, const void* d_in)
+{
+  if (!h || (n && (!d_idx || !d_in)) || n > h->s.M)
+    return RTP_ERR_INVALID;
+  void* p;
+  int rb;
+  const int rc = shardRows(h, buffer, &p, &rb);
+  if (rc != RTP_OK)
+    return rc;
+  CUDA_TRY(h, cudaSetDevice(h->cfg.device));
+  launchUnpackRows(p, rb, d_idx, (u32)n, d_in, h->stream);
+  CUDA_TRY(h, cudaGetLastError());
+  return RTP_OK;
+}
+
+extern "C" int rtp_shard_inverse_perm(rtp_handle* h, uint32_t* d_inv)
+{
+  if (!h || !d_inv)
+    return RTP_ERR_INVALID;
+  CUDA_TRY(h, cudaSetDevice(h->cfg.device));
+  launchInversePerm(h->s, d_inv, h->stream);
+  CUDA_TRY(h, cudaGetLastError());
+  return RTP_OK;
+}
+
+extern "C" int rtp_shard_check_ghosts(rtp_handle* h, const uint32_t* d_sorted_idx, uint64_t n, int next_epoch)
+{
+  if (!h || (n && !d_sorted_idx) || next_epoch < 0 || next_epoch >= NBR_EPOCHS)
+    return RTP_ERR_INVALID;
+  if (!h->s.nbrBuildPos || !n)
+    return RTP_OK; // lists off: nothing to invalidate
+  CUDA_TRY(h, cudaSetDevice(h->cfg.device));
+  launchGhostDisplacement(h->s, h->shardCur ? h->shardCur : h->s.pred1, d_sorted_idx, (u32)n, h->c.nbrDmaxSq, h->s.nbrInvalid + next_epoch, h->stream);
+  CUDA_TRY(h, cudaGetLastError());
   return RTP_OK;
 }
 

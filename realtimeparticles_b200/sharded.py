@@ -15,13 +15,22 @@ Per step (one process per GPU, neighbour-only point-to-point exchanges, no colle
      lambda after density+lambda, predPos (and vel on the last iteration) after correction, |vorticity| after the
      vorticity sweep, the confined velocity before XSPH: 2 I + 3 exchanges per step;
   4. ghosts are dropped, the owned particles stay in cell-sorted order for the next step.
-Ghost values computed locally (their neighbourhoods are incomplete) are never read before the refresh overwrites them.
-Results equal the single-GPU run up to the order of particles inside a cell (migrated particles are appended), i.e. up
-to fp32 summation order; cell ids and the cell table are identical.
+Ghost rows are never computed locally: the sweeps skip them (csrc/sweep.cuh isGhostRow) and the refreshes bring the
+owner's values before anybody reads them. Results equal the single-GPU run up to the order of particles inside a cell
+(migrated particles are appended), i.e. up to fp32 summation order; cell ids and the cell table are identical.
 
-The orchestration below is plumbing (index bookkeeping + torch.distributed send/recv on tensors that alias the
-library's device buffers); all per-particle work is done by the CUDA kernels through the stage API of
-include/rtp_cuda.h (rtp_shard_*). The engine is duck-typed so that the CPU tests can drive the same code over gloo.
+What keeps the host out of the step:
+  * ghost regions and exchange buffers have a FIXED capacity: a halo / refresh message is always `ghost_cap` rows, padded
+    with "no particle" rows (+inf positions: their cell key is beyond the grid, so they sort behind every real particle,
+    appear in no cell range and are skipped by the sweeps like any ghost). No count has to reach the host before the next
+    launch; the counts of a step are checked against the capacity one step later, together with the one read-back below;
+  * the only host synchronisation per step is the read-back of the migration counts (the number of owned particles sizes
+    the launches);
+  * gather / scatter of exchange rows, the inverse permutation and the ghost displacement check are kernels of the
+    library behind the C ABI (rtp_shard_pack / unpack / inverse_perm / check_ghosts), on the handle's stream.
+The transport is pluggable: torch.distributed P2P batches (NCCL over NVLink on GPUs, gloo on CPU) when every rank is a
+process, or LocalSlabGroup, which runs several ranks in ONE process (tests: 2 and 4 slabs on one device; C-side hosts can
+do the same with the stage API). The engine is duck-typed so that the CPU tests drive the same code over the oracle.
 """
 import torch
 import torch.distributed as dist
@@ -44,7 +53,8 @@ class CudaSlabEngine:
 
     ST = dict(PREDICT=0, GHOST_KEYS=1, SORT=2, DENSITY_LAMBDA=3, CORRECTION=4, VORTICITY=5, CONFINEMENT=6, XSPH=7, DROP_GHOSTS=8)
     BUF = dict(KEYS_IN=0, PRED_IN=1, PRED_CUR=2, LAMBDA=3, VEL_SORTED=4, VORT_NORM=5, VEL_CONFINED=6, LIST_BUILD_POS=7,
-               LIST_INVALID=8)
+               LIST_INVALID=8, POS=9, VEL=10)
+    ROW = dict(PRED_IN=4, PRED_CUR=4, LAMBDA=1, VEL_SORTED=4, VORT_NORM=1, VEL_CONFINED=4, POS=4, VEL=4)
 
     def __init__(self, capacity, box, grid, device, fluid_params=None, jacobi=3):
         self.device = torch.device("cuda", device)
@@ -55,7 +65,6 @@ class CudaSlabEngine:
         self.vorticity = bool(fp.isVorticityConfEnabled)
         self.h.set_fluid_params(fp, jacobi)
         self.stream = torch.cuda.ExternalStream(self.h.stream(), device=self.device)
-        self.dmax_sq = self.h.shard_list_dmax_sq()
 
     def stream_context(self):
         return torch.cuda.stream(self.stream)
@@ -69,8 +78,7 @@ class CudaSlabEngine:
 
     def buf(self, name):
         p, n = self.h.shard_buffer(self.BUF[name])
-        return self._view(p, n, f4=name in ("PRED_IN", "PRED_CUR", "VEL_SORTED", "VEL_CONFINED", "LIST_BUILD_POS"),
-                          u32=name in ("KEYS_IN", "LIST_INVALID"))
+        return self._view(p, n, f4=self.ROW.get(name) == 4, u32=name in ("KEYS_IN", "LIST_INVALID"))
 
     def field(self, name, f4=False, u32=False):
         p = self.h.device_ptr(name)
@@ -93,41 +101,55 @@ class CudaSlabEngine:
     def pred_in(self):
         return self.buf("PRED_IN")
 
-    def perm(self):
-        return self.field("RadixSortIndices", u32=True)
-
     def stage(self, name, it=0, last=False):
         self.h.shard_stage(self.ST[name], it, last)
 
-    def refresh_fields(self, name, last=False):
-        """tensors (cell-sorted index space) whose ghost rows must be refreshed after stage `name`"""
+    def refresh_buffers(self, name, last=False):
+        """internal buffers (cell-sorted index space) whose ghost rows must be refreshed after stage `name`"""
         if name == "DENSITY_LAMBDA":
-            return [self.buf("LAMBDA")]
+            return ["LAMBDA"]
         if name == "CORRECTION":
-            return [self.buf("PRED_CUR")] + ([self.buf("VEL_SORTED")] if last else [])
+            return ["PRED_CUR"] + (["VEL_SORTED"] if last else [])
         if name == "VORTICITY":
-            return [self.buf("VORT_NORM")]
+            return ["VORT_NORM"]
         if name == "CONFINEMENT":
-            return [self.buf("VEL_CONFINED")]
+            return ["VEL_CONFINED"]
         return []
 
-    def pred_cur(self):
-        return self.buf("PRED_CUR")
+    def row_width(self, name):
+        return self.ROW[name]
 
-    def list_state(self):
-        try:
-            return self.buf("LIST_BUILD_POS"), self.buf("LIST_INVALID"), self.dmax_sq
-        except _abi.RtpError:
-            return None
+    def pack(self, name, idx, out):
+        """out[k] = buffer[idx[k]] (idx int32 device tensor, -1 = "no particle" padding)"""
+        self.h.shard_pack(self.BUF[name], idx.data_ptr(), idx.numel(), out.data_ptr())
+
+    def unpack(self, name, idx, src):
+        self.h.shard_unpack(self.BUF[name], idx.data_ptr(), idx.numel(), src.data_ptr())
+
+    def inverse_perm(self, out):
+        self.h.shard_inverse_perm(out.data_ptr())
+
+    def check_ghosts(self, idx, next_epoch):
+        self.h.shard_check_ghosts(idx.data_ptr(), idx.numel(), next_epoch)
+
+    def new(self, shape, dtype):
+        return torch.empty(shape, dtype=dtype, device=self.device)
 
     def sync(self):
         self.h.sync()
 
 
+class _Exchange:
+    """one neighbour exchange: per side a list of (send tensor, receive tensor) pairs; None for a missing neighbour"""
+
+    def __init__(self, left, right):
+        self.left, self.right = left, right
+
+
 class SlabDecomposition:
     """One rank of the x-slab decomposition. `engine` is a CudaSlabEngine (or any object with the same interface)."""
 
-    def __init__(self, engine, grid, rank=None, world=None, group=None):
+    def __init__(self, engine, grid, rank=None, world=None, group=None, ghost_cap=None, migrate_cap=None):
         self.e = engine
         self.grid = tuple(grid)
         self.group = group
@@ -142,6 +164,24 @@ class SlabDecomposition:
         self.stats = {}
         self.profile = False  # record per-phase device times (ms) of the last step into stats["phases"]
         self._marks = []
+        # fixed capacities (rows) of a ghost region / a migration message per side
+        self.left = self.rank - 1 if self.rank > 0 else None
+        self.right = self.rank + 1 if self.rank < self.world - 1 else None
+        sides = (self.left is not None) + (self.right is not None)
+        self.ghost_cap = int(ghost_cap) if ghost_cap is not None else (engine.capacity // 8 if sides else 0)
+        self.migrate_cap = int(migrate_cap) if migrate_cap is not None else max(self.ghost_cap // 4, 1)
+        self.ghost_rows = self.ghost_cap * sides
+        self._pending_counts = None  # device tensor with the halo counts of the previous step (checked one step late)
+        e = engine
+        if sides:
+            f32, i64 = torch.float32, torch.int64
+            self._mig_s = {s: e.new((2, self.migrate_cap, 4), f32) for s in "lr"}
+            self._mig_r = {s: e.new((2, self.migrate_cap, 4), f32) for s in "lr"}
+            self._cnt_s = {s: e.new((1,), i64) for s in "lr"}
+            self._cnt_r = {s: e.new((1,), i64) for s in "lr"}
+            self._row_s = {w: {s: e.new((self.ghost_cap, w) if w > 1 else (self.ghost_cap,), f32) for s in "lr"} for w in (1, 4)}
+            self._row_r = {w: {s: e.new((self.ghost_cap, w) if w > 1 else (self.ghost_cap,), f32) for s in "lr"} for w in (1, 4)}
+            self._inv = e.new((e.capacity,), torch.int32)
 
     # ---- initial distribution: every rank is given the full initial state and keeps the particles of its slab
     def slab_of(self, keys):
@@ -151,56 +191,32 @@ class SlabDecomposition:
     def load_owned(self, pos, vel):
         """pos/vel: (n, 4) float32 tensors on the engine's device holding ONLY this rank's particles, any order"""
         n = pos.shape[0]
+        if n + self.ghost_rows > self.e.capacity:
+            raise RuntimeError("slab capacity exceeded: %d owned + %d ghost rows > %d" % (n, self.ghost_rows, self.e.capacity))
         with self.e.stream_context():
             self.e.set_counts(n, n)
             self.e.pos()[:n] = pos
             self.e.vel()[:n] = vel
         self.n_owned = n
 
-    # ---- exchanges with the left (rank-1) and right (rank+1) slab owners
-    def _peers(self):
-        return (self.rank - 1 if self.rank > 0 else None), (self.rank + 1 if self.rank < self.world - 1 else None)
-
     def _global(self, r):
         return r if self.group is None else dist.get_global_rank(self.group, r)
 
-    def _exchange_counts(self, n_left, n_right, like):
-        left, right = self._peers()
-        ops, bufs = [], {}
-        for peer, n, tag in ((left, n_left, "l"), (right, n_right, "r")):
-            if peer is None:
-                continue
-            s = torch.tensor([n], dtype=torch.int64, device=like.device)
-            rbuf = torch.zeros(1, dtype=torch.int64, device=like.device)
-            bufs[tag] = (s, rbuf)
-            ops.append(dist.P2POp(dist.isend, s, self._global(peer), self.group))
-            ops.append(dist.P2POp(dist.irecv, rbuf, self._global(peer), self.group))
-        if ops:
-            for w in dist.batch_isend_irecv(ops):
-                w.wait()
-        return (int(bufs["l"][1].item()) if "l" in bufs else 0), (int(bufs["r"][1].item()) if "r" in bufs else 0)
+    def _sides(self):
+        return [(s, p) for s, p in (("l", self.left), ("r", self.right)) if p is not None]
 
-    def _exchange(self, send_left, send_right, n_from_left, n_from_right):
-        """send rows to the neighbours, receive n_from_* rows from them (row shape/dtype of the sends).
-        Every exchange posts exactly one send and one receive per existing neighbour, also for empty payloads (one pad
-        row is appended), so the NCCL operation pattern never changes: a new pattern (e.g. the first send-only
-        migration) otherwise costs a one-off 50-100 ms connection set-up in the middle of the run."""
-        left, right = self._peers()
+    # ---- transport over torch.distributed: one batched P2P per exchange point
+    def _run_dist(self, x):
         ops = []
-        tail = tuple(send_left.shape[1:])
-        pad = torch.zeros((1,) + tail, dtype=send_left.dtype, device=send_left.device)
-        recv_l = torch.empty((n_from_left + 1,) + tail, dtype=send_left.dtype, device=send_left.device)
-        recv_r = torch.empty((n_from_right + 1,) + tail, dtype=send_left.dtype, device=send_left.device)
-        if left is not None:
-            ops.append(dist.P2POp(dist.isend, torch.cat([send_left, pad], dim=0), self._global(left), self.group))
-            ops.append(dist.P2POp(dist.irecv, recv_l, self._global(left), self.group))
-        if right is not None:
-            ops.append(dist.P2POp(dist.isend, torch.cat([send_right, pad], dim=0), self._global(right), self.group))
-            ops.append(dist.P2POp(dist.irecv, recv_r, self._global(right), self.group))
+        for peer, pairs in ((self.left, x.left), (self.right, x.right)):
+            if peer is None or pairs is None:
+                continue
+            for send, recv in pairs:
+                ops.append(dist.P2POp(dist.isend, send, self._global(peer), self.group))
+                ops.append(dist.P2POp(dist.irecv, recv, self._global(peer), self.group))
         if ops:
             for w in dist.batch_isend_irecv(ops):
                 w.wait()
-        return recv_l[:n_from_left], recv_r[:n_from_right]
 
     def _apply_migration(self, pos, vel, n, holes, arrivals):
         """arrivals (k_in, 8) fill the slots `holes` of the leavers; a surplus is appended, a deficit is filled from the tail"""
@@ -211,8 +227,8 @@ class SlabDecomposition:
             vel[holes[:m]] = arrivals[:m, 4:]
         if k_in > k_out:
             extra = k_in - k_out
-            if n + extra > pos.shape[0]:
-                raise RuntimeError("slab capacity exceeded: %d > %d" % (n + extra, pos.shape[0]))
+            if n + extra + self.ghost_rows > pos.shape[0]:
+                raise RuntimeError("slab capacity exceeded: %d > %d" % (n + extra + self.ghost_rows, pos.shape[0]))
             pos[n:n + extra] = arrivals[m:, :4]
             vel[n:n + extra] = arrivals[m:, 4:]
             n += extra
@@ -234,14 +250,12 @@ class SlabDecomposition:
         dev = self.e.pos().device
         with self.e.stream_context():
             for k_out, k_in in ((3, 1), (1, 3), (2, 2)):
-                p = torch.zeros((16, 4), device=dev)
-                v = torch.zeros((16, 4), device=dev)
+                p = torch.zeros((16 + self.ghost_rows, 4), device=dev)
+                v = torch.zeros((16 + self.ghost_rows, 4), device=dev)
                 holes = torch.arange(1, 1 + k_out, device=dev) * 3
                 self._apply_migration(p, v, 12, holes, torch.ones((k_in, 8), device=dev))
-                torch.cat([p[holes], v[holes]], dim=1)
             lay = self.slab_of(torch.arange(8, device=dev, dtype=torch.int32))
-            torch.nonzero(lay < 1).flatten()
-            torch.nonzero((lay < 1) | (lay >= 2)).flatten()
+            torch.nonzero_static(lay < 1, size=4, fill_value=-1)
         self.e.sync()
 
     def _mark(self, name):
@@ -251,12 +265,25 @@ class SlabDecomposition:
             self._marks.append((name, ev))
 
     def step(self):
+        """one step over torch.distributed (every rank is a process)"""
+        for x in self.step_gen():
+            with self.e.stream_context():  # the P2P batch is ordered after the pack kernels on the engine's stream
+                self._run_dist(x)
+
+    def step_gen(self):
+        """the step as a generator: yields an _Exchange at every point where rows travel between neighbours (the caller
+        performs it: SlabDecomposition.step over torch.distributed, LocalSlabGroup inside one process). The code between
+        two exchange points runs with the engine's stream current; the generator is never suspended inside that context."""
         e = self.e
         self._marks = []
-        with e.stream_context():
-            self._mark("begin")
-            self._step()
-            self._mark("end")
+        inner = self._step()
+        while True:
+            with e.stream_context():
+                try:
+                    x = next(inner)
+                except StopIteration:
+                    break
+            yield x
         if self.profile and self._marks:
             e.sync()
             ph = {}
@@ -264,88 +291,98 @@ class SlabDecomposition:
                 ph[name] = ph.get(name, 0.0) + a.elapsed_time(b)
             self.stats["phases"] = {k: round(v, 3) for k, v in ph.items()}
 
+    def _compact(self, mask, cap):
+        """indices of the set entries of `mask`, padded with -1 to `cap` rows (no host synchronisation), and their number"""
+        return torch.nonzero_static(mask, size=cap, fill_value=-1).flatten().to(torch.int32), mask.sum()
+
     def _step(self):
         e, n = self.e, self.n_owned
         jacobi = e.jacobi
-        left, right = self._peers()
+        sides = self._sides()
         pos, vel = e.pos(), e.vel()
+        self._mark("begin")
 
         # 1. predict, migrate
         e.set_counts(n, n)
         e.stage("PREDICT")
-        if self.world > 1:
+        if sides:
             layer = self.slab_of(e.keys_in()[:n])
-            go_l = (layer < self.xlo) if left is not None else torch.zeros_like(layer, dtype=torch.bool)
-            go_r = (layer >= self.xhi) if right is not None else torch.zeros_like(layer, dtype=torch.bool)
-            idx_l, idx_r = torch.nonzero(go_l).flatten(), torch.nonzero(go_r).flatten()
-            n_in_l, n_in_r = self._exchange_counts(idx_l.numel(), idx_r.numel(), pos)
-            self.stats["migrated_out"] = int(idx_l.numel() + idx_r.numel())
-            k_out, k_in = idx_l.numel() + idx_r.numel(), n_in_l + n_in_r
-            # every rank takes part in the (possibly empty) migration exchange: its neighbours cannot know it has nothing
-            in_l, in_r = self._exchange(torch.cat([pos[idx_l], vel[idx_l]], dim=1), torch.cat([pos[idx_r], vel[idx_r]], dim=1),
-                                        n_in_l, n_in_r)
-            if k_out + k_in:
+            idx = {}
+            for s, _ in sides:
+                idx[s], cnt = self._compact((layer < self.xlo) if s == "l" else (layer >= self.xhi), self.migrate_cap)
+                self._cnt_s[s].copy_(cnt.reshape(1))
+                e.pack("POS", idx[s], self._mig_s[s][0])
+                e.pack("VEL", idx[s], self._mig_s[s][1])
+            yield _Exchange(*[[(self._mig_s[s], self._mig_r[s]), (self._cnt_s[s], self._cnt_r[s])] if p is not None else None
+                              for s, p in (("l", self.left), ("r", self.right))])
+            # the one host synchronisation of the step: how many particles left and arrived (+ last step's halo counts)
+            vals = [self._cnt_s[s] for s, _ in sides] + [self._cnt_r[s] for s, _ in sides]
+            if self._pending_counts is not None:
+                vals.append(self._pending_counts)
+            host = torch.cat([v.reshape(-1) for v in vals]).cpu().tolist()
+            k = len(sides)
+            out_c, in_c, halo_c = host[:k], host[k:2 * k], host[2 * k:]
+            if max(out_c + in_c) > self.migrate_cap:
+                raise RuntimeError("migration capacity exceeded: %d > %d rows" % (max(out_c + in_c), self.migrate_cap))
+            if halo_c and max(halo_c) > self.ghost_cap:
+                raise RuntimeError("ghost capacity exceeded in the previous step: %d > %d rows" % (max(halo_c), self.ghost_cap))
+            self.stats["migrated_out"] = int(sum(out_c))
+            if sum(out_c) + sum(in_c):
+                holes = torch.cat([idx[s][:c] for (s, _), c in zip(sides, out_c)]).to(torch.int64)
+                arrivals = torch.cat([torch.cat([self._mig_r[s][0][:c], self._mig_r[s][1][:c]], dim=1) for (s, _), c in zip(sides, in_c)], dim=0)
                 # only the handful of migrating rows are touched: arrivals fill the slots of the leavers, a surplus is
                 # appended, a deficit is filled from the tail (order inside a cell is not preserved for moved rows)
-                n = self._apply_migration(pos, vel, n, torch.cat([idx_l, idx_r]), torch.cat([in_l, in_r], dim=0))
+                n = self._apply_migration(pos, vel, n, holes, arrivals)
                 e.set_counts(n, n)
                 e.stage("PREDICT")
         self._mark("predict+migrate")
 
-        # 2. halo of predicted positions, sort everything by cell
-        ng_l = ng_r = 0
-        if self.world > 1:
+        # 2. halo of predicted positions into the fixed-capacity ghost regions, sort everything by cell
+        G = self.ghost_cap
+        n_loc = n + self.ghost_rows
+        if sides:
+            if n_loc > e.capacity:
+                raise RuntimeError("slab capacity exceeded: %d > %d" % (n_loc, e.capacity))
             layer = self.slab_of(e.keys_in()[:n])
-            src_l = torch.nonzero(layer < self.xlo + GHOST_LAYERS).flatten() if left is not None else layer.new_empty(0)
-            src_r = torch.nonzero(layer >= self.xhi - GHOST_LAYERS).flatten() if right is not None else layer.new_empty(0)
-            ng_l, ng_r = self._exchange_counts(src_l.numel(), src_r.numel(), pos)
+            src, counts = {}, []
+            for s, _ in sides:
+                m = (layer < self.xlo + GHOST_LAYERS) if s == "l" else (layer >= self.xhi - GHOST_LAYERS)
+                src[s], c = self._compact(m, G)
+                counts.append(c.reshape(1))
+                e.pack("PRED_IN", src[s], self._row_s[4][s])
+            self._pending_counts = torch.cat(counts)
+            yield _Exchange(*[[(self._row_s[4][s], self._row_r[4][s])] if p is not None else None for s, p in (("l", self.left), ("r", self.right))])
             pred_in = e.pred_in()
-            gl, gr = self._exchange(pred_in[src_l], pred_in[src_r], ng_l, ng_r)
-            ng = ng_l + ng_r
-            if n + ng > e.capacity:
-                raise RuntimeError("slab capacity exceeded: %d > %d" % (n + ng, e.capacity))
-            ghosts = torch.cat([gl, gr], dim=0)
-            pred_in[n:n + ng] = ghosts
-            pos[n:n + ng] = ghosts
-            vel[n:n + ng] = 0.0
-            e.set_counts(n, n + ng)
+            off = {}
+            for k, (s, _) in enumerate(sides):
+                off[s] = n + k * G
+                pred_in[off[s]:off[s] + G] = self._row_r[4][s]
+                pos[off[s]:off[s] + G] = self._row_r[4][s]
+            vel[n:n_loc] = 0.0
+            e.set_counts(n, n_loc)
             e.stage("GHOST_KEYS")
-        n_loc = n + ng_l + ng_r
-        self.stats.update(owned=n, ghosts=ng_l + ng_r)
+        self.stats.update(owned=n, ghosts=self.ghost_rows)
         self._mark("halo")
         e.stage("SORT")
         self._mark("sort")
 
         refresh = None
-        if self.world > 1:
-            perm = e.perm()[:n_loc].to(torch.int64)
-            inv = torch.empty_like(perm)
-            inv[perm] = torch.arange(n_loc, device=perm.device)
-            send_l, send_r = inv[src_l], inv[src_r]
-            recv_l, recv_r = inv[n:n + ng_l], inv[n + ng_l:n_loc]
+        if sides:
+            inv = self._inv[:n_loc]
+            e.inverse_perm(inv)
+            send = {s: torch.where(src[s] >= 0, inv[src[s].clamp(min=0).to(torch.int64)], src[s]) for s, _ in sides}
+            recv = {s: inv[off[s]:off[s] + G] for s, _ in sides}
+            ghost_idx = torch.cat([recv[s] for s, _ in sides])
 
-            def refresh(tensors):
-                for t in tensors:
-                    rl, rr = self._exchange(t[send_l], t[send_r], ng_l, ng_r)
-                    if ng_l:
-                        t[recv_l] = rl
-                    if ng_r:
-                        t[recv_r] = rr
-
-            ghost_idx = torch.cat([recv_l, recv_r])
-            lists = e.list_state()
-
-            def check_ghost_displacement(next_epoch):
-                # the owner's kernel checks the particles it moves; a ghost moved by ITS owner is checked here
-                if lists is None or ghost_idx.numel() == 0:
-                    return
-                build_pos, invalid, dmax_sq = lists
-                d = e.pred_cur()[ghost_idx, :3] - build_pos[ghost_idx, :3]
-                moved = ((d * d).sum(dim=1) > dmax_sq).any().to(invalid.dtype)
-                invalid[next_epoch] = torch.maximum(invalid[next_epoch], moved)
-        else:
-            def check_ghost_displacement(next_epoch):
-                return
+            def refresh(names):
+                for name in names:
+                    w = e.row_width(name)
+                    for s, _ in sides:
+                        e.pack(name, send[s], self._row_s[w][s])
+                    yield _Exchange(*[[(self._row_s[w][s], self._row_r[w][s])] if p is not None else None
+                                      for s, p in (("l", self.left), ("r", self.right))])
+                    for s, _ in sides:
+                        e.unpack(name, recv[s], self._row_r[w][s])
         self._mark("index-maps")
 
         # 3. the solver stages, each followed by the refresh of what it produced
@@ -354,39 +391,73 @@ class SlabDecomposition:
             e.stage("DENSITY_LAMBDA", it)
             self._mark("compute")
             if refresh:
-                refresh(e.refresh_fields("DENSITY_LAMBDA"))
+                yield from refresh(e.refresh_buffers("DENSITY_LAMBDA"))
                 self._mark("refresh")
             e.stage("CORRECTION", it, last)
             self._mark("compute")
             if refresh:
-                refresh(e.refresh_fields("CORRECTION", last))
-                check_ghost_displacement(it + 1)
+                yield from refresh(e.refresh_buffers("CORRECTION", last))
+                e.check_ghosts(ghost_idx, it + 1)  # the owner's kernel checks the particles it moves; its ghosts are checked here
                 self._mark("refresh")
         if e.vorticity:
             e.stage("VORTICITY", jacobi)
             self._mark("compute")
             if refresh:
-                refresh(e.refresh_fields("VORTICITY"))
+                yield from refresh(e.refresh_buffers("VORTICITY"))
                 self._mark("refresh")
             e.stage("CONFINEMENT", jacobi)
             self._mark("compute")
             if refresh:
-                refresh(e.refresh_fields("CONFINEMENT"))
+                yield from refresh(e.refresh_buffers("CONFINEMENT"))
                 self._mark("refresh")
             e.stage("XSPH", jacobi)
             self._mark("compute")
 
         # 4. drop the ghosts; owned particles stay in cell-sorted order
-        if self.world > 1 and n_loc > n:
+        if n_loc > n:
             e.stage("DROP_GHOSTS")
         e.set_counts(n, n)
         self.n_owned = n
         self._mark("compact")
+        self._mark("end")
 
     def owned_state(self):
         n = self.n_owned
         with self.e.stream_context():
             return self.e.pos()[:n].clone(), self.e.vel()[:n].clone()
+
+
+class LocalSlabGroup:
+    """All ranks of a decomposition inside ONE process (any mix of devices, e.g. 4 slabs on one GPU): the ranks' steps are
+    generators advanced in lock step; at every exchange point the rows are copied between the ranks' buffers."""
+
+    def __init__(self, slabs):
+        self.slabs = list(slabs)
+
+    def step(self):
+        gens = [sd.step_gen() for sd in self.slabs]
+        while True:
+            xs = []
+            for g in gens:
+                try:
+                    xs.append(next(g))
+                except StopIteration:
+                    xs.append(None)
+            if all(x is None for x in xs):
+                return
+            if any(x is None for x in xs):
+                raise RuntimeError("the ranks of a LocalSlabGroup left the step at different exchange points")
+            for sd in self.slabs:
+                sd.e.sync()  # the rows to send are complete
+            for r, x in enumerate(xs):
+                if x.right is not None:  # my right-going rows are my right neighbour's rows "from the left", and vice versa
+                    for (send, _), (_, recv) in zip(x.right, xs[r + 1].left):
+                        recv.copy_(send)
+                    for (_, recv), (send, _) in zip(x.right, xs[r + 1].left):
+                        recv.copy_(send)
+            for sd in self.slabs:
+                if hasattr(sd.e, "device"):
+                    torch.cuda.synchronize(sd.e.device)
 
 
 def split_initial_state(pos, box, grid, rank, world):

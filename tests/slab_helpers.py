@@ -46,11 +46,52 @@ class OracleSlabEngine:
     def pred_cur(self):
         return self._t("PRED_POS")
 
-    def perm(self):
-        return self._t("PERM")
+    # ---- exchange helpers (library kernels on the CUDA engine, torch indexing here)
+    # (the CUDA engine refreshes |vorticity|, which it keeps as a scalar; the oracle's confinement sweep takes
+    #  fast_length(vort[e]) of the vector, so here the vector travels)
+    BUF = dict(PRED_IN="PRED_POS", PRED_CUR="PRED_POS", LAMBDA="CONST_FACTOR", VEL_SORTED="VEL", VORT4="VORT", VEL_CONFINED="VEL",
+               POS="POS", VEL="VEL")
+    ROW = dict(PRED_IN=4, PRED_CUR=4, LAMBDA=1, VEL_SORTED=4, VORT4=4, VEL_CONFINED=4, POS=4, VEL=4)
 
-    def list_state(self):
-        return None
+    def row_width(self, name):
+        return self.ROW[name]
+
+    def pack(self, name, idx, out):
+        i = idx.to(torch.int64)
+        ok = i >= 0
+        t = self._t(self.BUF[name])
+        out[ok] = t[i[ok]]
+        if t.dim() == 2:
+            out[~ok] = torch.tensor([float("inf")] * 3 + [0.0])
+        else:
+            out[~ok] = 0.0
+
+    def unpack(self, name, idx, src):
+        i = idx.to(torch.int64)
+        ok = i >= 0
+        self._t(self.BUF[name])[i[ok]] = src[ok]
+
+    def inverse_perm(self, out):
+        n = self.w.N
+        perm = self._t("PERM")[:n].to(torch.int64)
+        out[perm] = torch.arange(n, dtype=torch.int32)
+
+    def check_ghosts(self, idx, next_epoch):
+        pass  # the oracle has no neighbour lists
+
+    def new(self, shape, dtype):
+        return torch.empty(shape, dtype=dtype)
+
+    def refresh_buffers(self, name, last=False):
+        if name == "DENSITY_LAMBDA":
+            return ["LAMBDA"]
+        if name == "CORRECTION":
+            return ["PRED_CUR"] + (["VEL_SORTED"] if last else [])
+        if name == "VORTICITY":
+            return ["VORT4"]
+        if name == "CONFINEMENT":
+            return ["VEL_CONFINED"]
+        return []
 
     def stage(self, name, it=0, last=False):
         w = self.w
@@ -71,17 +112,6 @@ class OracleSlabEngine:
             w.reset_ids()
         for s in seq:
             w.run_stage(s)
-
-    def refresh_fields(self, name, last=False):
-        if name == "DENSITY_LAMBDA":
-            return [self._t("CONST_FACTOR")]
-        if name == "CORRECTION":
-            return [self._t("PRED_POS")] + ([self._t("VEL")] if last else [])
-        if name == "VORTICITY":
-            return [self._t("VORT")]
-        if name == "CONFINEMENT":
-            return [self._t("VEL")]
-        return []
 
     def sync(self):
         pass
