@@ -31,11 +31,11 @@ FLUID_DEFAULTS = (450.0, 600.0, 0.010, 3, 1, 0.006, 0.001, 4, 1, 0.0004, 0.0001)
 JACOBI = 3
 
 # algorithmic bytes per particle per launch; t = cell-table bytes per particle per pass
-def algorithmic_bytes(ncells, n):
+def algorithmic_bytes(ncells, n, sort_passes=2):
     t = 8.0 * ncells / n
     return {
         "predictPosition+fillCellIDs": 48 + 20,
-        "radixSort(onesweep)": 4 + 16 * 2,
+        "radixSort(onesweep)": 4 + 16 * sort_passes,
         "gather+cellTable": 100 + 4 + t,
         "adjustEndCell": t,
         "densityLambda": (20 + t) + (24 + t),  # fld_computeDensity + fld_computeConstraintFactor, fused
@@ -130,6 +130,41 @@ def cpu_world(pos, which):
     w.upload("VEL", np.zeros((N130K, 4), np.float32))
     w.reset_ids()
     return w, n_thr
+
+
+def parity_figures(abi, pos, device):
+    """CUDA path vs the CPU checkers on ONE step of the 130k dam break from the same initial state: max-norm relative error
+    per field against the reference's own kernel sources (oracle/_ref, IEEE arithmetic without contraction) and against the
+    oracle restatement (canonical fused arithmetic). Part of the cpu_baseline leg: the checkers are
+    never on the product path."""
+    import numpy as np
+    from oracle import oracle_py as O
+    h = abi.Handle(abi.FLUIDS, N130K, N130K, (10, 10, 10), (30, 30, 30), 3, 0, device)
+    h.set_fluid_params(abi.FluidParams(*FLUID_DEFAULTS), JACOBI)
+    h.upload("p_pos", pos)
+    h.upload("p_vel", np.zeros((N130K, 4), np.float32))
+    h.reset_ids()
+    h.step(abi.STEP_PHYSICS)
+    h.sync()
+    ours = {f: h.download(n) for f, n in (("POS", "p_pos"), ("VEL", "p_vel"), ("DENSITY", "p_density"), ("CONST_FACTOR", "p_constFactor"),
+                                           ("CELL_ID", "p_cellID"), ("PERM", "RadixSortIndices"), ("START_END_CELL", "c_startEndPartID"))}
+    h.close()
+    out = {"step": "1 step of pbf_dam_130k_I3_vorticity_xsph", "norm": "max|a-b| / max|b|"}
+    for kind in ("reference", "port"):
+        cw = cpu_world(pos, kind)
+        if cw is None:
+            continue
+        w = cw[0]
+        w.step(O.STEP_PHYSICS)
+        r = {}
+        for f, a in ours.items():
+            b = w.download(f)
+            if a.dtype.kind in "iu":
+                r[f] = "bit-exact" if np.array_equal(a, b) else "%d mismatches" % int((a != b).sum())
+            else:
+                r[f] = float(np.abs(a.astype(np.float64) - b).max() / max(np.abs(b).max(), 1e-30))
+        out["vs_reference_kernels_on_cpu" if kind == "reference" else "vs_oracle_port"] = r
+    return out
 
 
 def time_cpu_world(w, warmup, steps, budget_s):
@@ -255,6 +290,30 @@ def quick_bench(abi, torch, name, device, steps, warmup, flush):
     out = {"particles": n, "steps": steps, "warmup": warmup, "steps_per_s": round(steps / (ms * 1e-3), 2),
            "value": n * steps / (ms * 1e-3), "unit": "particle-updates/s", "launches_per_step": h.last_launch_count(),
            "algorithmic_bytes_per_particle": bpp, "whole_step_frac_of_hbm": round(n * steps / (ms * 1e-3) * bpp / 1e9 / peak, 4)}
+    if name.startswith("pbf_dam_16m"):
+        # where HBM is really in play (the state is 20x the L2): per-kernel algorithmic GB/s, events between launches of the
+        # next 4 steps after the timed window
+        h.enable_profiling(True)
+        acc, cnt, reps = {}, {}, 4
+        for _ in range(reps):
+            h.step(abi.STEP_PHYSICS)
+            for nm, v in h.stage_times():
+                acc[nm] = acc.get(nm, 0.0) + v
+                cnt[nm] = cnt.get(nm, 0) + 1
+        h.enable_profiling(False)
+        ab = algorithmic_bytes(240 * 120 * 120, n, sort_passes=3)
+        tot = sum(acc.values()) / reps
+        kern = {}
+        for nm in acc:
+            per = acc[nm] / cnt[nm]
+            gbs = ab[nm] * n / (per * 1e-3) / 1e9 if nm in ab else None
+            kern[nm] = {"ms_per_launch": round(per, 4), "launches_per_step": cnt[nm] // reps, "share": round(acc[nm] / reps / tot, 4),
+                        "algorithmic_GBps": None if gbs is None else round(gbs, 1), "frac_of_hbm": None if gbs is None else round(gbs / peak, 4)}
+        out["kernels_16m"] = kern
+        dom = max((k for k in kern if k in ab), key=lambda k: kern[k]["share"])
+        out["roofline_16m"] = {"bound": "hbm", "kernel": dom, "achieved": kern[dom]["algorithmic_GBps"], "peak": peak, "unit": "GB/s",
+                               "frac": kern[dom]["frac_of_hbm"], "window": "steps %d-%d of the 16M dam break, un-graphed launches" % (
+                                   warmup + steps + 1, warmup + steps + reps)}
     h.close()
     return out
 
@@ -420,6 +479,14 @@ def run_ours(args):
         torch.cuda.empty_cache()
         try:
             slab = run_slab_16m(args, torch, abi, rank, local_rank, world)
+            # the 1-GPU anchor of the strong-scaling efficiency: the SAME code path and step window with one slab, on rank 0
+            # (the other ranks wait), so that the efficiency is formed from like-for-like numbers of one box
+            dist.barrier()
+            if rank == 0:
+                one = run_slab_16m(args, torch, abi, 0, local_rank, 1)
+                slab["one_gpu_same_window"] = {k: one[k] for k in ("ms_per_step", "value", "invariants")}
+                slab["strong_scaling_efficiency"] = round(one["ms_per_step"] / (world * slab["ms_per_step"]), 4)
+            dist.barrier()
         except Exception as e:  # keep the headline line even if the large config cannot run here
             slab = {"error": repr(e)[:300]}
         flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
@@ -454,6 +521,9 @@ def run_ours(args):
                          "algorithmic_GBps": None if gbs is None else round(gbs, 1),
                          "frac_of_hbm": None if gbs is None else round(gbs / peak, 4)}
     dom = max((k for k in kernels if abytes.get(k)), key=lambda k: kernels[k]["share"])
+    kernels_window = ("steps %d-%d of the dam break (after the %d warm-up + %d timed + %d L2-resident steps), events between "
+                      "UN-GRAPHED launches with the L2 flushed before each step: their sum exceeds ms_per_step, which replays "
+                      "one CUDA graph per step over steps %d-%d" % (W + 2 * K + 1, W + 2 * K + reps, W, K, K, W + 1, W + K))
     roofline = {"bound": "hbm", "kernel": dom, "achieved": kernels[dom]["algorithmic_GBps"], "peak": peak, "unit": "GB/s",
                 "frac": kernels[dom]["frac_of_hbm"], "traffic": None, "peak_source": peak_src,
                 "algorithmic_bytes_per_launch": abytes[dom] * N130K,
@@ -484,14 +554,16 @@ def run_ours(args):
     m.setStepFlags(abi.STEP_PHYSICS)
     hpos = torch.from_numpy(pos0.copy()).pin_memory()
     hvel = torch.zeros((N130K, 4), dtype=torch.float32).pin_memory()
-    hout = torch.empty((N130K, 4), dtype=torch.float32).pin_memory()
     ke = max(20, min(K, 500))
 
     def e2e_step():
+        # the state lives on the HOST between steps: what step k downloads is what step k + 1 uploads, so the simulation
+        # advances (the dam collapses over the timed window like in the device-resident run)
         m.upload("p_pos", hpos.numpy())
         m.upload("p_vel", hvel.numpy())
         m.update()
-        m._h.download("p_pos", out=hout.numpy())
+        m._h.download("p_pos", out=hpos.numpy())
+        m._h.download("p_vel", out=hvel.numpy())
     for _ in range(3):
         e2e_step()
     torch.cuda.synchronize()
@@ -500,9 +572,33 @@ def run_ours(args):
         e2e_step()
     torch.cuda.synchronize()
     e2e_dt = time.perf_counter() - t0
+    e2e_moved = float(np.abs(hpos.numpy()[:, :3] - pos0[:, :3]).max())
     e2e = {"value": N130K * ke / e2e_dt, "unit": "particle-updates/s", "h2d_bytes_per_step": 2 * N130K * 16,
-           "d2h_bytes_per_step": N130K * 16, "steps": ke, "ms_per_step": round(1e3 * e2e_dt / ke, 4),
-           "api": "realtimeparticles_b200.models.Fluids: upload(p_pos,p_vel) + update() + download(p_pos), pinned host buffers"}
+           "d2h_bytes_per_step": 2 * N130K * 16, "steps": ke, "ms_per_step": round(1e3 * e2e_dt / ke, 4),
+           "max_displacement_over_run": round(e2e_moved, 4),
+           "api": "realtimeparticles_b200.models.Fluids: upload(p_pos,p_vel) + update() + download(p_pos,p_vel), pinned host "
+                  "buffers; the downloaded state is the next step's upload"}
+
+    # ---- what Model::update() costs in the app: physics + render-side kernels + camera sort (Fluids.cpp:400-471)
+    hf, _ = make_pbf(abi, local_rank)
+    sf = torch.cuda.ExternalStream(hf.stream(), device=dev)
+    full_flags = abi.STEP_PHYSICS | abi.STEP_RENDER_AUX | abi.STEP_CAMERA_SORT
+    with torch.cuda.stream(sf):
+        hf.step_n(W, full_flags)
+    hf.sync()
+    evf = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(min(K, 500))]
+    with torch.cuda.stream(sf):
+        for a, b in evf:
+            flush.zero_()
+            a.record(sf)
+            hf.step_n(1, full_flags)
+            b.record(sf)
+    hf.sync()
+    full_ms = sum(a.elapsed_time(b) for a, b in evf)
+    full_update = {"steps_per_s": round(len(evf) / (full_ms * 1e-3), 1), "ms_per_step": round(full_ms / len(evf), 4), "steps": len(evf),
+                   "launches_per_step": hf.last_launch_count(),
+                   "what": "rtp_step(PHYSICS | RENDER_AUX | CAMERA_SORT): the whole Fluids::update() of the app, L2 flushed per step"}
+    hf.close()
 
     # ---- CPU baseline on this box's host cores, bounded sample: the reference's own kernels compiled for the CPU
     # (oracle/_ref) when that library travelled here, and the oracle port beside it
@@ -519,6 +615,11 @@ def run_ours(args):
                 cpu = r
             else:
                 cpu["oracle_port"] = {k: r[k] for k in ("value", "cores", "sample")}
+        if cpu is not None:
+            try:
+                cpu["parity"] = parity_figures(abi, pos0, local_rank)
+            except Exception as e:
+                cpu["parity"] = {"error": repr(e)[:200]}
 
     others = {}
     if not args.no_other_workloads:
@@ -538,9 +639,10 @@ def run_ours(args):
         "steps_per_s": K / (ms_total * 1e-3),
         "l2_resident": {"value": N130K * K / (warm_ms * 1e-3), "steps_per_s": K / (warm_ms * 1e-3),
                         "note": "same K steps replayed back to back from one CUDA graph, no flush"},
-        "e2e": e2e, "gpu_launches": launches_per_step * K * world, "launches_per_step": launches_per_step,
-        "roofline": roofline, "kernels": kernels, "cpu_baseline": cpu, "clocks": sampler.result(),
+        "e2e": e2e, "full_update": full_update, "gpu_launches": launches_per_step * K * world, "launches_per_step": launches_per_step,
+        "roofline": roofline, "kernels": kernels, "kernels_window": kernels_window, "cpu_baseline": cpu, "clocks": sampler.result(),
         "other_workloads": others, "slab_16m": slab,
+        "slab_16m_strong_scaling_efficiency": (slab or {}).get("strong_scaling_efficiency"),
         "wall_s_timed_region": round(t_wall, 3),
     }
     print(json.dumps(out), flush=True)

@@ -242,6 +242,17 @@ RTP_API int64_t rtp_gen_random_box(float* out_xyzw, int64_t n, const float start
 /* the float a reference kernel sees for a -D constant: parse(FloatToStr(v)) (utils/Utils.cpp:24-29) */
 RTP_API float rtp_baked_constant(float v);
 
+/* ---- OpenGL interop (replaces the cl::BufferGL wrapping of the shared VBOs, Context.cpp:517-541, and
+ * acquireGLBuffers / releaseGLBuffers around every frame, Context.cpp:710-750). The render engine owns the VBOs
+ * (render/Engine.cpp:70-87 p_pos / p_col float4[maxNbParticles], :300-304 c_partDetector 8 floats per cell) and hands their
+ * names to the model (ModelParams, Model.hpp:67-70). After rtp_register_gl the VBO IS the field: rtp_step maps it
+ * (cudaGraphicsMapResources on the handle's stream), the kernels write straight into it, and it is unmapped before rtp_step
+ * returns, so OpenGL may draw as soon as the stream has drained (rtp_sync) -- no copy. rtp_upload / rtp_download of a
+ * registered field map it for the copy. Must be called on the thread that owns the OpenGL context; fails with RTP_ERR_CUDA
+ * (and leaves the handle as it was) when there is none. field: RTP_F_POS, RTP_F_COL or RTP_F_PART_DETECTOR. */
+RTP_API int rtp_register_gl(rtp_handle* h, int field, unsigned int vbo);
+RTP_API int rtp_unregister_gl(rtp_handle* h, int field);
+
 /* ---- boids target trajectory (host side; replaces Physics::Target, physics/utils/Target.cpp:11-50 with its three
  * PerlinNoise channels, physics/utils/PerlinNoise.cpp:10-85). The reference moves the target once per frame on the CPU
  * (Boids.cpp:351-358) and hands the position to bd_addTargetRule; a host does the same with rtp_target_update() and

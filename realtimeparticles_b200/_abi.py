@@ -82,7 +82,7 @@ EXPORTS = ["rtp_abi_version", "rtp_device_count", "rtp_create", "rtp_destroy", "
            "rtp_sync", "rtp_get_stream", "rtp_sort_keys", "rtp_sort_keys_host", "rtp_selftest_math", "rtp_enable_profiling", "rtp_get_stage_times",
            "rtp_last_launch_count", "rtp_list_stats", "rtp_shard_set_owned", "rtp_shard_stage", "rtp_shard_buffer", "rtp_shard_list_dmax_sq", "rtp_shard_pack", "rtp_shard_unpack", "rtp_shard_inverse_perm", "rtp_shard_check_ghosts",
            "rtp_gen_box_grid", "rtp_gen_sphere_grid", "rtp_gen_rectangle_grid", "rtp_gen_circle_grid", "rtp_gen_random_box",
-           "rtp_baked_constant", "rtp_target_create", "rtp_target_destroy", "rtp_target_update"]
+           "rtp_baked_constant", "rtp_register_gl", "rtp_unregister_gl", "rtp_target_create", "rtp_target_destroy", "rtp_target_update"]
 
 _lib = None
 
@@ -299,6 +299,11 @@ class Handle:
         p, n = C.c_void_p(), C.c_size_t()
         self._check(self.L.rtp_shard_buffer(self.h, int(which), C.byref(p), C.byref(n)), "rtp_shard_buffer")
         return p.value, n.value
+
+    def register_gl(self, field, vbo):
+        """share an OpenGL VBO (by name) as the buffer of p_pos / p_col / c_partDetector (rtp_register_gl)"""
+        self.L.rtp_register_gl.argtypes = [C.c_void_p, C.c_int, C.c_uint]
+        self._check(self.L.rtp_register_gl(self.h, field_id(field), int(vbo)), "rtp_register_gl")
 
     def shard_pack(self, which, idx_ptr, n, out_ptr):
         self._check(self.L.rtp_shard_pack(self.h, int(which), idx_ptr, int(n), out_ptr), "rtp_shard_pack")

@@ -16,6 +16,9 @@
 #include <memory>
 #include <stdexcept>
 #include <string>
+#include <utility>
+#include <cstdlib>
+#include <utility>
 #include <variant>
 #include <vector>
 
@@ -32,6 +35,13 @@ using TargetKernelInputs = rtp_target_params;
 using FluidKernelInputs = rtp_fluid_params;
 using CloudKernelInputs = rtp_cloud_params;
 
+// which GPU the backend runs on: RTP_DEVICE in the environment (default 0); the OpenCL backend picks "the" GPU itself
+inline int deviceFromEnv()
+{
+  const char* e = std::getenv("RTP_DEVICE");
+  return e ? std::atoi(e) : 0;
+}
+
 // CUDA counterpart of OclModel<KernelInputs...> (physics/ocl/OclModel.hpp:12-70)
 template <typename... KernelInputs>
 class CudaModel : public Model
@@ -43,7 +53,7 @@ class CudaModel : public Model
     (m_kernelInputs.push_back(kernelInputs), ...);
     rtp_config cfg {};
     cfg.model = rtpModel;
-    cfg.device = 0;
+    cfg.device = deviceFromEnv(); // RTP_DEVICE selects the GPU (default 0); the reference has no such notion
     cfg.max_particles = params.maxNbParticles;
     cfg.nb_particles = params.currNbParticles <= params.maxNbParticles ? params.currNbParticles : params.maxNbParticles;
     cfg.box[0] = (uint32_t)params.boxSize.x, cfg.box[1] = (uint32_t)params.boxSize.y, cfg.box[2] = (uint32_t)params.boxSize.z;
@@ -55,6 +65,16 @@ class CudaModel : public Model
       // like a failed OpenCL context: the model stays un-initialised and the app shows its pop-up
       m_handle = nullptr;
       m_createError = rtp_last_error(nullptr);
+    }
+    // the VBOs of the render engine (Model.hpp:67-70, created by render/Engine.cpp:70-87, :300-304) become the buffers of
+    // p_pos / p_col / c_partDetector, like the reference's createGLBuffer calls (Fluids.cpp:132-135). 0 = headless host.
+    if (m_handle)
+    {
+      const std::pair<int, unsigned int> shared[] = { { RTP_F_POS, params.particlePosVBO }, { RTP_F_COL, params.particleColVBO },
+        { RTP_F_PART_DETECTOR, params.gridVBO } };
+      for (const auto& sh : shared)
+        if (sh.second != 0 && rtp_register_gl(m_handle, sh.first, sh.second) != RTP_OK)
+          m_createError = rtp_last_error(m_handle); // keeps running on the library's own buffer for this field
     }
   }
   ~CudaModel() override { rtp_destroy(m_handle); }

@@ -17,6 +17,10 @@
 
 using namespace rtp;
 
+// cuda_gl_interop.h needs <GL/gl.h>, which a headless build box does not have; the one entry point used here only takes the
+// VBO name (GLuint = unsigned int), so it is declared by hand. libcudart resolves the driver's GL interop at run time.
+extern "C" cudaError_t cudaGraphicsGLRegisterBuffer(struct cudaGraphicsResource** resource, unsigned int buffer, unsigned int flags);
+
 static thread_local std::string g_createError;
 
 struct StageMark
@@ -52,6 +56,12 @@ struct rtp_handle
   bool graphValid = false;
   float4* graphPredFinal = nullptr; // p_predPos buffer at the start of the captured step
   int lastLaunches = 0;
+  // OpenGL interop: VBOs the render engine owns, borrowed by name (Model.hpp:67-70). While registered, the VBO IS the
+  // canonical buffer of the field: every step maps it and the kernels write straight into it (no copy).
+  static const int GL_SLOTS = 3; // p_pos, p_col, c_partDetector
+  cudaGraphicsResource* glRes[GL_SLOTS] = { nullptr, nullptr, nullptr };
+  void* glOwn[GL_SLOTS] = { nullptr, nullptr, nullptr }; // the library's own allocation, back in place after unregister
+  bool glMapped = false;
   // profiling
   bool profiling = false;
   std::vector<StageMark> marks;
@@ -198,6 +208,13 @@ extern "C" void rtp_destroy(rtp_handle* h)
     cudaStreamSynchronize(h->stream);
   if (h->graphExec)
     cudaGraphExecDestroy(h->graphExec);
+  for (int k = 0; k < rtp_handle::GL_SLOTS; ++k)
+    if (h->glRes[k])
+    {
+      cudaGraphicsUnregisterResource(h->glRes[k]);
+      h->allocs.push_back(h->glOwn[k]); // (the field pointer is the VBO's: release the library's own buffer too)
+      h->glRes[k] = nullptr;
+    }
   for (auto& m : h->marks)
     cudaEventDestroy(m.ev);
   for (void* p : h->allocs)
@@ -393,6 +410,59 @@ extern "C" int rtp_create(const rtp_config* cfg, rtp_handle** out)
   return RTP_OK;
 }
 
+// ------------------------------------------------------------------ OpenGL interop
+// Replaces the cl::BufferGL wrapping of the four shared VBOs (Context.cpp:517-541; created by render/Engine.cpp:70-87,
+// :300-304) and acquireGLBuffers / releaseGLBuffers around every frame (Context.cpp:710-750).
+
+static int glSlot(int field) { return field == RTP_F_POS ? 0 : (field == RTP_F_COL ? 1 : (field == RTP_F_PART_DETECTOR ? 2 : -1)); }
+static void** glFieldPtr(rtp_handle* h, int slot)
+{
+  return slot == 0 ? (void**)&h->s.posA : (slot == 1 ? (void**)&h->s.col : (void**)&h->s.partDetector);
+}
+static size_t glFieldBytes(rtp_handle* h, int slot) { return slot == 2 ? 32 * (size_t)h->g.numCells : 16 * (size_t)h->s.M; }
+static bool glAny(const rtp_handle* h) { return h->glRes[0] || h->glRes[1] || h->glRes[2]; }
+
+// map every registered VBO on the handle's stream and point the field at it; glUnmap gives it back to OpenGL
+static int glMap(rtp_handle* h)
+{
+  if (!glAny(h) || h->glMapped)
+    return RTP_OK;
+  cudaGraphicsResource* res[rtp_handle::GL_SLOTS];
+  int n = 0;
+  for (int k = 0; k < rtp_handle::GL_SLOTS; ++k)
+    if (h->glRes[k])
+      res[n++] = h->glRes[k];
+  CUDA_TRY(h, cudaGraphicsMapResources(n, res, h->stream));
+  h->glMapped = true;
+  for (int k = 0; k < rtp_handle::GL_SLOTS; ++k)
+    if (h->glRes[k])
+    {
+      void* p = nullptr;
+      size_t bytes = 0;
+      CUDA_TRY(h, cudaGraphicsResourceGetMappedPointer(&p, &bytes, h->glRes[k]));
+      if (bytes < glFieldBytes(h, k))
+        return fail(h, RTP_ERR_INVALID, "registered VBO is smaller than the field");
+      *glFieldPtr(h, k) = p;
+    }
+  return RTP_OK;
+}
+static int glUnmap(rtp_handle* h)
+{
+  if (!h->glMapped)
+    return RTP_OK;
+  cudaGraphicsResource* res[rtp_handle::GL_SLOTS];
+  int n = 0;
+  for (int k = 0; k < rtp_handle::GL_SLOTS; ++k)
+    if (h->glRes[k])
+    {
+      res[n++] = h->glRes[k];
+      *glFieldPtr(h, k) = nullptr; // nobody may touch the VBO while OpenGL has it
+    }
+  h->glMapped = false;
+  CUDA_TRY(h, cudaGraphicsUnmapResources(n, res, h->stream));
+  return RTP_OK;
+}
+
 // ------------------------------------------------------------------ buffers
 
 static int fieldInfo(rtp_handle* h, int field, void** ptr, size_t* bytes)
@@ -430,7 +500,7 @@ static int fieldInfo(rtp_handle* h, int field, void** ptr, size_t* bytes)
   case RTP_F_PART_DETECTOR: p = s.partDetector; b = 32 * C; break;
   default: return fail(h, RTP_ERR_INVALID, "unknown field id");
   }
-  if (!p)
+  if (!p && !(glSlot(field) >= 0 && h->glRes[glSlot(field)])) // (a field that lives in a VBO has no pointer while unmapped)
     return fail(h, RTP_ERR_STATE, "field does not exist for this model");
   *ptr = p;
   *bytes = b;
@@ -457,7 +527,21 @@ extern "C" int rtp_upload(rtp_handle* h, int field, const void* host, size_t byt
   if (bytes != b)
     return fail(h, RTP_ERR_INVALID, "rtp_upload: size mismatch");
   CUDA_TRY(h, cudaSetDevice(h->cfg.device));
+  const bool shared = glSlot(field) >= 0 && h->glRes[glSlot(field)];
+  if (shared)
+  {
+    const int mrc = glMap(h);
+    if (mrc != RTP_OK)
+      return mrc;
+    p = *glFieldPtr(h, glSlot(field));
+  }
   CUDA_TRY(h, cudaMemcpyAsync(p, host, bytes, cudaMemcpyHostToDevice, h->stream));
+  if (shared)
+  {
+    const int urc = glUnmap(h);
+    if (urc != RTP_OK)
+      return urc;
+  }
   CUDA_TRY(h, cudaStreamSynchronize(h->stream)); // blocking, like the reference's CL_TRUE writes (Context.cpp:368)
   return RTP_OK;
 }
@@ -474,7 +558,21 @@ extern "C" int rtp_download(rtp_handle* h, int field, void* host, size_t bytes)
   if (bytes != b)
     return fail(h, RTP_ERR_INVALID, "rtp_download: size mismatch");
   CUDA_TRY(h, cudaSetDevice(h->cfg.device));
+  const bool shared = glSlot(field) >= 0 && h->glRes[glSlot(field)];
+  if (shared)
+  {
+    const int mrc = glMap(h);
+    if (mrc != RTP_OK)
+      return mrc;
+    p = *glFieldPtr(h, glSlot(field));
+  }
   CUDA_TRY(h, cudaMemcpyAsync(host, p, bytes, cudaMemcpyDeviceToHost, h->stream));
+  if (shared)
+  {
+    const int urc = glUnmap(h);
+    if (urc != RTP_OK)
+      return urc;
+  }
   CUDA_TRY(h, cudaStreamSynchronize(h->stream));
   return RTP_OK;
 }
@@ -615,6 +713,72 @@ extern "C" int rtp_init_clouds_fields(rtp_handle* h)
   launchCloudsInitFields(h->s, h->g, h->cp, h->stream);
   CUDA_TRY(h, cudaGetLastError());
   return RTP_OK;
+}
+
+// ------------------------------------------------------------------ OpenGL interop: registration
+
+extern "C" int rtp_register_gl(rtp_handle* h, int field, unsigned int vbo)
+{
+  if (!h)
+    return RTP_ERR_INVALID;
+  const int slot = glSlot(field);
+  if (slot < 0)
+    return fail(h, RTP_ERR_INVALID, "rtp_register_gl: only p_pos, p_col and c_partDetector are shared with OpenGL");
+  if (h->glRes[slot])
+    return fail(h, RTP_ERR_STATE, "rtp_register_gl: field already registered");
+  CUDA_TRY(h, cudaSetDevice(h->cfg.device));
+  CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+  cudaGraphicsResource* res = nullptr;
+  const cudaError_t e = cudaGraphicsGLRegisterBuffer(&res, vbo, cudaGraphicsRegisterFlagsNone);
+  if (e != cudaSuccess)
+  {
+    (void)cudaGetLastError();
+    h->err = std::string("cudaGraphicsGLRegisterBuffer: ") + cudaGetErrorString(e) + " (is an OpenGL context current on this thread?)";
+    return RTP_ERR_CUDA;
+  }
+  // the current contents of the field move into the VBO; from now on the VBO is the field
+  void* own = *glFieldPtr(h, slot);
+  h->glRes[slot] = res;
+  h->glOwn[slot] = own;
+  int rc = glMap(h);
+  if (rc == RTP_OK)
+  {
+    cudaMemcpyAsync(*glFieldPtr(h, slot), own, glFieldBytes(h, slot), cudaMemcpyDeviceToDevice, h->stream);
+    rc = glUnmap(h);
+  }
+  if (rc != RTP_OK)
+  {
+    cudaGraphicsUnregisterResource(res);
+    h->glRes[slot] = nullptr;
+    *glFieldPtr(h, slot) = own;
+    return rc;
+  }
+  invalidateGraph(h);
+  return RTP_OK;
+}
+
+extern "C" int rtp_unregister_gl(rtp_handle* h, int field)
+{
+  if (!h)
+    return RTP_ERR_INVALID;
+  const int slot = glSlot(field);
+  if (slot < 0 || !h->glRes[slot])
+    return fail(h, RTP_ERR_STATE, "rtp_unregister_gl: field is not registered");
+  CUDA_TRY(h, cudaSetDevice(h->cfg.device));
+  // the VBO's contents come back into the library's own buffer
+  int rc = glMap(h);
+  if (rc == RTP_OK)
+  {
+    cudaMemcpyAsync(h->glOwn[slot], *glFieldPtr(h, slot), glFieldBytes(h, slot), cudaMemcpyDeviceToDevice, h->stream);
+    rc = glUnmap(h);
+  }
+  cudaStreamSynchronize(h->stream);
+  cudaGraphicsUnregisterResource(h->glRes[slot]);
+  h->glRes[slot] = nullptr;
+  *glFieldPtr(h, slot) = h->glOwn[slot];
+  h->glOwn[slot] = nullptr;
+  invalidateGraph(h);
+  return rc;
 }
 
 // ------------------------------------------------------------------ the step
@@ -837,7 +1001,15 @@ extern "C" int rtp_step(rtp_handle* h, unsigned flags, const float camera_pos[3]
   if (!h)
     return RTP_ERR_INVALID;
   CUDA_TRY(h, cudaSetDevice(h->cfg.device));
+  // acquireGLBuffers / releaseGLBuffers of the reference (Context.cpp:710-750): the kernels of the step write the mapped
+  // VBOs directly
+  int rc = glMap(h);
+  if (rc != RTP_OK)
+    return rc;
   h->lastLaunches = enqueueStep(h, flags, camera_pos ? camera_pos : kDefaultCam, h->profiling);
+  rc = glUnmap(h);
+  if (rc != RTP_OK)
+    return rc;
   CUDA_TRY(h, cudaGetLastError());
   return RTP_OK;
 }
@@ -850,6 +1022,17 @@ extern "C" int rtp_step_n(rtp_handle* h, unsigned flags, const float camera_pos[
     return RTP_OK;
   const float* cam = camera_pos ? camera_pos : kDefaultCam;
   CUDA_TRY(h, cudaSetDevice(h->cfg.device));
+  if (glAny(h))
+  {
+    // a mapped VBO may come back at another address: no graph replay, one map / step / unmap per frame
+    for (int i = 0; i < n; ++i)
+    {
+      const int rc = rtp_step(h, flags, cam);
+      if (rc != RTP_OK)
+        return rc;
+    }
+    return RTP_OK;
+  }
   // the captured graph bakes in the flags, the camera and the buffer p_predPos currently lives in (the camera sort reads it)
   if (!h->graphValid || h->graphFlags != flags || memcmp(h->graphCam, cam, sizeof h->graphCam) != 0 || h->graphPredFinal != h->predFinal)
   {

@@ -244,6 +244,21 @@ def test_fluid_presets_bomb_and_drop_vs_oracle(case):
     assert_close(p, ("POS", "VEL", "PRED_POS", "DENSITY", "VORT"), N=N)
 
 
+def test_gl_interop_without_a_gl_context_fails_cleanly():
+    # rtp_register_gl (cudaGraphicsGLRegisterBuffer on the VBO names of ModelParams, Model.hpp:67-70) needs a current OpenGL
+    # context; the GPU box is headless. The entry points must exist, refuse with RTP_ERR_CUDA + a message, and leave the
+    # handle fully usable (the zero-copy path itself needs a display: INTEGRATION.md section 4).
+    p = make_fluids(M=4096, res=(16, 16, 16), jacobi=2)
+    for field in ("p_pos", "p_col"):
+        with pytest.raises(_abi.RtpError) as ei:
+            p.h.register_gl(field, 1)
+        assert "cudaGraphicsGLRegisterBuffer" in str(ei.value)
+    with pytest.raises(_abi.RtpError):
+        p.h.register_gl("p_vel", 1)  # not a shared buffer
+    p.step(O.STEP_PHYSICS | O.STEP_RENDER_AUX)
+    assert_close(p, ("POS", "VEL", "COL"))
+
+
 def test_step_n_graph_replay_equals_single_steps():
     a = make_fluids(M=16384, res=(32, 32, 16), jacobi=3)
     b = make_fluids(M=16384, res=(32, 32, 16), jacobi=3)
