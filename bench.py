@@ -167,6 +167,34 @@ def parity_figures(abi, pos, device):
     return out
 
 
+def reference_opencl_figures(pos, steps=12, warm=4):
+    """The reference's unmodified .cl kernels on this box's OpenCL GPU device (oracle/_ref/libref_ocl.so, NVIDIA's OpenCL
+    driver, the reference's build options): device time of the MODEL kernels per step from OpenCL profiling events. The
+    reference's radix sort is replaced by a host-side stable sort in this runner, so its 2 x 21 sort launches per frame
+    are NOT in the figure: it is a lower bound of the reference's step time on this GPU, reported beside the CPU arm."""
+    import numpy as np
+    from oracle import ocl_py
+    if not ocl_py.available():
+        raise RuntimeError("oracle/_ref/libref_ocl.so not built")
+    r = ocl_py.OclFluids(N130K, N130K, jacobi=JACOBI)
+    r.upload("p_pos", pos)
+    r.upload("p_vel", np.zeros((N130K, 4), np.float32))
+    r.reset_ids()
+    for _ in range(warm):
+        r.step()
+    r.kernel_times(reset=True)
+    for _ in range(steps):
+        r.step()
+    t = r.kernel_times()
+    per_step_us = {k: round(v[0] / steps, 2) for k, v in t.items() if v[1]}
+    total = sum(per_step_us.values())
+    out = {"device": r.device, "steps": steps, "kernel_us_per_step": per_step_us, "model_kernels_ms_per_step": round(total * 1e-3, 4),
+           "value": N130K / (total * 1e-6), "unit": "particle-updates/s (model kernels only, sort excluded)",
+           "build_options": "-cl-denorms-are-zero -cl-fast-relaxed-math + the -D constants of Fluids.cpp:104-119"}
+    r.close()
+    return out
+
+
 def time_cpu_world(w, warmup, steps, budget_s):
     from oracle import oracle_py as O
     for _ in range(warmup):
@@ -620,6 +648,10 @@ def run_ours(args):
                 cpu["parity"] = parity_figures(abi, pos0, local_rank)
             except Exception as e:
                 cpu["parity"] = {"error": repr(e)[:200]}
+            try:
+                cpu["reference_opencl_on_this_gpu"] = reference_opencl_figures(pos0)
+            except Exception as e:
+                cpu["reference_opencl_on_this_gpu"] = {"unavailable": repr(e)[:200]}
 
     others = {}
     if not args.no_other_workloads:
