@@ -316,20 +316,31 @@ __global__ void __launch_bounds__(NB_THREADS, NB_MIN_BLOCKS) densityLambdaKernel
       });
 }
 
-// The same sweep as the list BUILD of a step (first Jacobi iteration): block-cooperative, candidates from shared-memory
-// tiles staged by TMA (tilebuild.cuh)
+// The list BUILD of a step (first Jacobi iteration) runs as two kernels (tilebuild.cuh): the block-cooperative filter
+// (CTA tiles staged by TMA, candidates within the list radius -> margin mask) and the same sweep as above walking that mask.
+template <int TRAV>
+__global__ void __launch_bounds__(NB_THREADS, NB_MIN_BLOCKS) marginMaskKernel(DeviceState s, GridParams g, SphConsts c, const float4* __restrict__ P)
+{
+  RTP_PDL_PROLOGUE();
+  __shared__ TileSmem sm;
+  const u32 i = blockIdx.x * NB_THREADS + threadIdx.x;
+  const bool active = i < s.N && !isGhostRow(s, i);
+  const float4 pi = active ? P[i] : make_float4(0.f, 0.f, 0.f, 0.f);
+  tileFilterToMask<TRAV>(sm, g, c.nbrRadiusSq, s.table, P, pi, active, s.marginMask, s.buildStats);
+}
+
 template <int TRAV>
 __global__ void __launch_bounds__(NB_THREADS, NB_MIN_BLOCKS) densityLambdaBuildKernel(DeviceState s, GridParams g, SphConsts c, float rho0, float cfm,
     const float4* __restrict__ pred, int epoch)
 {
   RTP_PDL_PROLOGUE();
-  __shared__ TileSmem sm;
+  __shared__ MaskWalkSmem sm;
   const u32 i = blockIdx.x * NB_THREADS + threadIdx.x;
   recordGhostBuildPos(s, pred, NBR_BUILD, epoch);
   const bool active = i < s.N && !isGhostRow(s, i);
   const float4 pi = active ? pred[i] : make_float4(0.f, 0.f, 0.f, 0.f);
   float density = 0.f, gx = 0.f, gy = 0.f, gz = 0.f, sumG2 = 0.f;
-  const bool done = sweepProducerBuildTiled<TRAV>(sm, g, c, s, pred, pi, i, active, epoch,
+  const bool done = sweepProducerFromMask<TRAV>(sm, g, c, s, pred, pi, i, active, epoch,
       [&](u32, float dx, float dy, float dz, float sq)
       {
         const float cs = spikyCoefOrZero(c, sq);
@@ -568,18 +579,18 @@ __global__ void __launch_bounds__(NB_THREADS, NB_MIN_BLOCKS) laplacianTempKernel
       });
 }
 
-// the same sweep as the block-cooperative list build of the temperature epoch (tilebuild.cuh)
+// the same sweep as the list build of the temperature epoch: walks the margin mask marginMaskKernel wrote (tilebuild.cuh)
 __global__ void __launch_bounds__(NB_THREADS, NB_MIN_BLOCKS) laplacianTempBuildKernel(DeviceState s, GridParams g, SphConsts c, float rho0)
 {
   RTP_PDL_PROLOGUE();
-  __shared__ TileSmem sm;
+  __shared__ MaskWalkSmem sm;
   const float* __restrict__ T = s.tempB;
   const u32 i = blockIdx.x * NB_THREADS + threadIdx.x;
   const bool active = i < s.N;
   const float4 pi = active ? s.posB[i] : make_float4(0.f, 0.f, 0.f, 0.f);
   const float Ti = active ? T[i] : 0.f;
   float lap = 0.f;
-  const bool done = sweepProducerBuildTiled<TRAV_CLOUDS>(sm, g, c, s, s.posB, pi, i, active, NBR_EPOCH_TEMP,
+  const bool done = sweepProducerFromMask<TRAV_CLOUDS>(sm, g, c, s, s.posB, pi, i, active, NBR_EPOCH_TEMP,
       [&](u32 e, float, float, float, float sq)
       {
         const float cs = spikyCoefOrZero(c, sq);
@@ -648,6 +659,15 @@ void launchFluidPredict(const DeviceState& s, const GridParams& g, const FluidSt
     launchKernel(fluidPredictKernel<false>, blocks, EW_THREADS, st, s, g, p.f.timeStep, keysOut, 0, PassDesc {}, (u32*)nullptr, (u32*)nullptr,
         (size_t)0);
 }
+void launchMarginMask(const DeviceState& s, int model, const GridParams& g, const SphConsts& c, const float4* P, cudaStream_t st)
+{
+  if (!s.N)
+    return;
+  if (model == RTP_MODEL_CLOUDS)
+    launchKernel(marginMaskKernel<TRAV_CLOUDS>, nbBlocks(s.N), NB_THREADS, st, s, g, c, P);
+  else
+    launchKernel(marginMaskKernel<TRAV_FLUIDS>, nbBlocks(s.N), NB_THREADS, st, s, g, c, P);
+}
 void launchFluidGather(const DeviceState& s, const GridParams& g, cudaStream_t st)
 {
   if (s.N)
@@ -661,6 +681,7 @@ void launchDensityLambda(const DeviceState& s, int model, const GridParams& g, c
   static_assert(NB_THREADS == TB_THREADS, "tilebuild.cuh is written for the neighbour kernels' block size");
   if (nbrMode == NBR_BUILD && s.tiledBuild)
   {
+    launchMarginMask(s, model, g, c, pred, st);
     if (model == RTP_MODEL_CLOUDS)
       launchKernel(densityLambdaBuildKernel<TRAV_CLOUDS>, nbBlocks(s.N), NB_THREADS, st, s, g, c, p.f.restDensity, p.f.relaxCFM, pred, epoch);
     else
@@ -751,7 +772,10 @@ void launchCloudsGather(const DeviceState& s, const GridParams& g, cudaStream_t 
 void launchCloudsLaplacianTemp(const DeviceState& s, const GridParams& g, const SphConsts& c, const rtp_cloud_params& cloud, int nbrMode, cudaStream_t st)
 {
   if (s.N && nbrMode == NBR_BUILD && s.tiledBuild)
+  {
+    launchMarginMask(s, RTP_MODEL_CLOUDS, g, c, s.posB, st);
     launchKernel(laplacianTempBuildKernel, nbBlocks(s.N), NB_THREADS, st, s, g, c, cloud.restDensity);
+  }
   else if (s.N)
     launchKernel(laplacianTempKernel, nbBlocks(s.N), NB_THREADS, st, s, g, c, cloud.restDensity, nbrMode);
 }

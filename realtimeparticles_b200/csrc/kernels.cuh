@@ -7,6 +7,15 @@
 
 namespace rtp
 {
+// margin mask of a step (tilebuild.cuh MarginMask): word w of lane l of warp W at words[(W * wordCap + w) * 32 + l]
+struct MarginMaskBuffers
+{
+  u32* words = nullptr;
+  u32* desc = nullptr;
+  u32* warpWords = nullptr;
+  u32 wordCap = 0;
+};
+
 // Buffers of one model instance. "A" buffers hold the canonical state seen by rtp_upload/rtp_download (the
 // reference's named buffers); "B" buffers are the cell-sorted working copies the neighbour kernels read. Every
 // step ends with the state back in the A buffers, so one captured CUDA graph replays for every step.
@@ -39,7 +48,8 @@ struct DeviceState
   u32 *stragQueue = nullptr, *stragCount = nullptr, *stragCursor = nullptr; // straggler queue of the producer sweeps (sweep.cuh), counters per epoch
   u32 hitCap = 0;
   int tiledBuild = 0; // the list build of a step runs block-cooperatively (tilebuild.cuh)
-  u32* buildStats = nullptr; // tilebuild.cuh counters: { warps on the per-thread build, -, CTAs over the tile capacity }
+  MarginMaskBuffers marginMask; // the margin mask of the step (tilebuild.cuh), written by the filter kernel, read by the build sweep
+  u32* buildStats = nullptr; // tilebuild.cuh counters: { irregular warps, warps over the word capacity, CTAs over the tile capacity }
 };
 
 // how a neighbour sweep treats the per-step neighbour lists
@@ -96,6 +106,8 @@ struct SortPlan;
 // fusedSort != nullptr: the kernel also builds that sort's histograms (sort.cuh enqueueSortBegin / enqueueSortPasses around it)
 void launchFluidPredict(const DeviceState& s, const GridParams& g, const FluidStepParams& p, u32* keysOut, const SortPlan* fusedSort,
     u32* sortCtrl, u32* sortStatus, cudaStream_t st);
+// the block-cooperative filter of a list build: writes the margin mask of positions P (tilebuild.cuh)
+void launchMarginMask(const DeviceState& s, int model, const GridParams& g, const SphConsts& c, const float4* P, cudaStream_t st);
 void launchFluidGather(const DeviceState& s, const GridParams& g, cudaStream_t st);
 void launchDensityLambda(const DeviceState& s, int model, const GridParams& g, const SphConsts& c, const FluidStepParams& p,
     const float4* pred, int nbrMode, int epoch, cudaStream_t st);

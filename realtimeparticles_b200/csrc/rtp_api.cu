@@ -361,6 +361,18 @@ extern "C" int rtp_create(const rtp_config* cfg, rtp_handle** out)
       s.tiledBuild = (M <= (1u << 27) && cfg->grid[0] >= 4 && cfg->grid[1] >= 4 && cfg->grid[2] >= 4) ? 1 : 0;
       if (const char* e = getenv("RTP_TILED_BUILD"))
         s.tiledBuild = s.tiledBuild && atoi(e) != 0;
+      if (s.tiledBuild)
+      {
+        // margin mask of the step: ~30 words per warp-lane; a warp that straddles two dense columns needs more
+        u32 wcap = 96;
+        if (const char* e = getenv("RTP_MASK_WORDS"))
+          wcap = (u32)atoi(e) < 1 ? 1u : (u32)atoi(e);
+        const size_t warps = ((M + 127) / 128) * 4;
+        s.marginMask.wordCap = wcap;
+        LIST_TRY(devAlloc(h, &s.marginMask.words, warps * wcap * 32));
+        LIST_TRY(devAlloc(h, &s.marginMask.desc, warps * wcap));
+        LIST_TRY(devAlloc(h, &s.marginMask.warpWords, warps));
+      }
       if (getenv("RTP_TEST_FAIL_LIST_ALLOC")) // (tests: exercise the out-of-memory path)
         listsOk = false;
       if (!listsOk)
@@ -371,6 +383,7 @@ extern "C" int rtp_create(const rtp_config* cfg, rtp_handle** out)
         s.nbrList = s.nbrCount = s.nbrInvalid = s.hitList = s.hitCount = s.stragQueue = s.stragCount = s.stragCursor = s.buildStats = nullptr;
         s.nbrBuildPos = nullptr;
         s.tiledBuild = 0;
+        s.marginMask = MarginMaskBuffers {};
         h->nbrEnabled = false;
       }
     }

@@ -19,9 +19,13 @@
 //   bit of a 32-candidate mask word. No divergence, no per-lane addresses. Candidates of the window outside the lane's
 //   own run (another lane's cell) are removed per word with a range mask, so a lane keeps exactly the reference's
 //   candidate set; words no lane needs (a hole between two families of runs) are skipped.
-//  WALK. After each stage every lane walks the set bits of its buffered words in order (= the reference's order: slots
-//   ascending, index ascending) and hands each candidate (entry, position from the tile) to the caller, which appends it
-//   to the margin list, applies the exact support test and runs the sweep's pair term (sweep.cuh).
+//  MASKS. The words go straight to global memory (one coalesced 128-byte row per word and warp) as the MARGIN MASK of the
+//   step: per warp up to wordCap words per lane plus, per word, the global index of its bit 0 and its slot. A second,
+//   per-thread kernel (sweep.cuh sweepProducerFromMask) walks the set bits of a particle's words in order (= the
+//   reference's order: slots ascending, index ascending), appends the candidates to the margin list, applies the exact
+//   support test and runs the sweep's pair term. (One fused kernel had to walk after every stage, while the stage's tile
+//   was still in shared memory: three short walks per particle, each paced by its slowest lane -- 16 of 32 lanes busy.
+//   The split walk covers a whole particle at once and needs no tile.)
 //  FALLBACK. A warp whose lanes cannot be described this way (a cap or start = 1 quirk breaks a run, more than NGROUP
 //   columns in one warp, windows larger than the tile) builds its lists with the per-thread 27-cell traversal. Both
 //   paths emit the same candidates in the same order.
@@ -35,7 +39,6 @@ constexpr int TB_THREADS = 128; // == the neighbour kernels' block size
 constexpr int TB_WARPS = TB_THREADS / 32;
 constexpr u32 TILE_STAGE_CAP = 1088; // positions one stage may hold: 128 + 2 x 101 (cell cap) per column, x 3
 constexpr u32 TILE_PAD = 32; // the filter reads whole 32-candidate words: over-read room behind the last window
-constexpr int WORD_BUF = 12; // mask words a warp buffers between two walks
 constexpr int NSLOT = 27;
 constexpr int NGROUP = 4; // lane groups of a warp (lanes with the same centre column)
 constexpr int SEG_MAX = TB_WARPS * NGROUP + 4; // staged index segments of one column
@@ -46,9 +49,6 @@ constexpr u32 TB_INDEX_MASK = (1u << TB_INDEX_BITS) - 1u;
 struct __align__(16) TileSmem
 {
   float4 tile[TILE_STAGE_CAP + TILE_PAD];
-  u32 words[TB_WARPS][WORD_BUF][32];
-  u32 wordDesc[TB_WARPS][WORD_BUF]; // global index of bit 0 | slot << 27
-  u32 wordTile[TB_WARPS][WORD_BUF]; // tile index of bit 0
   // per warp and neighbour column: its non-empty windows in slot order: (first index, last index, slot | group << 8, -)
   uint4 winList[TB_WARPS][9][WIN_MAX];
   u32 winCount[TB_WARPS][9];
@@ -216,14 +216,18 @@ __device__ __forceinline__ void tmaLoad1D(void* dstSmem, const void* srcGlobal, 
 
 // ---------------------------------------------------------------- the builder
 
-// Stream, in the reference's order, every candidate of particle i (position pi) that is closer than sqrt(radiusSq) to
-// it: onCandidate(entry, pj) with entry = index | image code (sweep.cuh) and pj = the candidate's position. Every thread
-// of the CTA must call (inactive threads: active = false). Returns false -- before any candidate has been handed out --
-// when this warp has to build with the per-thread traversal instead. stats: optional counters { irregular warps, -,
-// CTAs over the tile capacity }.
-template <int TRAV, typename CandF>
-__device__ __forceinline__ bool tileBuildCandidates(TileSmem& sm, const GridParams& g, const float radiusSq, const uint2* __restrict__ table,
-    const float4* __restrict__ P, const float4 pi, const bool active, u32* __restrict__ stats, CandF&& onCandidate)
+// The margin mask of one step / position epoch (see MASKS above): word w of lane l of warp W at
+// words[(W * wordCap + w) * 32 + l], its descriptor (global index of bit 0 | slot << 27) at desc[W * wordCap + w];
+// warpWords[W] = number of words, or MASK_FALLBACK: that warp builds with the per-thread traversal.
+constexpr u32 MASK_FALLBACK = 0xFFFFFFFFu;
+typedef MarginMaskBuffers MarginMask; // kernels.cuh
+
+// Filter the candidates of the CTA's 128 particles (positions P, particle of this thread: pi) against sqrt(radiusSq) and
+// write the margin mask. Every thread of the CTA must call (inactive threads: active = false). stats: optional counters
+// { irregular warps, warps over the word capacity, CTAs over the tile capacity }.
+template <int TRAV>
+__device__ __forceinline__ void tileFilterToMask(TileSmem& sm, const GridParams& g, const float radiusSq, const uint2* __restrict__ table,
+    const float4* __restrict__ P, const float4 pi, const bool active, const MarginMask& mm, u32* __restrict__ stats)
 {
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int3 ci = cell3D(g, pi.x, pi.y, pi.z);
@@ -388,8 +392,13 @@ __device__ __forceinline__ bool tileBuildCandidates(TileSmem& sm, const GridPara
   const bool useTiles = sm.overflow == 0u;
   if (!useTiles && tid == 0 && stats)
     atomicAdd(stats + 2, 1u);
+  const u32 gwarp = blockIdx.x * TB_WARPS + warp;
   if (!useTiles)
-    return false; // (uniform for the CTA: nobody is left behind at a barrier)
+  {
+    if (lane == 0)
+      mm.warpWords[gwarp] = MASK_FALLBACK;
+    return; // (uniform for the CTA: nobody is left behind at a barrier)
+  }
 
   // one thread: one bulk copy per staged segment of the stage's columns behind one mbarrier phase; false: nothing to stage
   auto issueStage = [&](u32 stage) -> bool
@@ -419,44 +428,8 @@ __device__ __forceinline__ bool tileBuildCandidates(TileSmem& sm, const GridPara
   //  list radius has 12 % of slack and the caller applies the exact support test)
   const float filterSq = radiusSq;
 
-  // hand the candidates of the buffered words to the caller: per lane, set bits in word order
-  auto flush = [&](u32& used, const float4* tileBuf)
-  {
-    __syncwarp();
-    u32 nz = 0u;
-    for (u32 w = 0; w < used; ++w)
-      nz |= (sm.words[warp][w][lane] != 0u ? 1u : 0u) << w;
-    // one candidate per lane and iteration; moving on to the lane's next non-empty word is a find-first-set on nz (lanes
-    // reach the end of a word at different iterations: a per-word loop would run with a handful of lanes)
-    u32 m = 0u, base = 0u, tb = 0u;
-    for (;;)
-    {
-      if (m == 0u)
-      {
-        if (nz == 0u)
-          break;
-        const u32 j = __ffs(nz) - 1u;
-        nz &= nz - 1u;
-        m = sm.words[warp][j][lane];
-        const u32 desc = sm.wordDesc[warp][j];
-        tb = sm.wordTile[warp][j];
-        u32 code = 0u;
-        if (TRAV == TRAV_CLOUDS)
-        {
-          const u32 slot = desc >> TB_INDEX_BITS;
-          const u32 col = slot / 3u, kind = slot - col * 3u, ix = col / 3u;
-          code = imageCode(ix == 0u ? sh.sx[0] : (ix == 1u ? sh.sx[1] : sh.sx[2]), kind == 0u ? sh.sz[0] : (kind == 1u ? sh.sz[1] : sh.sz[2]));
-        }
-        base = (desc & TB_INDEX_MASK) | code;
-      }
-      const u32 b = __ffs(m) - 1u;
-      m &= m - 1u;
-      onCandidate(base + b, tileBuf[tb + b]);
-    }
-    used = 0u;
-    __syncwarp();
-  };
-
+  u32 wordsOut = 0u;
+  const size_t wordBase = (size_t)gwarp * mm.wordCap;
   {
     u32 phase = 0u;
     const u32 nStages = sm.nStages;
@@ -474,7 +447,6 @@ __device__ __forceinline__ bool tileBuildCandidates(TileSmem& sm, const GridPara
       if (!warpRegular)
         continue;
       const float4* tileBuf = sm.tile;
-      u32 used = 0u;
 #pragma unroll 1
       for (int col = (int)sm.stageFirst[stage]; col < (int)sm.stageFirst[stage + 1]; ++col)
       {
@@ -510,8 +482,6 @@ __device__ __forceinline__ bool tileBuildCandidates(TileSmem& sm, const GridPara
             }
             if (!__any_sync(0xFFFFFFFFu, rm != 0u))
               continue; // nobody's run reaches into this word (a hole between two families of runs)
-            if (used == (u32)WORD_BUF)
-              flush(used, tileBuf);
             const float4* __restrict__ tp = tileBuf + tileBase + 32u * w;
             u32 m = 0u;
 #pragma unroll
@@ -523,20 +493,25 @@ __device__ __forceinline__ bool tileBuildCandidates(TileSmem& sm, const GridPara
               if (sq < filterSq)
                 m |= 1u << k;
             }
-            sm.words[warp][used][lane] = m & rm;
-            if (lane == 0)
+            if (wordsOut < mm.wordCap)
             {
-              sm.wordDesc[warp][used] = B | ((u32)slot << TB_INDEX_BITS);
-              sm.wordTile[warp][used] = tileBase + 32u * w;
+              mm.words[(wordBase + wordsOut) * 32u + lane] = m & rm;
+              if (lane == 0)
+                mm.desc[wordBase + wordsOut] = B | ((u32)slot << TB_INDEX_BITS);
             }
-            ++used;
+            ++wordsOut;
           }
         }
       }
-      flush(used, tileBuf);
     }
   }
-  return warpRegular;
+  const bool fits = wordsOut <= mm.wordCap;
+  if (lane == 0)
+  {
+    mm.warpWords[gwarp] = (warpRegular && fits) ? wordsOut : MASK_FALLBACK;
+    if (warpRegular && !fits && stats)
+      atomicAdd(stats + 1, 1u);
+  }
 }
 
 } // namespace rtp
