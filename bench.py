@@ -365,10 +365,11 @@ def run_slab_16m(args, torch, abi, rank, local_rank, world, steps=10, warmup=8):
     # fixed capacities per slab face: a ghost region of 2 x-layers (120 x 120 cells each, 4.9 particles per cell in the
     # initial lattice; room for 10) and a migration message
     ghost_cap = sharded.GHOST_LAYERS * 120 * 120 * 10 if world > 1 else 0
-    capacity = int(n_own * 1.15) + 2 * ghost_cap
+    migrate_cap = (1 << 16) if world > 1 else 1
+    capacity = int(n_own * 1.10) + 2 * migrate_cap + 2 * ghost_cap
     dev = torch.device("cuda", local_rank)
     eng = sharded.CudaSlabEngine(capacity, box, grid, local_rank, jacobi=JACOBI)
-    sd = sharded.SlabDecomposition(eng, grid, rank, world, ghost_cap=ghost_cap, migrate_cap=1 << 16)
+    sd = sharded.SlabDecomposition(eng, grid, rank, world, ghost_cap=ghost_cap, migrate_cap=migrate_cap)
     sd.load_owned(torch.from_numpy(pos).to(dev), torch.zeros((n_own, 4), device=dev))
     sd.warm_up_code_paths()
     for _ in range(warmup):
@@ -410,9 +411,16 @@ def run_slab_16m(args, torch, abi, rank, local_rank, world, steps=10, warmup=8):
     per_step = [a.elapsed_time(b) for a, b in zip([e0] + marks[:-1], marks)]
     # aggregate invariants of the state after the timed window (north_star: mean PBF density error and kinetic energy must
     # agree between decompositions within 1 %): sums over the OWNED particles of every rank
+    sd.check()  # static layout: device-side capacity flags + the current particle count (a host synchronisation, untimed)
     with eng.stream_context():
-        n_loc = sd.n_owned + sd.ghost_rows
-        own = eng.field("RadixSortIndices", u32=True)[:n_loc] < sd.n_owned  # rows of the last sort that are not ghosts
+        if sd.static:
+            # own region [0, S) at the last sort: rows that held a particle (the sort's permutation maps sorted row -> row)
+            n_loc = sd.S + 2 * sd.ghost_cap
+            perm = eng.field("RadixSortIndices", u32=True)[:n_loc].to(torch.int64)
+            own = (perm < sd.S) & torch.isfinite(eng.buf("PRED_CUR")[:n_loc, 0])
+        else:
+            n_loc = sd.n_owned + sd.ghost_rows
+            own = eng.field("RadixSortIndices", u32=True)[:n_loc] < sd.n_owned  # rows of the last sort that are not ghosts
         dens = eng.field("p_density")[:n_loc][own].double()
         v = eng.vel()[:sd.n_owned, :3].double()
         inv = torch.stack([(dens / 450.0 - 1.0).abs().sum(), 0.5 * (v * v).sum(), torch.tensor(float(sd.n_owned), dtype=torch.float64, device=dev)])

@@ -304,11 +304,14 @@ RTP_API int rtp_shard_buffer(rtp_handle* h, int which, void** dptr, size_t* byte
  * caller). All pointers are DEVICE pointers, everything is enqueued on the handle's stream, nothing synchronises.
  *  pack:   d_out[k] = buffer[d_idx[k]], k < n; an index 0xFFFFFFFF ("no particle": fixed-capacity exchanges are padded)
  *          packs a +inf position (f4 rows) or 0 (scalar rows);  unpack: buffer[d_idx[k]] = d_in[k], padding skipped.
+ *  clear_rows: p_pos[d_idx[k]] = +inf, p_vel[d_idx[k]] = 0: the row holds no particle any more (it migrated); such rows sort
+ *          behind every particle, appear in no cell range and are skipped by the sweeps of a sharded handle.
  *  inverse_perm: d_inv[perm[i]] = i for the nb_particles cell-sorted rows (where did unsorted row j go).
  *  check_ghosts: raise the "lists invalid" flag of next_epoch when a ghost row (sorted indices d_sorted_idx) has been moved
  *          further than the list validity bound from its position at the list build (its owner moves it, not this rank). */
 RTP_API int rtp_shard_pack(rtp_handle* h, int buffer, const uint32_t* d_idx, uint64_t n, void* d_out);
 RTP_API int rtp_shard_unpack(rtp_handle* h, int buffer, const uint32_t* d_idx, uint64_t n, const void* d_in);
+RTP_API int rtp_shard_clear_rows(rtp_handle* h, const uint32_t* d_idx, uint64_t n);
 RTP_API int rtp_shard_inverse_perm(rtp_handle* h, uint32_t* d_inv);
 RTP_API int rtp_shard_check_ghosts(rtp_handle* h, const uint32_t* d_sorted_idx, uint64_t n, int next_epoch);
 /* neighbour-list validity: radius^2 a particle may move from its list-build position (see sweep.cuh) */

@@ -80,7 +80,7 @@ EXPORTS = ["rtp_abi_version", "rtp_device_count", "rtp_create", "rtp_destroy", "
            "rtp_set_cloud_params", "rtp_set_boundary", "rtp_set_nb_particles", "rtp_set_dimension",
            "rtp_set_displayed_quantity", "rtp_reset_ids", "rtp_init_clouds_fields", "rtp_step", "rtp_step_n",
            "rtp_sync", "rtp_get_stream", "rtp_sort_keys", "rtp_sort_keys_host", "rtp_selftest_math", "rtp_enable_profiling", "rtp_get_stage_times",
-           "rtp_last_launch_count", "rtp_list_stats", "rtp_shard_set_owned", "rtp_shard_stage", "rtp_shard_buffer", "rtp_shard_list_dmax_sq", "rtp_shard_pack", "rtp_shard_unpack", "rtp_shard_inverse_perm", "rtp_shard_check_ghosts",
+           "rtp_last_launch_count", "rtp_list_stats", "rtp_shard_set_owned", "rtp_shard_stage", "rtp_shard_buffer", "rtp_shard_list_dmax_sq", "rtp_shard_pack", "rtp_shard_unpack", "rtp_shard_clear_rows", "rtp_shard_inverse_perm", "rtp_shard_check_ghosts",
            "rtp_gen_box_grid", "rtp_gen_sphere_grid", "rtp_gen_rectangle_grid", "rtp_gen_circle_grid", "rtp_gen_random_box",
            "rtp_baked_constant", "rtp_register_gl", "rtp_unregister_gl", "rtp_target_create", "rtp_target_destroy", "rtp_target_update"]
 
@@ -131,6 +131,7 @@ def lib():
     L.rtp_shard_buffer.argtypes = [vp, C.c_int, C.POINTER(vp), C.POINTER(C.c_size_t)]
     L.rtp_shard_pack.argtypes = [vp, C.c_int, C.c_void_p, C.c_uint64, C.c_void_p]
     L.rtp_shard_unpack.argtypes = [vp, C.c_int, C.c_void_p, C.c_uint64, C.c_void_p]
+    L.rtp_shard_clear_rows.argtypes = [vp, C.c_void_p, C.c_uint64]
     L.rtp_shard_inverse_perm.argtypes = [vp, C.c_void_p]
     L.rtp_shard_check_ghosts.argtypes = [vp, C.c_void_p, C.c_uint64, C.c_int]
     L.rtp_shard_list_dmax_sq.argtypes = [vp]
@@ -310,6 +311,9 @@ class Handle:
 
     def shard_unpack(self, which, idx_ptr, n, in_ptr):
         self._check(self.L.rtp_shard_unpack(self.h, int(which), idx_ptr, int(n), in_ptr), "rtp_shard_unpack")
+
+    def shard_clear_rows(self, idx_ptr, n):
+        self._check(self.L.rtp_shard_clear_rows(self.h, idx_ptr, int(n)), "rtp_shard_clear_rows")
 
     def shard_inverse_perm(self, out_ptr):
         self._check(self.L.rtp_shard_inverse_perm(self.h, out_ptr), "rtp_shard_inverse_perm")

@@ -20,6 +20,8 @@
 // Numerics: bit-exact with the oracle everywhere. Hit tests, element-wise stages and the per-pair terms use the
 // canonical operation sequence (rtp_common.cuh, DESIGN.md "Canonical arithmetic"); sums run in the reference's
 // order (27 cells, ascending e, one fp32 accumulator per component).
+#include <math.h>
+
 #include <algorithm>
 #include <cstdlib>
 
@@ -119,7 +121,9 @@ __global__ void __launch_bounds__(EW_THREADS) fluidGatherKernel(DeviceState s, G
   const u32 j = s.perm[i];
   s.posB[i] = s.posA[j];
   s.velB[i] = s.velA[j];
-  s.pred1[i] = fluidBoundary(g, s.pred0[j]);
+  const float4 pr = s.pred0[j];
+  // (slab decomposition: a "no particle" row keeps its +inf position instead of being clamped into the box)
+  s.pred1[i] = (s.nOwned != 0xFFFFFFFFu && !isfinite(pr.x)) ? pr : fluidBoundary(g, pr);
   fillCellTable(s.cellID, i, s.N, g.numCells, s.table);
 }
 
@@ -285,7 +289,7 @@ __global__ void __launch_bounds__(NB_THREADS, NB_MIN_BLOCKS) densityLambdaKernel
 {
   RTP_PDL_PROLOGUE();
   recordGhostBuildPos(s, pred, nbrMode, epoch);
-  producerLoop(s, nbrMode, epoch,
+  producerLoop(s, pred, nbrMode, epoch,
       [&](const u32 i, const bool strag) -> int
       {
         const float4 pi = pred[i];
@@ -324,7 +328,7 @@ __global__ void __launch_bounds__(NB_THREADS, NB_MIN_BLOCKS) marginMaskKernel(De
   RTP_PDL_PROLOGUE();
   __shared__ TileSmem sm;
   const u32 i = blockIdx.x * NB_THREADS + threadIdx.x;
-  const bool active = i < s.N && !isGhostRow(s, i);
+  const bool active = i < s.N && !isPassiveRow(s, i, P[i]);
   const float4 pi = active ? P[i] : make_float4(0.f, 0.f, 0.f, 0.f);
   tileFilterToMask<TRAV>(sm, g, c.nbrRadiusSq, s.table, P, pi, active, s.marginMask, s.buildStats);
 }
@@ -337,7 +341,7 @@ __global__ void __launch_bounds__(NB_THREADS, NB_MIN_BLOCKS) densityLambdaBuildK
   __shared__ MaskWalkSmem sm;
   const u32 i = blockIdx.x * NB_THREADS + threadIdx.x;
   recordGhostBuildPos(s, pred, NBR_BUILD, epoch);
-  const bool active = i < s.N && !isGhostRow(s, i);
+  const bool active = i < s.N && !isPassiveRow(s, i, pred[i]);
   const float4 pi = active ? pred[i] : make_float4(0.f, 0.f, 0.f, 0.f);
   float density = 0.f, gx = 0.f, gy = 0.f, gz = 0.f, sumG2 = 0.f;
   const bool done = sweepProducerFromMask<TRAV>(sm, g, c, s, pred, pi, i, active, epoch,
@@ -371,9 +375,20 @@ __global__ void __launch_bounds__(NB_THREADS, NB_MIN_BLOCKS) correctionKernel(De
 {
   RTP_PDL_PROLOGUE();
   const u32 i = blockIdx.x * NB_THREADS + threadIdx.x;
-  if (i >= s.N || isGhostRow(s, i))
+  if (i >= s.N)
     return;
   const float4 pi = pred[i];
+  if (isPassiveRow(s, i, pi))
+  {
+    // slab decomposition: ghost rows get the owner's value from the caller; "no particle" rows stay what they are
+    predOut[i] = pi;
+    if (LAST && !fp.f.isVorticityConfEnabled)
+    {
+      s.posA[i] = make_float4(INFINITY, INFINITY, INFINITY, 0.0f);
+      s.velA[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+    return;
+  }
   const float* __restrict__ lambda = s.lambda;
   const float li = lambda[i];
   const bool art = ART == 0 ? fp.f.isArtPressureEnabled != 0 : ART > 0;
@@ -463,7 +478,7 @@ __global__ void __launch_bounds__(NB_THREADS, NB_MIN_BLOCKS) vorticityKernel(Dev
   RTP_PDL_PROLOGUE();
   const float4* __restrict__ V = s.velB;
   recordGhostBuildPos(s, pred, nbrMode, epoch);
-  producerLoop(s, nbrMode, epoch,
+  producerLoop(s, pred, nbrMode, epoch,
       [&](const u32 i, const bool strag) -> int
       {
         const float4 pi = pred[i];
@@ -498,9 +513,11 @@ __global__ void __launch_bounds__(NB_THREADS, NB_MIN_BLOCKS) confinementKernel(D
 {
   RTP_PDL_PROLOGUE();
   const u32 i = blockIdx.x * NB_THREADS + threadIdx.x;
-  if (i >= s.N || isGhostRow(s, i))
+  if (i >= s.N)
     return;
   const float4 pi = pred[i];
+  if (isPassiveRow(s, i, pi))
+    return;
   const float* __restrict__ wn = s.vortNorm;
   float nx = 0.f, ny = 0.f, nz = 0.f;
   sweepConsumer<TRAV>(g, c, s, pred, pi, i, nbrMode, epoch,
@@ -533,9 +550,16 @@ __global__ void __launch_bounds__(NB_THREADS, NB_MIN_BLOCKS) xsphKernel(DeviceSt
 {
   RTP_PDL_PROLOGUE();
   const u32 i = blockIdx.x * NB_THREADS + threadIdx.x;
-  if (i >= s.N || isGhostRow(s, i))
+  if (i >= s.N)
     return;
   const float4 pi = pred[i];
+  if (isPassiveRow(s, i, pi))
+  {
+    // slab decomposition: the step leaves ghost and "no particle" rows marked (the caller compacts the particles to the front)
+    s.posA[i] = make_float4(INFINITY, INFINITY, INFINITY, 0.0f);
+    s.velA[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    return;
+  }
   const float4* __restrict__ V = s.velC;
   const float4 vi = V[i];
   float sx = 0.f, sy = 0.f, sz = 0.f;
@@ -558,7 +582,7 @@ __global__ void __launch_bounds__(NB_THREADS, NB_MIN_BLOCKS) laplacianTempKernel
 {
   RTP_PDL_PROLOGUE();
   const float* __restrict__ T = s.tempB;
-  producerLoop(s, nbrMode, NBR_EPOCH_TEMP,
+  producerLoop(s, s.posB, nbrMode, NBR_EPOCH_TEMP,
       [&](const u32 i, const bool strag) -> int
       {
         const float4 pi = s.posB[i];

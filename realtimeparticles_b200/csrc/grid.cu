@@ -172,12 +172,13 @@ void launchSelftestMath(u32 lo, u32 hi, unsigned long long* bad, cudaStream_t st
 
 // slab decomposition: drop the ghost copies after a step. Keys = "is ghost" (1 bit) -> one stable radix pass gives the
 // owned particles first, in their cell-sorted order; then the state is gathered through that permutation.
-__global__ void __launch_bounds__(EW_THREADS) ghostFlagKernel(const u32* __restrict__ perm, u32 nOwned, u32* __restrict__ keys, u32 N)
+__global__ void __launch_bounds__(EW_THREADS) ghostFlagKernel(const u32* __restrict__ perm, const float4* __restrict__ pos, u32 nOwned,
+    u32* __restrict__ keys, u32 N)
 {
   RTP_PDL_PROLOGUE();
   const u32 i = blockIdx.x * EW_THREADS + threadIdx.x;
   if (i < N)
-    keys[i] = perm[i] >= nOwned ? 1u : 0u;
+    keys[i] = (perm[i] >= nOwned || !isfinite(pos[i].x)) ? 1u : 0u; // (the last sweep left +inf in the rows it skipped)
 }
 __global__ void __launch_bounds__(EW_THREADS) compactGatherKernel(DeviceState s, const u32* __restrict__ order, u32 n)
 {
@@ -192,7 +193,7 @@ __global__ void __launch_bounds__(EW_THREADS) compactGatherKernel(DeviceState s,
 void launchGhostFlags(const DeviceState& s, u32* keysOut, cudaStream_t st)
 {
   if (s.N)
-    launchKernel(ghostFlagKernel, ewBlocks(s.N), EW_THREADS, st, s.perm, s.nOwned, keysOut, s.N);
+    launchKernel(ghostFlagKernel, ewBlocks(s.N), EW_THREADS, st, s.perm, s.posA, s.nOwned, keysOut, s.N);
 }
 void launchCompactGather(const DeviceState& s, const u32* order, u32 n, cudaStream_t st)
 {
@@ -244,6 +245,25 @@ __global__ void __launch_bounds__(EW_THREADS) ghostDisplacementKernel(const floa
   const float dx = p.x - b.x, dy = p.y - b.y, dz = p.z - b.z;
   if (!(dx * dx + dy * dy + dz * dz <= dmaxSq) && isfinite(p.x))
     *invalid = 1u;
+}
+// rows that hold no particle any more (it migrated): +inf position, zero velocity
+__global__ void __launch_bounds__(EW_THREADS) clearRowsKernel(float4* __restrict__ pos, float4* __restrict__ vel, const u32* __restrict__ idx, u32 n)
+{
+  RTP_PDL_PROLOGUE();
+  const u32 k = blockIdx.x * EW_THREADS + threadIdx.x;
+  if (k >= n)
+    return;
+  const u32 j = idx[k];
+  if (j != 0xFFFFFFFFu)
+  {
+    pos[j] = make_float4(INFINITY, INFINITY, INFINITY, 0.0f);
+    vel[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+  }
+}
+void launchClearRows(const DeviceState& s, const u32* idx, u32 n, cudaStream_t st)
+{
+  if (n)
+    launchKernel(clearRowsKernel, ewBlocks(n), EW_THREADS, st, s.posA, s.velA, idx, n);
 }
 void launchPackRows(const void* buf, int rowBytes, const u32* idx, u32 n, void* out, cudaStream_t st)
 {

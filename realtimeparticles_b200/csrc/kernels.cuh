@@ -82,6 +82,7 @@ struct FluidStepParams
 
 // ---- grid.cu
 void launchSelftestMath(u32 lo, u32 hi, unsigned long long* bad, cudaStream_t st);
+void launchClearRows(const DeviceState& s, const u32* idx, u32 n, cudaStream_t st);
 void launchPackRows(const void* buf, int rowBytes, const u32* idx, u32 n, void* out, cudaStream_t st);
 void launchUnpackRows(void* buf, int rowBytes, const u32* idx, u32 n, const void* in, cudaStream_t st);
 void launchInversePerm(const DeviceState& s, u32* inv, cudaStream_t st);

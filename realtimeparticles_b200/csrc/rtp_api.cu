@@ -1268,6 +1268,16 @@ extern "C" int rtp_shard_unpack(rtp_handle* h, int buffer, const uint32_t* d_idx
   return RTP_OK;
 }
 
+extern "C" int rtp_shard_clear_rows(rtp_handle* h, const uint32_t* d_idx, uint64_t n)
+{
+  if (!h || (n && !d_idx) || n > h->s.M)
+    return RTP_ERR_INVALID;
+  CUDA_TRY(h, cudaSetDevice(h->cfg.device));
+  launchClearRows(h->s, d_idx, (u32)n, h->stream);
+  CUDA_TRY(h, cudaGetLastError());
+  return RTP_OK;
+}
+
 extern "C" int rtp_shard_inverse_perm(rtp_handle* h, uint32_t* d_inv)
 {
   if (!h || !d_inv)

@@ -19,13 +19,19 @@ Ghost rows are never computed locally: the sweeps skip them (csrc/sweep.cuh isGh
 owner's values before anybody reads them. Results equal the single-GPU run up to the order of particles inside a cell
 (migrated particles are appended), i.e. up to fp32 summation order; cell ids and the cell table are identical.
 
-What keeps the host out of the step:
+What keeps the host out of the step (CUDA engine; `static_layout`):
+  * the row layout of a rank never changes: rows [0, S) are the rank's own region -- its particles, cell-sorted, at the
+    front, "no particle" rows behind them, the last 2 x migrate_cap rows reserved as arrival slots --, followed by one ghost
+    region of ghost_cap rows per slab face. Every launch covers the same rows every step, so NOTHING has to come back to
+    the host inside a step: the Python driver only enqueues, it runs ahead of the GPU, and its cost is hidden. Leavers are
+    marked "no particle" on the device, arrivals land in the arrival slots, the end-of-step compaction moves the particles
+    to the front again. Capacity violations raise a device flag that is read every `check_every` steps.
   * ghost regions and exchange buffers have a FIXED capacity: a halo / refresh message is always `ghost_cap` rows, padded
     with "no particle" rows (+inf positions: their cell key is beyond the grid, so they sort behind every real particle,
     appear in no cell range and are skipped by the sweeps like any ghost). No count has to reach the host before the next
     launch; the counts of a step are checked against the capacity one step later, together with the one read-back below;
-  * the only host synchronisation per step is the read-back of the migration counts (the number of owned particles sizes
-    the launches);
+  * (engines without static_layout -- the oracle in the CPU tests -- read the migration counts back once per step: the
+    number of owned particles sizes their launches);
   * gather / scatter of exchange rows, the inverse permutation and the ghost displacement check are kernels of the
     library behind the C ABI (rtp_shard_pack / unpack / inverse_perm / check_ghosts), on the handle's stream.
 The transport is pluggable: torch.distributed P2P batches (NCCL over NVLink on GPUs, gloo on CPU) when every rank is a
@@ -135,6 +141,12 @@ class CudaSlabEngine:
     def new(self, shape, dtype):
         return torch.empty(shape, dtype=dtype, device=self.device)
 
+    static_layout = True  # the sweeps of a sharded handle skip "no particle" rows (+inf position): see SlabDecomposition
+
+    def clear_rows(self, idx):
+        """the rows idx (int32, -1 = padding) hold no particle any more"""
+        self.h.shard_clear_rows(idx.data_ptr(), idx.numel())
+
     def sync(self):
         self.h.sync()
 
@@ -172,6 +184,9 @@ class SlabDecomposition:
         self.migrate_cap = int(migrate_cap) if migrate_cap is not None else max(self.ghost_cap // 4, 1)
         self.ghost_rows = self.ghost_cap * sides
         self._pending_counts = None  # device tensor with the halo counts of the previous step (checked one step late)
+        self.static = bool(getattr(engine, "static_layout", False)) and sides > 0
+        self.check_every = 16  # static layout: how often the device-side capacity flag is read back
+        self._steps = 0
         e = engine
         if sides:
             f32, i64 = torch.float32, torch.int64
@@ -182,6 +197,16 @@ class SlabDecomposition:
             self._row_s = {w: {s: e.new((self.ghost_cap, w) if w > 1 else (self.ghost_cap,), f32) for s in "lr"} for w in (1, 4)}
             self._row_r = {w: {s: e.new((self.ghost_cap, w) if w > 1 else (self.ghost_cap,), f32) for s in "lr"} for w in (1, 4)}
             self._inv = e.new((e.capacity,), torch.int32)
+            if self.static:
+                # rows [0, S): own region (arrival slots at its end); [S, S + 2 * ghost_cap): ghost regions (left, right)
+                self.S = e.capacity - 2 * self.ghost_cap
+                self.A0 = self.S - 2 * self.migrate_cap
+                if self.A0 <= 0:
+                    raise ValueError("slab capacity too small for the ghost regions and arrival slots")
+                self._err = torch.zeros(1, dtype=torch.int64, device=e.device)
+                self._migrated = torch.zeros(1, dtype=torch.int64, device=e.device)
+                self._inf_rows = torch.zeros((max(self.ghost_cap, self.migrate_cap), 4), device=e.device)
+                self._inf_rows[:, :3] = float("inf")
 
     # ---- initial distribution: every rank is given the full initial state and keeps the particles of its slab
     def slab_of(self, keys):
@@ -191,6 +216,19 @@ class SlabDecomposition:
     def load_owned(self, pos, vel):
         """pos/vel: (n, 4) float32 tensors on the engine's device holding ONLY this rank's particles, any order"""
         n = pos.shape[0]
+        if self.static:
+            if n > self.A0:
+                raise RuntimeError("slab capacity exceeded: %d particles > %d rows before the arrival slots" % (n, self.A0))
+            with self.e.stream_context():
+                p, v = self.e.pos(), self.e.vel()
+                p[:, :3] = float("inf")  # "no particle" everywhere ...
+                p[:, 3] = 0.0
+                v.zero_()
+                p[:n] = pos  # ... except the rank's particles at the front
+                v[:n] = vel
+                self.e.set_counts(self.S, self.S)
+            self.n_owned = n
+            return
         if n + self.ghost_rows > self.e.capacity:
             raise RuntimeError("slab capacity exceeded: %d owned + %d ghost rows > %d" % (n, self.ghost_rows, self.e.capacity))
         with self.e.stream_context():
@@ -249,9 +287,9 @@ class SlabDecomposition:
         autotuned launch or allocator growth lands inside a timed step (the first use of a torch op costs milliseconds;
         the first migrating step of the 16M dam used to be 4 ms slower than its neighbours)."""
         dev = self.e.pos().device
-        rows = 4096 + self.ghost_rows
+        rows = 8192 + self.ghost_rows
         with self.e.stream_context():
-            for k_out, k_in in ((700, 100), (100, 700), (300, 300), (0, 5), (5, 0)):
+            for k_out, k_in in (() if self.static else ((700, 100), (100, 700), (300, 300), (0, 5), (5, 0))):
                 p = torch.zeros((rows, 4), device=dev)
                 v = torch.zeros((rows, 4), device=dev)
                 idx = torch.nonzero_static(torch.arange(4096, device=dev) % 5 == 0, size=1024, fill_value=-1).flatten().to(torch.int32)
@@ -282,7 +320,7 @@ class SlabDecomposition:
         two exchange points runs with the engine's stream current; the generator is never suspended inside that context."""
         e = self.e
         self._marks = []
-        inner = self._step()
+        inner = self._step_static() if self.static else self._step()
         while True:
             with e.stream_context():
                 try:
@@ -427,7 +465,129 @@ class SlabDecomposition:
         self._mark("compact")
         self._mark("end")
 
+    def _step_static(self):
+        """one step on the static row layout (module docstring): no host synchronisation"""
+        e = self.e
+        jacobi = e.jacobi
+        sides = self._sides()
+        S, G, Mc, A0 = self.S, self.ghost_cap, self.migrate_cap, self.A0
+        pos, vel = e.pos(), e.vel()
+        self._mark("begin")
+
+        # 1. predict; particles whose predicted cell left the slab migrate: their row is cleared here, the neighbour gets
+        #    them in its arrival slots
+        e.set_counts(S, S)
+        e.stage("PREDICT")
+        keys = e.keys_in()[:S]
+        layer = self.slab_of(keys)
+        alive = torch.isfinite(pos[:S, 0])
+        self._err += torch.isfinite(pos[A0:S, 0]).any().to(torch.int64)  # the arrival slots must be free
+        for s, _ in sides:
+            idx, cnt = self._compact(alive & ((layer < self.xlo) if s == "l" else (layer >= self.xhi)), Mc)
+            self._cnt_s[s].copy_(cnt.reshape(1))
+            self._migrated += cnt
+            self._err += (cnt > Mc).to(torch.int64) * 2
+            e.pack("POS", idx, self._mig_s[s][0])
+            e.pack("VEL", idx, self._mig_s[s][1])
+            e.clear_rows(idx)
+        yield _Exchange(*[[(self._mig_s[s], self._mig_r[s])] if p is not None else None for s, p in (("l", self.left), ("r", self.right))])
+        for k, s in enumerate("lr"):
+            a = A0 + k * Mc
+            if (self.left if s == "l" else self.right) is not None:
+                pos[a:a + Mc] = self._mig_r[s][0]  # (the message is padded with "no particle" rows)
+                vel[a:a + Mc] = self._mig_r[s][1]
+        e.stage("PREDICT")  # (again: the arrivals need their prediction and cell id; same arithmetic, same bits for the rest)
+        self._mark("predict+migrate")
+
+        # 2. halo of predicted positions into the ghost regions, sort everything by cell
+        layer = self.slab_of(e.keys_in()[:S])
+        alive = torch.isfinite(pos[:S, 0])
+        src, off = {}, {"l": S, "r": S + G}
+        for s, _ in sides:
+            m = alive & ((layer < self.xlo + GHOST_LAYERS) if s == "l" else (layer >= self.xhi - GHOST_LAYERS))
+            src[s], c = self._compact(m, G)
+            self._err += (c > G).to(torch.int64) * 4
+            e.pack("PRED_IN", src[s], self._row_s[4][s])
+        yield _Exchange(*[[(self._row_s[4][s], self._row_r[4][s])] if p is not None else None for s, p in (("l", self.left), ("r", self.right))])
+        pred_in = e.pred_in()
+        for s in "lr":
+            rows = self._row_r[4][s] if (self.left if s == "l" else self.right) is not None else self._inf_rows[:G]
+            pred_in[off[s]:off[s] + G] = rows
+            pos[off[s]:off[s] + G] = rows
+        vel[S:S + 2 * G] = 0.0
+        n_loc = S + 2 * G
+        e.set_counts(S, n_loc)
+        e.stage("GHOST_KEYS")
+        self.stats.update(owned=self.n_owned, ghosts=2 * G)
+        self._mark("halo")
+        e.stage("SORT")
+        self._mark("sort")
+
+        inv = self._inv[:n_loc]
+        e.inverse_perm(inv)
+        send = {s: torch.where(src[s] >= 0, inv[src[s].clamp(min=0).to(torch.int64)], src[s]) for s, _ in sides}
+        recv = {s: inv[off[s]:off[s] + G] for s, _ in sides}
+        ghost_idx = torch.cat([recv[s] for s, _ in sides])
+
+        def refresh(names):
+            for name in names:
+                w = e.row_width(name)
+                for s, _ in sides:
+                    e.pack(name, send[s], self._row_s[w][s])
+                yield _Exchange(*[[(self._row_s[w][s], self._row_r[w][s])] if p is not None else None
+                                  for s, p in (("l", self.left), ("r", self.right))])
+                for s, _ in sides:
+                    e.unpack(name, recv[s], self._row_r[w][s])
+        self._mark("index-maps")
+
+        # 3. the solver stages, each followed by the refresh of what it produced
+        for it in range(jacobi):
+            last = it == jacobi - 1
+            e.stage("DENSITY_LAMBDA", it)
+            self._mark("compute")
+            yield from refresh(e.refresh_buffers("DENSITY_LAMBDA"))
+            self._mark("refresh")
+            e.stage("CORRECTION", it, last)
+            self._mark("compute")
+            yield from refresh(e.refresh_buffers("CORRECTION", last))
+            e.check_ghosts(ghost_idx, it + 1)
+            self._mark("refresh")
+        if e.vorticity:
+            e.stage("VORTICITY", jacobi)
+            self._mark("compute")
+            yield from refresh(e.refresh_buffers("VORTICITY"))
+            self._mark("refresh")
+            e.stage("CONFINEMENT", jacobi)
+            self._mark("compute")
+            yield from refresh(e.refresh_buffers("CONFINEMENT"))
+            self._mark("refresh")
+            e.stage("XSPH", jacobi)
+            self._mark("compute")
+
+        # 4. particles to the front of the own region, in cell-sorted order; everything else is "no particle"
+        e.stage("DROP_GHOSTS")
+        e.set_counts(S, S)
+        self._mark("compact")
+        self._mark("end")
+        self._steps += 1
+        if self._steps % self.check_every == 0:
+            self.check()
+
+    def check(self):
+        """static layout: read the device-side flags back (a host synchronisation); raises if a capacity was exceeded"""
+        if not self.static:
+            return
+        with self.e.stream_context():
+            vals = torch.cat([self._err, self._migrated, torch.isfinite(self.e.pos()[:self.S, 0]).sum().reshape(1)]).cpu().tolist()
+        if vals[0]:
+            raise RuntimeError("slab capacity exceeded on the device (flags %d: 1 = arrival slots in use, 2 = migration message, "
+                               "4 = ghost region)" % vals[0])
+        self.stats["migrated_out_total"] = int(vals[1])
+        self.n_owned = int(vals[2])
+
     def owned_state(self):
+        if self.static:
+            self.check()
         n = self.n_owned
         with self.e.stream_context():
             return self.e.pos()[:n].clone(), self.e.vel()[:n].clone()

@@ -165,7 +165,7 @@ def _gpu_worker(rank, world, port, cfg, out_dir):
     p, v = sd.owned_state()
     eng.sync()
     np.savez(os.path.join(out_dir, "rank%d.npz" % rank), pos=p.cpu().numpy(), vel=v.cpu().numpy(),
-             migrated=sum(h.get("migrated_out", 0) for h in hist), ghosts=hist[-1].get("ghosts", 0))
+             migrated=sd.stats.get("migrated_out_total", sum(h.get("migrated_out", 0) for h in hist)), ghosts=hist[-1].get("ghosts", 0))
     dist.barrier()
     dist.destroy_process_group()
 

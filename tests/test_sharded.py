@@ -97,11 +97,10 @@ def test_slab_decomposition_on_one_device_matches_single_handle(world):
     n = len(pos0)
     grp, sds = _local_group(lambda: __import__("realtimeparticles_b200.sharded", fromlist=["x"]).CudaSlabEngine(n, BOX, GRID, 0, jacobi=jacobi),
                             world, pos0, vel0, lambda a: torch.from_numpy(a).cuda())
-    migrated = 0
     for _ in range(steps):
         grp.step()
-        migrated += sum(sd.stats.get("migrated_out", 0) for sd in sds)
-    parts = [sd.owned_state() for sd in sds]
+    parts = [sd.owned_state() for sd in sds]  # (reads the device-side counters and capacity flags back)
+    migrated = sum(sd.stats.get("migrated_out_total", 0) for sd in sds)
     for sd in sds:
         sd.e.sync()
     pos = np.concatenate([p.cpu().numpy() for p, _ in parts])
