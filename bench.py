@@ -363,9 +363,9 @@ def run_slab_16m(args, torch, abi, rank, local_rank, world, steps=10, warmup=8):
     pos = abi.gen_box_grid((nx, 256, 128), (x0, -20.0, -20.0), (x0 + 80.0 / world, 0.0, 0.0))
     n_own = len(pos)
     # fixed capacities per slab face: a ghost region of 2 x-layers (120 x 120 cells each, 4.9 particles per cell in the
-    # initial lattice; room for 10) and a migration message
-    ghost_cap = sharded.GHOST_LAYERS * 120 * 120 * 10 if world > 1 else 0
-    migrate_cap = (1 << 16) if world > 1 else 1
+    # initial lattice; room for 8) and a migration message
+    ghost_cap = sharded.GHOST_LAYERS * 120 * 120 * 8 if world > 1 else 0
+    migrate_cap = (1 << 15) if world > 1 else 1
     capacity = int(n_own * 1.10) + 2 * migrate_cap + 2 * ghost_cap
     dev = torch.device("cuda", local_rank)
     eng = sharded.CudaSlabEngine(capacity, box, grid, local_rank, jacobi=JACOBI)

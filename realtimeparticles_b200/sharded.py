@@ -196,6 +196,12 @@ class SlabDecomposition:
             self._cnt_r = {s: e.new((1,), i64) for s in "lr"}
             self._row_s = {w: {s: e.new((self.ghost_cap, w) if w > 1 else (self.ghost_cap,), f32) for s in "lr"} for w in (1, 4)}
             self._row_r = {w: {s: e.new((self.ghost_cap, w) if w > 1 else (self.ghost_cap,), f32) for s in "lr"} for w in (1, 4)}
+            # static layout: [field of a refresh][row width] -> (2 faces, ghost_cap rows): both faces in one pack / unpack
+            self._rows2_s = [{w: e.new((2, self.ghost_cap, w) if w > 1 else (2, self.ghost_cap), f32) for w in ws} for ws in ((1, 4), (4,))]
+            self._rows2_r = [{w: e.new((2, self.ghost_cap, w) if w > 1 else (2, self.ghost_cap), f32) for w in ws} for ws in ((1, 4), (4,))]
+            for d in self._rows2_r:
+                for t in d.values():
+                    t.zero_()
             self._inv = e.new((e.capacity,), torch.int32)
             if self.static:
                 # rows [0, S): own region (arrival slots at its end); [S, S + 2 * ghost_cap): ghost regions (left, right)
@@ -529,15 +535,23 @@ class SlabDecomposition:
         recv = {s: inv[off[s]:off[s] + G] for s, _ in sides}
         ghost_idx = torch.cat([recv[s] for s, _ in sides])
 
+        # both faces are packed / unpacked by ONE kernel launch each: index lists and buffers of the two sides are contiguous
+        none = torch.full((G,), -1, dtype=torch.int32, device=inv.device)
+        send_all = torch.cat([send.get("l", none), send.get("r", none)])
+        recv_all = torch.cat([recv.get("l", none), recv.get("r", none)])
+
         def refresh(names):
-            for name in names:
+            # all fields a stage produced travel in ONE exchange (one send + one receive per neighbour)
+            bufs = []
+            for k, name in enumerate(names):
                 w = e.row_width(name)
-                for s, _ in sides:
-                    e.pack(name, send[s], self._row_s[w][s])
-                yield _Exchange(*[[(self._row_s[w][s], self._row_r[w][s])] if p is not None else None
-                                  for s, p in (("l", self.left), ("r", self.right))])
-                for s, _ in sides:
-                    e.unpack(name, recv[s], self._row_r[w][s])
+                sb, rb = self._rows2_s[k][w], self._rows2_r[k][w]
+                e.pack(name, send_all, sb)
+                bufs.append((name, sb, rb))
+            yield _Exchange(*[[(sb[k2], rb[k2]) for _, sb, rb in bufs] if p is not None else None
+                              for k2, p in ((0, self.left), (1, self.right))])
+            for name, sb, rb in bufs:
+                e.unpack(name, recv_all, rb)
         self._mark("index-maps")
 
         # 3. the solver stages, each followed by the refresh of what it produced
