@@ -417,7 +417,8 @@ def run_slab_16m(args, torch, abi, rank, local_rank, world, steps=10, warmup=8):
             # own region [0, S) at the last sort: rows that held a particle (the sort's permutation maps sorted row -> row)
             n_loc = sd.S + 2 * sd.ghost_cap
             perm = eng.field("RadixSortIndices", u32=True)[:n_loc].to(torch.int64)
-            own = (perm < sd.S) & torch.isfinite(eng.buf("PRED_CUR")[:n_loc, 0])
+            keys = eng.field("p_cellID", u32=True)[:n_loc]  # sorted cell ids: "no particle" rows carry an id beyond the grid
+            own = (perm < sd.S) & (keys >= 0) & (keys < sd.grid[0] * sd.grid[1] * sd.grid[2])
         else:
             n_loc = sd.n_owned + sd.ghost_rows
             own = eng.field("RadixSortIndices", u32=True)[:n_loc] < sd.n_owned  # rows of the last sort that are not ghosts
@@ -452,6 +453,7 @@ def run_ours(args):
     torch.cuda.set_device(local_rank)
     if world > 1:
         import torch.distributed as dist
+        os.environ.setdefault("TORCH_NCCL_HIGH_PRIORITY", "1")  # the slab refreshes travel while sweeps fill the SMs
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     dev = torch.device("cuda", local_rank)
 
@@ -710,7 +712,8 @@ def main():
         torch.cuda.set_device(local_rank)
         if world > 1:
             import torch.distributed as dist
-            dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+            os.environ.setdefault("TORCH_NCCL_HIGH_PRIORITY", "1")  # the slab refreshes travel while sweeps fill the SMs
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
         out = run_slab_16m(args, torch, abi, rank, local_rank, world, steps=max(args.steps, 1) if args.steps < 100 else 10)
         if rank == 0:
             print(json.dumps(out), flush=True)

@@ -317,6 +317,31 @@ RTP_API int rtp_shard_check_ghosts(rtp_handle* h, const uint32_t* d_sorted_idx, 
 /* neighbour-list validity: radius^2 a particle may move from its list-build position (see sweep.cuh) */
 RTP_API float rtp_shard_list_dmax_sq(const rtp_handle* h);
 
+/* ---- overlap of a ghost refresh with the sweeps of the interior rows ----
+ * The cells [cell_lo, cell_hi) (x-layers two or more from both faces of the slab) hold the INTERIOR particles: no ghost among
+ * their neighbours, and nobody's ghost. Every RTP_SHARD_SORT finds their (contiguous) range of sorted rows on the device; a
+ * neighbour sweep can then run in two launches -- rtp_shard_stage_rows(..., RTP_ROWS_INTERIOR) first, RTP_ROWS_BOUNDARY
+ * second -- and only the second has to wait for the refresh of the previous stage:
+ *     stage k BOUNDARY | fork, pack, <transport on the exchange stream>, unpack, check_ghosts, done | stage k+1 INTERIOR |
+ *     join | stage k+1 BOUNDARY | ...
+ * Between fork and done, pack / unpack / check_ghosts are enqueued on the exchange stream (a second, high-priority stream
+ * of the handle; the caller runs its transport on it too); join makes the compute stream wait for the last `done`.
+ * A step runs ALL its sweeps by row phase or none (the straggler queues of the sweeps are split by row class).
+ * max_boundary_rows bounds the rows outside the interior (ghost rows + the owned rows of the face layers: the caller's
+ * exchange capacities): it sizes the BOUNDARY launches; "no particle" rows are not visited by launches by row phase. */
+typedef enum rtp_rows_id
+{
+  RTP_ROWS_ALL = 0,
+  RTP_ROWS_BOUNDARY = 1, /* thread blocks holding a row outside the interior range (ghost rows included) */
+  RTP_ROWS_INTERIOR = 2 /* thread blocks entirely inside it */
+} rtp_rows_id;
+RTP_API int rtp_shard_set_interior(rtp_handle* h, uint32_t cell_lo, uint32_t cell_hi, uint64_t max_boundary_rows);
+RTP_API int rtp_shard_stage_rows(rtp_handle* h, int stage, int iter, int last, int rows);
+RTP_API int rtp_shard_exchange_stream(rtp_handle* h, void** stream);
+RTP_API int rtp_shard_exchange_fork(rtp_handle* h);
+RTP_API int rtp_shard_exchange_done(rtp_handle* h);
+RTP_API int rtp_shard_exchange_join(rtp_handle* h);
+
 #ifdef __cplusplus
 }
 #endif

@@ -89,8 +89,8 @@ __global__ void __launch_bounds__(EW_THREADS) fluidPredictKernel(DeviceState s, 
   if (i < NBR_EPOCHS && s.nbrInvalid)
   {
     s.nbrInvalid[i] = 0u;
-    s.stragCount[i] = 0u;
-    s.stragCursor[i] = 0u;
+    s.stragCount[i] = s.stragCount[NBR_EPOCHS + i] = 0u; // (two queue classes, sweep.cuh)
+    s.stragCursor[i] = s.stragCursor[NBR_EPOCHS + i] = 0u;
   }
   const bool valid = i < s.N;
   u32 key = 0u;
@@ -203,8 +203,8 @@ __global__ void __launch_bounds__(EW_THREADS) cloudsThermoPredictKernel(DeviceSt
   if (i < NBR_EPOCHS && s.nbrInvalid)
   {
     s.nbrInvalid[i] = 0u;
-    s.stragCount[i] = 0u;
-    s.stragCursor[i] = 0u;
+    s.stragCount[i] = s.stragCount[NBR_EPOCHS + i] = 0u; // (two queue classes, sweep.cuh)
+    s.stragCursor[i] = s.stragCursor[NBR_EPOCHS + i] = 0u;
   }
   if (i >= s.N)
     return;
@@ -288,8 +288,11 @@ __global__ void __launch_bounds__(NB_THREADS, NB_MIN_BLOCKS) densityLambdaKernel
     const float4* __restrict__ pred, int nbrMode, int epoch)
 {
   RTP_PDL_PROLOGUE();
-  recordGhostBuildPos(s, pred, nbrMode, epoch);
-  producerLoop(s, pred, nbrMode, epoch,
+  const u32 row0 = ctaFirstRow(s);
+  if (row0 == NO_ROWS)
+    return;
+  recordGhostBuildPos(s, row0, pred, nbrMode, epoch);
+  producerLoop(s, row0, pred, nbrMode, epoch,
       [&](const u32 i, const bool strag) -> int
       {
         const float4 pi = pred[i];
@@ -326,8 +329,11 @@ template <int TRAV>
 __global__ void __launch_bounds__(NB_THREADS, NB_MIN_BLOCKS) marginMaskKernel(DeviceState s, GridParams g, SphConsts c, const float4* __restrict__ P)
 {
   RTP_PDL_PROLOGUE();
+  const u32 row0 = ctaFirstRow(s);
+  if (row0 == NO_ROWS)
+    return;
   __shared__ TileSmem sm;
-  const u32 i = blockIdx.x * NB_THREADS + threadIdx.x;
+  const u32 i = row0 + threadIdx.x;
   const bool active = i < s.N && !isPassiveRow(s, i, P[i]);
   const float4 pi = active ? P[i] : make_float4(0.f, 0.f, 0.f, 0.f);
   tileFilterToMask<TRAV>(sm, g, c.nbrRadiusSq, s.table, P, pi, active, s.marginMask, s.buildStats);
@@ -338,9 +344,12 @@ __global__ void __launch_bounds__(NB_THREADS, NB_MIN_BLOCKS) densityLambdaBuildK
     const float4* __restrict__ pred, int epoch)
 {
   RTP_PDL_PROLOGUE();
+  const u32 row0 = ctaFirstRow(s);
+  if (row0 == NO_ROWS)
+    return;
   __shared__ MaskWalkSmem sm;
-  const u32 i = blockIdx.x * NB_THREADS + threadIdx.x;
-  recordGhostBuildPos(s, pred, NBR_BUILD, epoch);
+  const u32 i = row0 + threadIdx.x;
+  recordGhostBuildPos(s, row0, pred, NBR_BUILD, epoch);
   const bool active = i < s.N && !isPassiveRow(s, i, pred[i]);
   const float4 pi = active ? pred[i] : make_float4(0.f, 0.f, 0.f, 0.f);
   float density = 0.f, gx = 0.f, gy = 0.f, gz = 0.f, sumG2 = 0.f;
@@ -374,7 +383,10 @@ __global__ void __launch_bounds__(NB_THREADS, NB_MIN_BLOCKS) correctionKernel(De
     const float4* __restrict__ pred, float4* __restrict__ predOut, int writeCorr, int nbrMode, int epoch)
 {
   RTP_PDL_PROLOGUE();
-  const u32 i = blockIdx.x * NB_THREADS + threadIdx.x;
+  const u32 row0 = ctaFirstRow(s);
+  if (row0 == NO_ROWS)
+    return;
+  const u32 i = row0 + threadIdx.x;
   if (i >= s.N)
     return;
   const float4 pi = pred[i];
@@ -476,9 +488,12 @@ __global__ void __launch_bounds__(NB_THREADS, NB_MIN_BLOCKS) vorticityKernel(Dev
     int nbrMode, int epoch)
 {
   RTP_PDL_PROLOGUE();
+  const u32 row0 = ctaFirstRow(s);
+  if (row0 == NO_ROWS)
+    return;
   const float4* __restrict__ V = s.velB;
-  recordGhostBuildPos(s, pred, nbrMode, epoch);
-  producerLoop(s, pred, nbrMode, epoch,
+  recordGhostBuildPos(s, row0, pred, nbrMode, epoch);
+  producerLoop(s, row0, pred, nbrMode, epoch,
       [&](const u32 i, const bool strag) -> int
       {
         const float4 pi = pred[i];
@@ -512,7 +527,10 @@ __global__ void __launch_bounds__(NB_THREADS, NB_MIN_BLOCKS) confinementKernel(D
     const float4* __restrict__ pred, int nbrMode, int epoch)
 {
   RTP_PDL_PROLOGUE();
-  const u32 i = blockIdx.x * NB_THREADS + threadIdx.x;
+  const u32 row0 = ctaFirstRow(s);
+  if (row0 == NO_ROWS)
+    return;
+  const u32 i = row0 + threadIdx.x;
   if (i >= s.N)
     return;
   const float4 pi = pred[i];
@@ -549,7 +567,10 @@ __global__ void __launch_bounds__(NB_THREADS, NB_MIN_BLOCKS) xsphKernel(DeviceSt
     int nbrMode, int epoch)
 {
   RTP_PDL_PROLOGUE();
-  const u32 i = blockIdx.x * NB_THREADS + threadIdx.x;
+  const u32 row0 = ctaFirstRow(s);
+  if (row0 == NO_ROWS)
+    return;
+  const u32 i = row0 + threadIdx.x;
   if (i >= s.N)
     return;
   const float4 pi = pred[i];
@@ -582,7 +603,7 @@ __global__ void __launch_bounds__(NB_THREADS, NB_MIN_BLOCKS) laplacianTempKernel
 {
   RTP_PDL_PROLOGUE();
   const float* __restrict__ T = s.tempB;
-  producerLoop(s, s.posB, nbrMode, NBR_EPOCH_TEMP,
+  producerLoop(s, blockIdx.x * NB_THREADS, s.posB, nbrMode, NBR_EPOCH_TEMP,
       [&](const u32 i, const bool strag) -> int
       {
         const float4 pi = s.posB[i];
@@ -670,6 +691,8 @@ __global__ void __launch_bounds__(NB_THREADS, NB_MIN_BLOCKS) correctTempKernel(D
 
 static inline int ewBlocks(size_t n) { return (int)((n + EW_THREADS - 1) / EW_THREADS); }
 static inline int nbBlocks(size_t n) { return (int)((n + NB_THREADS - 1) / NB_THREADS); }
+// grid of a PBF neighbour sweep: every row, or the caller's bound for a launch by row phase (kernels.cuh: rowPhase)
+static inline int sweepBlocks(const DeviceState& s) { return s.rowPhase ? (int)s.rowPhaseBlocks : nbBlocks(s.N); }
 
 static_assert(EW_THREADS == SORT_THREADS, "fluidPredictKernel<true> builds the sort histograms with SORT_THREADS threads per block");
 void launchFluidPredict(const DeviceState& s, const GridParams& g, const FluidStepParams& p, u32* keysOut, const SortPlan* fusedSort,
@@ -688,9 +711,9 @@ void launchMarginMask(const DeviceState& s, int model, const GridParams& g, cons
   if (!s.N)
     return;
   if (model == RTP_MODEL_CLOUDS)
-    launchKernel(marginMaskKernel<TRAV_CLOUDS>, nbBlocks(s.N), NB_THREADS, st, s, g, c, P);
+    launchKernel(marginMaskKernel<TRAV_CLOUDS>, sweepBlocks(s), NB_THREADS, st, s, g, c, P);
   else
-    launchKernel(marginMaskKernel<TRAV_FLUIDS>, nbBlocks(s.N), NB_THREADS, st, s, g, c, P);
+    launchKernel(marginMaskKernel<TRAV_FLUIDS>, sweepBlocks(s), NB_THREADS, st, s, g, c, P);
 }
 void launchFluidGather(const DeviceState& s, const GridParams& g, cudaStream_t st)
 {
@@ -702,26 +725,26 @@ void launchDensityLambda(const DeviceState& s, int model, const GridParams& g, c
 {
   if (!s.N)
     return;
-  static_assert(NB_THREADS == TB_THREADS, "tilebuild.cuh is written for the neighbour kernels' block size");
+  static_assert(NB_THREADS == TB_THREADS && NB_THREADS == SWEEP_BLOCK_ROWS, "tilebuild.cuh is written for the neighbour kernels' block size");
   if (nbrMode == NBR_BUILD && s.tiledBuild)
   {
     launchMarginMask(s, model, g, c, pred, st);
     if (model == RTP_MODEL_CLOUDS)
-      launchKernel(densityLambdaBuildKernel<TRAV_CLOUDS>, nbBlocks(s.N), NB_THREADS, st, s, g, c, p.f.restDensity, p.f.relaxCFM, pred, epoch);
+      launchKernel(densityLambdaBuildKernel<TRAV_CLOUDS>, sweepBlocks(s), NB_THREADS, st, s, g, c, p.f.restDensity, p.f.relaxCFM, pred, epoch);
     else
-      launchKernel(densityLambdaBuildKernel<TRAV_FLUIDS>, nbBlocks(s.N), NB_THREADS, st, s, g, c, p.f.restDensity, p.f.relaxCFM, pred, epoch);
+      launchKernel(densityLambdaBuildKernel<TRAV_FLUIDS>, sweepBlocks(s), NB_THREADS, st, s, g, c, p.f.restDensity, p.f.relaxCFM, pred, epoch);
     return;
   }
   if (model == RTP_MODEL_CLOUDS)
-    launchKernel(densityLambdaKernel<TRAV_CLOUDS>, nbBlocks(s.N), NB_THREADS, st, s, g, c, p.f.restDensity, p.f.relaxCFM, pred, nbrMode, epoch);
+    launchKernel(densityLambdaKernel<TRAV_CLOUDS>, sweepBlocks(s), NB_THREADS, st, s, g, c, p.f.restDensity, p.f.relaxCFM, pred, nbrMode, epoch);
   else
-    launchKernel(densityLambdaKernel<TRAV_FLUIDS>, nbBlocks(s.N), NB_THREADS, st, s, g, c, p.f.restDensity, p.f.relaxCFM, pred, nbrMode, epoch);
+    launchKernel(densityLambdaKernel<TRAV_FLUIDS>, sweepBlocks(s), NB_THREADS, st, s, g, c, p.f.restDensity, p.f.relaxCFM, pred, nbrMode, epoch);
 }
 template <int TRAV, bool LAST>
 static void launchCorrectionArt(const DeviceState& s, const GridParams& g, const SphConsts& c, const FluidStepParams& p, const float4* pred,
     float4* predOut, int wc, int nbrMode, int epoch, cudaStream_t st)
 {
-  const int nb = nbBlocks(s.N);
+  const int nb = sweepBlocks(s);
   if (!p.f.isArtPressureEnabled)
     launchKernel(correctionKernel<TRAV, LAST, -1>, nb, NB_THREADS, st, s, g, c, p, pred, predOut, wc, nbrMode, epoch);
   else if (p.f.artPressureExp == 4u)
@@ -756,9 +779,9 @@ void launchVorticity(const DeviceState& s, int model, const GridParams& g, const
   if (!s.N)
     return;
   if (model == RTP_MODEL_CLOUDS)
-    launchKernel(vorticityKernel<TRAV_CLOUDS>, nbBlocks(s.N), NB_THREADS, st, s, g, c, pred, nbrMode, epoch);
+    launchKernel(vorticityKernel<TRAV_CLOUDS>, sweepBlocks(s), NB_THREADS, st, s, g, c, pred, nbrMode, epoch);
   else
-    launchKernel(vorticityKernel<TRAV_FLUIDS>, nbBlocks(s.N), NB_THREADS, st, s, g, c, pred, nbrMode, epoch);
+    launchKernel(vorticityKernel<TRAV_FLUIDS>, sweepBlocks(s), NB_THREADS, st, s, g, c, pred, nbrMode, epoch);
 }
 void launchConfinement(const DeviceState& s, int model, const GridParams& g, const SphConsts& c, const FluidStepParams& p,
     const float4* pred, int nbrMode, int epoch, cudaStream_t st)
@@ -766,9 +789,9 @@ void launchConfinement(const DeviceState& s, int model, const GridParams& g, con
   if (!s.N)
     return;
   if (model == RTP_MODEL_CLOUDS)
-    launchKernel(confinementKernel<TRAV_CLOUDS>, nbBlocks(s.N), NB_THREADS, st, s, g, c, p.f.vorticityConfCoeff, p.f.timeStep, pred, nbrMode, epoch);
+    launchKernel(confinementKernel<TRAV_CLOUDS>, sweepBlocks(s), NB_THREADS, st, s, g, c, p.f.vorticityConfCoeff, p.f.timeStep, pred, nbrMode, epoch);
   else
-    launchKernel(confinementKernel<TRAV_FLUIDS>, nbBlocks(s.N), NB_THREADS, st, s, g, c, p.f.vorticityConfCoeff, p.f.timeStep, pred, nbrMode, epoch);
+    launchKernel(confinementKernel<TRAV_FLUIDS>, sweepBlocks(s), NB_THREADS, st, s, g, c, p.f.vorticityConfCoeff, p.f.timeStep, pred, nbrMode, epoch);
 }
 void launchXsph(const DeviceState& s, int model, const GridParams& g, const SphConsts& c, const FluidStepParams& p,
     const rtp_cloud_params&, const float4* pred, int nbrMode, int epoch, cudaStream_t st)
@@ -776,9 +799,9 @@ void launchXsph(const DeviceState& s, int model, const GridParams& g, const SphC
   if (!s.N)
     return;
   if (model == RTP_MODEL_CLOUDS)
-    launchKernel(xsphKernel<TRAV_CLOUDS>, nbBlocks(s.N), NB_THREADS, st, s, g, c, p.f.xsphViscosityCoeff, pred, nbrMode, epoch);
+    launchKernel(xsphKernel<TRAV_CLOUDS>, sweepBlocks(s), NB_THREADS, st, s, g, c, p.f.xsphViscosityCoeff, pred, nbrMode, epoch);
   else
-    launchKernel(xsphKernel<TRAV_FLUIDS>, nbBlocks(s.N), NB_THREADS, st, s, g, c, p.f.xsphViscosityCoeff, pred, nbrMode, epoch);
+    launchKernel(xsphKernel<TRAV_FLUIDS>, sweepBlocks(s), NB_THREADS, st, s, g, c, p.f.xsphViscosityCoeff, pred, nbrMode, epoch);
 }
 void launchCloudsInitFields(const DeviceState& s, const GridParams& g, const rtp_cloud_params& cloud, cudaStream_t st)
 {

@@ -246,6 +246,46 @@ __global__ void __launch_bounds__(EW_THREADS) ghostDisplacementKernel(const floa
   if (!(dx * dx + dy * dy + dz * dz <= dmaxSq) && isfinite(p.x))
     *invalid = 1u;
 }
+// interior rows of a slab (kernels.cuh: rowPhaseBounds) = the sorted rows of the cells [cellLo, cellHi): bounds[0] = first
+// row, bounds[1] = one past the last one; bounds[2] = one past the last row that holds a particle (any cell). Pre-set to
+// 0xFFFFFFFF / 0 / 0 by the launcher (an empty interior, no particle); runs on the table BEFORE adjustEndCell caps the ends.
+__global__ void __launch_bounds__(EW_THREADS) rowPhaseBoundsKernel(const uint2* __restrict__ table, u32 numCells, u32 cellLo, u32 cellHi,
+    u32* __restrict__ bounds)
+{
+  RTP_PDL_PROLOGUE();
+  const u32 c = blockIdx.x * EW_THREADS + threadIdx.x;
+  u32 lo = 0xFFFFFFFFu, hi = 0u, last = 0u;
+  if (c < numCells)
+  {
+    const uint2 se = table[c];
+    if (se.y >= se.x) // (start, LAST index) of a cell that holds particles
+    {
+      last = se.y + 1u;
+      if (c >= cellLo && c < cellHi)
+        lo = se.x, hi = se.y + 1u;
+    }
+  }
+  lo = __reduce_min_sync(0xFFFFFFFFu, lo);
+  hi = __reduce_max_sync(0xFFFFFFFFu, hi);
+  last = __reduce_max_sync(0xFFFFFFFFu, last);
+  if ((threadIdx.x & 31u) == 0u && last != 0u)
+  {
+    if (hi != 0u)
+    {
+      atomicMin(bounds, lo);
+      atomicMax(bounds + 1, hi);
+    }
+    atomicMax(bounds + 2, last);
+  }
+}
+void launchRowPhaseBounds(const DeviceState& s, const GridParams& g, u32 cellLo, u32 cellHi, u32* bounds, cudaStream_t st)
+{
+  cudaMemsetAsync(bounds, 0xFF, sizeof(u32), st);
+  cudaMemsetAsync(bounds + 1, 0, 2 * sizeof(u32), st);
+  if (cellHi > cellLo)
+    launchKernel(rowPhaseBoundsKernel, ewBlocks(g.numCells), EW_THREADS, st, (const uint2*)s.table, g.numCells, cellLo, cellHi, bounds);
+}
+
 // rows that hold no particle any more (it migrated): +inf position, zero velocity
 __global__ void __launch_bounds__(EW_THREADS) clearRowsKernel(float4* __restrict__ pos, float4* __restrict__ vel, const u32* __restrict__ idx, u32 n)
 {

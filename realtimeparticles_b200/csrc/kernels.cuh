@@ -23,6 +23,13 @@ struct DeviceState
 {
   u32 M = 0, N = 0;
   u32 nOwned = 0xFFFFFFFFu; // slab decomposition: unsorted indices >= nOwned are ghost copies (sweep.cuh validity check)
+  // slab decomposition, overlap of the ghost refresh with the sweeps: sorted rows [rowPhaseBounds[0], rowPhaseBounds[1]) are
+  // INTERIOR (two cell layers or more from both slab faces: no ghost among their neighbours, not a ghost of anybody).
+  // rowPhase 0 = a launch covers every row, 1 = only the CTAs with a row outside the interior, 2 = only the CTAs inside it.
+  const u32* rowPhaseBounds = nullptr; // { first interior row, one past the last, one past the last row holding a particle }
+  int rowPhase = 0;
+  int rowPhaseToEnd = 0; // a BOUNDARY launch also visits the "no particle" rows behind the last particle (the sweep that writes the state back)
+  u32 rowPhaseBlocks = 0; // grid of a launch by row phase (an upper bound from the caller's capacities; sweep.cuh maps the blocks)
   // float4[M]
   float4 *posA = nullptr, *posB = nullptr, *velA = nullptr, *velB = nullptr, *velC = nullptr;
   float4 *col = nullptr, *colB = nullptr, *acc = nullptr;
@@ -51,6 +58,8 @@ struct DeviceState
   MarginMaskBuffers marginMask; // the margin mask of the step (tilebuild.cuh), written by the filter kernel, read by the build sweep
   u32* buildStats = nullptr; // tilebuild.cuh counters: { irregular warps, warps over the word capacity, CTAs over the tile capacity }
 };
+
+constexpr u32 SWEEP_BLOCK_ROWS = 128; // rows per thread block of a neighbour sweep (fluids.cu: NB_THREADS, tilebuild.cuh: TB_THREADS)
 
 // how a neighbour sweep treats the per-step neighbour lists
 enum NbrMode
@@ -82,6 +91,7 @@ struct FluidStepParams
 
 // ---- grid.cu
 void launchSelftestMath(u32 lo, u32 hi, unsigned long long* bad, cudaStream_t st);
+void launchRowPhaseBounds(const DeviceState& s, const GridParams& g, u32 cellLo, u32 cellHi, u32* bounds, cudaStream_t st);
 void launchClearRows(const DeviceState& s, const u32* idx, u32 n, cudaStream_t st);
 void launchPackRows(const void* buf, int rowBytes, const u32* idx, u32 n, void* out, cudaStream_t st);
 void launchUnpackRows(void* buf, int rowBytes, const u32* idx, u32 n, const void* in, cudaStream_t st);

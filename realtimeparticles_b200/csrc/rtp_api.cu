@@ -45,6 +45,13 @@ struct rtp_handle
   SortPlan cellPlan, camPlan;
   float4* predFinal = nullptr;
   float4* shardCur = nullptr; // slab decomposition: prediction buffer the next stage reads
+  // ... overlap of a ghost refresh with the sweeps of the interior rows (rtp_shard_set_interior, rtp_shard_exchange_*)
+  u32 interiorCellLo = 0, interiorCellHi = 0, maxBoundaryRows = 0;
+  u32* rowBounds = nullptr; // device: sorted rows [rowBounds[0], rowBounds[1]) are interior
+  cudaStream_t exchStream = nullptr;
+  cudaEvent_t exchFork = nullptr, exchDone = nullptr;
+  bool exchActive = false, exchPending = false;
+  cudaStream_t shardStream() const { return exchActive ? exchStream : stream; } // pack / unpack / check_ghosts
   float nbrMargin = 0.12f; // RTP_NBR_MARGIN (0.10 / 0.12 / 0.15 measured: equal with a cold L2, 4 / 2 / 0 % faster L2-resident)
   bool nbrEnabled = true; // RTP_NBR_LISTS=0 disables the lists (plain 27-cell traversal in every sweep)
   std::vector<void*> allocs;
@@ -217,6 +224,13 @@ extern "C" void rtp_destroy(rtp_handle* h)
     }
   for (auto& m : h->marks)
     cudaEventDestroy(m.ev);
+  if (h->exchStream)
+  {
+    cudaStreamSynchronize(h->exchStream);
+    cudaStreamDestroy(h->exchStream);
+    cudaEventDestroy(h->exchFork);
+    cudaEventDestroy(h->exchDone);
+  }
   for (void* p : h->allocs)
     cudaFree(p);
   if (h->stream)
@@ -353,8 +367,8 @@ extern "C" int rtp_create(const rtp_config* cfg, rtp_handle** out)
       LIST_TRY(devAlloc(h, &s.hitList, (size_t)hcap * M));
       LIST_TRY(devAlloc(h, &s.hitCount, M));
       LIST_TRY(devAlloc(h, &s.stragQueue, M));
-      LIST_TRY(devAlloc(h, &s.stragCount, (size_t)NBR_EPOCHS));
-      LIST_TRY(devAlloc(h, &s.stragCursor, (size_t)NBR_EPOCHS));
+      LIST_TRY(devAlloc(h, &s.stragCount, (size_t)2 * NBR_EPOCHS));
+      LIST_TRY(devAlloc(h, &s.stragCursor, (size_t)2 * NBR_EPOCHS));
       LIST_TRY(devAlloc(h, &s.buildStats, (size_t)4));
       // block-cooperative list build (tilebuild.cuh): word descriptors keep 27 bits for the index, the slot logic needs
       // >= 4 cells per axis; RTP_TILED_BUILD=0 selects the per-thread build (bit-identical lists, slower)
@@ -1113,14 +1127,33 @@ extern "C" int rtp_shard_set_owned(rtp_handle* h, uint64_t n_owned)
 
 extern "C" float rtp_shard_list_dmax_sq(const rtp_handle* h) { return h ? h->c.nbrDmaxSq : 0.0f; }
 
-extern "C" int rtp_shard_stage(rtp_handle* h, int stage, int iter, int last)
+extern "C" int rtp_shard_stage(rtp_handle* h, int stage, int iter, int last) { return rtp_shard_stage_rows(h, stage, iter, last, RTP_ROWS_ALL); }
+
+extern "C" int rtp_shard_stage_rows(rtp_handle* h, int stage, int iter, int last, int rows)
 {
-  if (!h)
+  if (!h || rows < RTP_ROWS_ALL || rows > RTP_ROWS_INTERIOR)
     return RTP_ERR_INVALID;
   if (h->cfg.model != RTP_MODEL_FLUIDS)
     return fail(h, RTP_ERR_STATE, "slab decomposition is implemented for the fluids model");
+  if (rows != RTP_ROWS_ALL && (stage < RTP_SHARD_DENSITY_LAMBDA || stage > RTP_SHARD_XSPH))
+    return fail(h, RTP_ERR_INVALID, "only the neighbour sweeps run by row phase");
+  if (rows != RTP_ROWS_ALL && !h->rowBounds)
+    return fail(h, RTP_ERR_STATE, "rtp_shard_set_interior first");
   CUDA_TRY(h, cudaSetDevice(h->cfg.device));
-  DeviceState& s = h->s;
+  // a sweep by row phase: INTERIOR first, then BOUNDARY -- the call that completes the stage moves on the ping-pong buffer
+  DeviceState sPhase = h->s;
+  sPhase.rowPhase = rows;
+  // grids: every block could be interior; the boundary blocks hold at most maxBoundaryRows rows + one straddling block per side
+  const u32 allBlocks = (h->s.N + SWEEP_BLOCK_ROWS - 1) / SWEEP_BLOCK_ROWS;
+  // (the sweep that writes p_pos / p_vel back writes the "no particle" rows too: they held particles in the unsorted layout)
+  sPhase.rowPhaseToEnd = rows == RTP_ROWS_BOUNDARY
+      && (stage == RTP_SHARD_XSPH || (stage == RTP_SHARD_CORRECTION && last && !h->fp.f.isVorticityConfEnabled));
+  sPhase.rowPhaseBlocks = rows == RTP_ROWS_BOUNDARY && !sPhase.rowPhaseToEnd
+      ? min(allBlocks, (h->maxBoundaryRows + SWEEP_BLOCK_ROWS - 1) / SWEEP_BLOCK_ROWS + 3u) : allBlocks;
+  sPhase.rowPhaseBounds = rows != RTP_ROWS_ALL ? h->rowBounds : nullptr; // (a step runs all its sweeps one way or the other:
+                                                                          //  the straggler queues are split by row class)
+  const bool completes = rows != RTP_ROWS_INTERIOR;
+  DeviceState& s = stage >= RTP_SHARD_DENSITY_LAMBDA && stage <= RTP_SHARD_XSPH ? sPhase : h->s;
   const GridParams& g = h->g;
   const SphConsts& c = h->c;
   cudaStream_t st = h->stream;
@@ -1151,6 +1184,8 @@ extern "C" int rtp_shard_stage(rtp_handle* h, int stage, int iter, int last)
   case RTP_SHARD_SORT:
     enqueueSort(h->cellPlan, s.cellID, s.perm, s.keysTmp, s.permTmp, s.sortCtrl, s.sortStatus, st);
     launchFluidGather(s, g, st);
+    if (h->rowBounds)
+      launchRowPhaseBounds(s, g, h->interiorCellLo, h->interiorCellHi, h->rowBounds, st);
     launchAdjustEndCell(s, g, st);
     h->shardCur = s.pred1;
     h->predFinal = s.pred1;
@@ -1162,8 +1197,11 @@ extern "C" int rtp_shard_stage(rtp_handle* h, int stage, int iter, int last)
   {
     float4* nxt = (h->shardCur == s.pred1) ? s.pred0 : s.pred1;
     launchCorrection(s, RTP_MODEL_FLUIDS, g, c, h->fp, h->cp, h->shardCur, nxt, last != 0, false, lists ? NBR_USE : NBR_OFF, iter, st);
-    h->shardCur = nxt;
-    h->predFinal = nxt;
+    if (completes)
+    {
+      h->shardCur = nxt;
+      h->predFinal = nxt;
+    }
     break;
   }
   case RTP_SHARD_VORTICITY:
@@ -1248,7 +1286,7 @@ extern "C" int rtp_shard_pack(rtp_handle* h, int buffer, const uint32_t* d_idx, 
   if (rc != RTP_OK)
     return rc;
   CUDA_TRY(h, cudaSetDevice(h->cfg.device));
-  launchPackRows(p, rb, d_idx, (u32)n, d_out, h->stream);
+  launchPackRows(p, rb, d_idx, (u32)n, d_out, h->shardStream());
   CUDA_TRY(h, cudaGetLastError());
   return RTP_OK;
 }
@@ -1263,7 +1301,7 @@ extern "C" int rtp_shard_unpack(rtp_handle* h, int buffer, const uint32_t* d_idx
   if (rc != RTP_OK)
     return rc;
   CUDA_TRY(h, cudaSetDevice(h->cfg.device));
-  launchUnpackRows(p, rb, d_idx, (u32)n, d_in, h->stream);
+  launchUnpackRows(p, rb, d_idx, (u32)n, d_in, h->shardStream());
   CUDA_TRY(h, cudaGetLastError());
   return RTP_OK;
 }
@@ -1295,8 +1333,91 @@ extern "C" int rtp_shard_check_ghosts(rtp_handle* h, const uint32_t* d_sorted_id
   if (!h->s.nbrBuildPos || !n)
     return RTP_OK; // lists off: nothing to invalidate
   CUDA_TRY(h, cudaSetDevice(h->cfg.device));
-  launchGhostDisplacement(h->s, h->shardCur ? h->shardCur : h->s.pred1, d_sorted_idx, (u32)n, h->c.nbrDmaxSq, h->s.nbrInvalid + next_epoch, h->stream);
+  launchGhostDisplacement(h->s, h->shardCur ? h->shardCur : h->s.pred1, d_sorted_idx, (u32)n, h->c.nbrDmaxSq, h->s.nbrInvalid + next_epoch, h->shardStream());
   CUDA_TRY(h, cudaGetLastError());
+  return RTP_OK;
+}
+
+// ---- overlap of a ghost refresh with the sweeps of the interior rows
+extern "C" int rtp_shard_set_interior(rtp_handle* h, uint32_t cell_lo, uint32_t cell_hi, uint64_t max_boundary_rows)
+{
+  if (!h || cell_lo > cell_hi || cell_hi > h->g.numCells)
+    return RTP_ERR_INVALID;
+  h->maxBoundaryRows = (u32)(max_boundary_rows < h->s.M ? max_boundary_rows : h->s.M);
+  CUDA_TRY(h, cudaSetDevice(h->cfg.device));
+  if (!h->rowBounds)
+  {
+    const int rc = devAlloc(h, &h->rowBounds, (size_t)3);
+    if (rc != RTP_OK)
+      return rc;
+  }
+  h->interiorCellLo = cell_lo, h->interiorCellHi = cell_hi;
+  launchRowPhaseBounds(h->s, h->g, 0, 0, h->rowBounds, h->stream); // empty interior, no rows until the next RTP_SHARD_SORT
+  return RTP_OK;
+}
+
+static int ensureExchangeStream(rtp_handle* h)
+{
+  if (h->exchStream)
+    return RTP_OK;
+  int lo = 0, hi = 0;
+  CUDA_TRY(h, cudaDeviceGetStreamPriorityRange(&lo, &hi));
+  CUDA_TRY(h, cudaStreamCreateWithPriority(&h->exchStream, cudaStreamNonBlocking, hi)); // small kernels: ahead of the sweeps' CTAs
+  CUDA_TRY(h, cudaEventCreateWithFlags(&h->exchFork, cudaEventDisableTiming));
+  CUDA_TRY(h, cudaEventCreateWithFlags(&h->exchDone, cudaEventDisableTiming));
+  return RTP_OK;
+}
+
+extern "C" int rtp_shard_exchange_stream(rtp_handle* h, void** stream)
+{
+  if (!h || !stream)
+    return RTP_ERR_INVALID;
+  CUDA_TRY(h, cudaSetDevice(h->cfg.device));
+  const int rc = ensureExchangeStream(h);
+  *stream = (void*)h->exchStream;
+  return rc;
+}
+
+extern "C" int rtp_shard_exchange_fork(rtp_handle* h)
+{
+  if (!h)
+    return RTP_ERR_INVALID;
+  CUDA_TRY(h, cudaSetDevice(h->cfg.device));
+  const int rc = ensureExchangeStream(h);
+  if (rc != RTP_OK)
+    return rc;
+  if (h->exchActive)
+    return fail(h, RTP_ERR_STATE, "an exchange is already open");
+  CUDA_TRY(h, cudaEventRecord(h->exchFork, h->stream));
+  CUDA_TRY(h, cudaStreamWaitEvent(h->exchStream, h->exchFork, 0));
+  h->exchActive = true;
+  return RTP_OK;
+}
+
+extern "C" int rtp_shard_exchange_done(rtp_handle* h)
+{
+  if (!h)
+    return RTP_ERR_INVALID;
+  if (!h->exchActive)
+    return fail(h, RTP_ERR_STATE, "no exchange is open");
+  CUDA_TRY(h, cudaSetDevice(h->cfg.device));
+  CUDA_TRY(h, cudaEventRecord(h->exchDone, h->exchStream));
+  h->exchActive = false;
+  h->exchPending = true;
+  return RTP_OK;
+}
+
+extern "C" int rtp_shard_exchange_join(rtp_handle* h)
+{
+  if (!h)
+    return RTP_ERR_INVALID;
+  if (h->exchActive)
+    return fail(h, RTP_ERR_STATE, "the exchange is still open (rtp_shard_exchange_done first)");
+  if (!h->exchPending)
+    return RTP_OK;
+  CUDA_TRY(h, cudaSetDevice(h->cfg.device));
+  CUDA_TRY(h, cudaStreamWaitEvent(h->stream, h->exchDone, 0));
+  h->exchPending = false;
   return RTP_OK;
 }
 

@@ -38,6 +38,8 @@ The transport is pluggable: torch.distributed P2P batches (NCCL over NVLink on G
 process, or LocalSlabGroup, which runs several ranks in ONE process (tests: 2 and 4 slabs on one device; C-side hosts can
 do the same with the stage API). The engine is duck-typed so that the CPU tests drive the same code over the oracle.
 """
+import os
+
 import torch
 import torch.distributed as dist
 
@@ -107,8 +109,26 @@ class CudaSlabEngine:
     def pred_in(self):
         return self.buf("PRED_IN")
 
-    def stage(self, name, it=0, last=False):
-        self.h.shard_stage(self.ST[name], it, last)
+    ROWS = dict(ALL=0, BOUNDARY=1, INTERIOR=2)
+
+    def stage(self, name, it=0, last=False, rows="ALL"):
+        self.h.shard_stage_rows(self.ST[name], it, last, self.ROWS[rows])
+
+    # ---- overlap of a ghost refresh with the sweeps of the interior rows (include/rtp_cuda.h: rtp_shard_set_interior ...)
+    overlap_capable = True
+
+    def set_interior(self, cell_lo, cell_hi, max_boundary_rows):
+        self.h.shard_set_interior(cell_lo, cell_hi, max_boundary_rows)
+        self.exchange_stream = torch.cuda.ExternalStream(self.h.shard_exchange_stream(), device=self.device)
+
+    def exchange_fork(self):
+        self.h.shard_exchange_fork()
+
+    def exchange_done(self):
+        self.h.shard_exchange_done()
+
+    def exchange_join(self):
+        self.h.shard_exchange_join()
 
     def refresh_buffers(self, name, last=False):
         """internal buffers (cell-sorted index space) whose ghost rows must be refreshed after stage `name`"""
@@ -154,14 +174,15 @@ class CudaSlabEngine:
 class _Exchange:
     """one neighbour exchange: per side a list of (send tensor, receive tensor) pairs; None for a missing neighbour"""
 
-    def __init__(self, left, right):
+    def __init__(self, left, right, overlapped=False):
         self.left, self.right = left, right
+        self.overlapped = overlapped  # the transport runs on the engine's exchange stream (between exchange_fork and _done)
 
 
 class SlabDecomposition:
     """One rank of the x-slab decomposition. `engine` is a CudaSlabEngine (or any object with the same interface)."""
 
-    def __init__(self, engine, grid, rank=None, world=None, group=None, ghost_cap=None, migrate_cap=None):
+    def __init__(self, engine, grid, rank=None, world=None, group=None, ghost_cap=None, migrate_cap=None, overlap=None):
         self.e = engine
         self.grid = tuple(grid)
         self.group = group
@@ -213,6 +234,17 @@ class SlabDecomposition:
                 self._migrated = torch.zeros(1, dtype=torch.int64, device=e.device)
                 self._inf_rows = torch.zeros((max(self.ghost_cap, self.migrate_cap), 4), device=e.device)
                 self._inf_rows[:, :3] = float("inf")
+        # static layout: the refresh after a stage travels while the next stage sweeps the interior rows (x-layers two or
+        # more from both faces: no ghost among their neighbours, nobody's ghost); RTP_SLAB_OVERLAP=0 / overlap=False: in order
+        if overlap is None:
+            overlap = os.environ.get("RTP_SLAB_OVERLAP", "1") != "0"
+        self.overlap = bool(overlap) and self.static and bool(getattr(engine, "overlap_capable", False))
+        if self.overlap:
+            plane = self.grid[1] * self.grid[2]
+            lo = self.xlo + (GHOST_LAYERS if self.left is not None else 0)
+            hi = self.xhi - (GHOST_LAYERS if self.right is not None else 0)
+            # rows outside the interior: per face at most ghost_cap ghosts and ghost_cap owned rows of the two face layers
+            engine.set_interior(lo * plane, max(lo, hi) * plane, 2 * self.ghost_cap * sides)
 
     # ---- initial distribution: every rank is given the full initial state and keeps the particles of its slab
     def slab_of(self, keys):
@@ -317,7 +349,9 @@ class SlabDecomposition:
     def step(self):
         """one step over torch.distributed (every rank is a process)"""
         for x in self.step_gen():
-            with self.e.stream_context():  # the P2P batch is ordered after the pack kernels on the engine's stream
+            # the P2P batch is ordered after the pack kernels on the engine's stream (the exchange stream for a refresh
+            # that overlaps the next sweep)
+            with (torch.cuda.stream(self.e.exchange_stream) if x.overlapped else self.e.stream_context()):
                 self._run_dist(x)
 
     def step_gen(self):
@@ -540,8 +574,10 @@ class SlabDecomposition:
         send_all = torch.cat([send.get("l", none), send.get("r", none)])
         recv_all = torch.cat([recv.get("l", none), recv.get("r", none)])
 
-        def refresh(names):
+        def refresh(names, check_epoch=None):
             # all fields a stage produced travel in ONE exchange (one send + one receive per neighbour)
+            if self.overlap:
+                e.exchange_fork()
             bufs = []
             for k, name in enumerate(names):
                 w = e.row_width(name)
@@ -549,34 +585,37 @@ class SlabDecomposition:
                 e.pack(name, send_all, sb)
                 bufs.append((name, sb, rb))
             yield _Exchange(*[[(sb[k2], rb[k2]) for _, sb, rb in bufs] if p is not None else None
-                              for k2, p in ((0, self.left), (1, self.right))])
+                              for k2, p in ((0, self.left), (1, self.right))], overlapped=self.overlap)
             for name, sb, rb in bufs:
                 e.unpack(name, recv_all, rb)
+            if check_epoch is not None:
+                e.check_ghosts(ghost_idx, check_epoch)
+            if self.overlap:
+                e.exchange_done()
         self._mark("index-maps")
 
-        # 3. the solver stages, each followed by the refresh of what it produced
+        # 3. the solver stages, each followed by the refresh of what it produced. With overlap, a stage sweeps its interior
+        #    rows first -- while the refresh of the previous stage is still travelling -- and the rest once it has arrived.
+        stages = []
         for it in range(jacobi):
             last = it == jacobi - 1
-            e.stage("DENSITY_LAMBDA", it)
-            self._mark("compute")
-            yield from refresh(e.refresh_buffers("DENSITY_LAMBDA"))
-            self._mark("refresh")
-            e.stage("CORRECTION", it, last)
-            self._mark("compute")
-            yield from refresh(e.refresh_buffers("CORRECTION", last))
-            e.check_ghosts(ghost_idx, it + 1)
-            self._mark("refresh")
+            stages.append(("DENSITY_LAMBDA", it, False, e.refresh_buffers("DENSITY_LAMBDA"), None))
+            stages.append(("CORRECTION", it, last, e.refresh_buffers("CORRECTION", last), it + 1))
         if e.vorticity:
-            e.stage("VORTICITY", jacobi)
+            stages.append(("VORTICITY", jacobi, False, e.refresh_buffers("VORTICITY"), None))
+            stages.append(("CONFINEMENT", jacobi, False, e.refresh_buffers("CONFINEMENT"), None))
+            stages.append(("XSPH", jacobi, False, [], None))
+        for name, it, last, fields, check_epoch in stages:
+            if self.overlap:
+                e.stage(name, it, last, rows="INTERIOR")
+                e.exchange_join()
+                e.stage(name, it, last, rows="BOUNDARY")
+            else:
+                e.stage(name, it, last)
             self._mark("compute")
-            yield from refresh(e.refresh_buffers("VORTICITY"))
-            self._mark("refresh")
-            e.stage("CONFINEMENT", jacobi)
-            self._mark("compute")
-            yield from refresh(e.refresh_buffers("CONFINEMENT"))
-            self._mark("refresh")
-            e.stage("XSPH", jacobi)
-            self._mark("compute")
+            if fields:
+                yield from refresh(fields, check_epoch)
+                self._mark("refresh")
 
         # 4. particles to the front of the own region, in cell-sorted order; everything else is "no particle"
         e.stage("DROP_GHOSTS")
@@ -629,6 +668,8 @@ class LocalSlabGroup:
                 raise RuntimeError("the ranks of a LocalSlabGroup left the step at different exchange points")
             for sd in self.slabs:
                 sd.e.sync()  # the rows to send are complete
+                if hasattr(sd.e, "device"):
+                    torch.cuda.synchronize(sd.e.device)  # (also on the exchange stream)
             for r, x in enumerate(xs):
                 if x.right is not None:  # my right-going rows are my right neighbour's rows "from the left", and vice versa
                     for (send, _), (_, recv) in zip(x.right, xs[r + 1].left):

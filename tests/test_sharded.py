@@ -59,11 +59,11 @@ def test_initial_split_is_a_partition():
     assert np.array_equal(allidx, np.arange(len(pos0)))
 
 
-def _local_group(make_engine, world, pos0, vel0, to_dev):
+def _local_group(make_engine, world, pos0, vel0, to_dev, **kw):
     from realtimeparticles_b200 import sharded
     sds = []
     for r in range(world):
-        sd = sharded.SlabDecomposition(make_engine(), GRID, rank=r, world=world)
+        sd = sharded.SlabDecomposition(make_engine(), GRID, rank=r, world=world, **kw)
         mine = sharded.split_initial_state(pos0, BOX, GRID, r, world)
         sd.load_owned(to_dev(pos0[mine]), to_dev(vel0[mine]))
         sds.append(sd)
@@ -124,6 +124,27 @@ def test_slab_decomposition_on_one_device_matches_single_handle(world):
     # aggregate invariants (north_star: within 1 %): kinetic energy of the decomposed run vs the single handle
     ke, ke_ref = 0.5 * (vel[:, :3].astype(np.float64) ** 2).sum(), 0.5 * (ref_vel[:, :3].astype(np.float64) ** 2).sum()
     assert abs(ke - ke_ref) <= 1e-4 * ke_ref, (ke, ke_ref)
+
+
+@pytest.mark.gpu
+def test_refresh_overlapped_with_interior_sweeps_same_bits():
+    # the ghost refresh of a stage travelling on the exchange stream while the next stage sweeps its interior rows
+    # (rtp_shard_stage_rows INTERIOR / BOUNDARY, split straggler queues) is a re-ordering of launches only: same bits as
+    # the in-order schedule. 3 ranks: rank 1 has two faces, ranks 0 / 2 have interior rows up to the domain wall.
+    from realtimeparticles_b200 import sharded
+    pos0 = _dam((48, 32, 32), end=(3.0, 0.0, 0.0))
+    vel0 = _drift(pos0)
+    steps, jacobi, n = 8, 3, len(pos0)
+    out = {}
+    for overlap in (False, True):
+        grp, sds = _local_group(lambda: sharded.CudaSlabEngine(n, BOX, GRID, 0, jacobi=jacobi), 3, pos0, vel0,
+                                lambda a: torch.from_numpy(a).cuda(), overlap=overlap)
+        assert all(sd.overlap == overlap for sd in sds)
+        for _ in range(steps):
+            grp.step()
+        out[overlap] = [tuple(t.cpu().numpy() for t in sd.owned_state()) for sd in sds]
+    for (p0, v0), (p1, v1) in zip(out[False], out[True]):
+        assert len(p0) > 0 and np.array_equal(p0, p1) and np.array_equal(v0, v1)
 
 
 @pytest.mark.gpu
