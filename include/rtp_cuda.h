@@ -291,7 +291,7 @@ typedef enum rtp_shard_buffer_id
   RTP_SHARD_BUF_VORT_NORM = 5, /* f[M] */
   RTP_SHARD_BUF_VEL_CONFINED = 6, /* f4[M] velocity after vorticity confinement (input of the XSPH sweep) */
   RTP_SHARD_BUF_LIST_BUILD_POS = 7, /* f4[M] positions the neighbour lists were built from */
-  RTP_SHARD_BUF_LIST_INVALID = 8, /* u32[16] per-epoch "lists invalid" flags */
+  RTP_SHARD_BUF_LIST_INVALID = 8, /* u32[2][16] per-epoch "lists invalid" flags: raised by own particles / by ghosts */
   RTP_SHARD_BUF_POS = 9, /* f4[M] p_pos (unsorted between steps: migration) */
   RTP_SHARD_BUF_VEL = 10 /* f4[M] p_vel */
 } rtp_shard_buffer_id;

@@ -88,7 +88,7 @@ __global__ void __launch_bounds__(EW_THREADS) fluidPredictKernel(DeviceState s, 
     s.table[i] = make_uint2(1u, 0u);
   if (i < NBR_EPOCHS && s.nbrInvalid)
   {
-    s.nbrInvalid[i] = 0u;
+    s.nbrInvalid[i] = s.nbrInvalid[NBR_EPOCHS + i] = 0u; // (own particles / ghosts of a slab, sweep.cuh)
     s.stragCount[i] = s.stragCount[NBR_EPOCHS + i] = 0u; // (two queue classes, sweep.cuh)
     s.stragCursor[i] = s.stragCursor[NBR_EPOCHS + i] = 0u;
   }
@@ -202,7 +202,7 @@ __global__ void __launch_bounds__(EW_THREADS) cloudsThermoPredictKernel(DeviceSt
     s.table[i] = make_uint2(1u, 0u);
   if (i < NBR_EPOCHS && s.nbrInvalid)
   {
-    s.nbrInvalid[i] = 0u;
+    s.nbrInvalid[i] = s.nbrInvalid[NBR_EPOCHS + i] = 0u; // (own particles / ghosts of a slab, sweep.cuh)
     s.stragCount[i] = s.stragCount[NBR_EPOCHS + i] = 0u; // (two queue classes, sweep.cuh)
     s.stragCursor[i] = s.stragCursor[NBR_EPOCHS + i] = 0u;
   }

@@ -358,7 +358,7 @@ extern "C" int rtp_create(const rtp_config* cfg, rtp_handle** out)
       LIST_TRY(devAlloc(h, &s.nbrList, (size_t)cap * M));
       LIST_TRY(devAlloc(h, &s.nbrCount, M));
       LIST_TRY(devAlloc(h, &s.nbrBuildPos, M));
-      LIST_TRY(devAlloc(h, &s.nbrInvalid, (size_t)NBR_EPOCHS));
+      LIST_TRY(devAlloc(h, &s.nbrInvalid, (size_t)2 * NBR_EPOCHS));
       u32 hcap = 160;
       if (const char* e = getenv("RTP_HIT_CAP"))
         hcap = (u32)atoi(e);
@@ -1255,7 +1255,7 @@ extern "C" int rtp_shard_buffer(rtp_handle* h, int which, void** dptr, size_t* b
   case RTP_SHARD_BUF_POS: p = s.posA; b = 16 * M; break;
   case RTP_SHARD_BUF_VEL: p = s.velA; b = 16 * M; break;
   case RTP_SHARD_BUF_LIST_BUILD_POS: p = s.nbrBuildPos; b = 16 * M; break;
-  case RTP_SHARD_BUF_LIST_INVALID: p = s.nbrInvalid; b = 4 * (size_t)NBR_EPOCHS; break;
+  case RTP_SHARD_BUF_LIST_INVALID: p = s.nbrInvalid; b = 4 * (size_t)2 * NBR_EPOCHS; break;
   default: return fail(h, RTP_ERR_INVALID, "unknown shard buffer");
   }
   if (!p)
@@ -1333,7 +1333,7 @@ extern "C" int rtp_shard_check_ghosts(rtp_handle* h, const uint32_t* d_sorted_id
   if (!h->s.nbrBuildPos || !n)
     return RTP_OK; // lists off: nothing to invalidate
   CUDA_TRY(h, cudaSetDevice(h->cfg.device));
-  launchGhostDisplacement(h->s, h->shardCur ? h->shardCur : h->s.pred1, d_sorted_idx, (u32)n, h->c.nbrDmaxSq, h->s.nbrInvalid + next_epoch, h->shardStream());
+  launchGhostDisplacement(h->s, h->shardCur ? h->shardCur : h->s.pred1, d_sorted_idx, (u32)n, h->c.nbrDmaxSq, h->s.nbrInvalid + NBR_EPOCHS + next_epoch, h->shardStream());
   CUDA_TRY(h, cudaGetLastError());
   return RTP_OK;
 }
