@@ -277,7 +277,8 @@ typedef enum rtp_shard_stage_id
   RTP_SHARD_VORTICITY = 5,
   RTP_SHARD_CONFINEMENT = 6,
   RTP_SHARD_XSPH = 7, /* + updatePosition: state back in p_pos / p_vel, sorted order */
-  RTP_SHARD_DROP_GHOSTS = 8 /* compact p_pos / p_vel to the owned particles (first n_owned), cell-sorted order kept */
+  RTP_SHARD_DROP_GHOSTS = 8, /* compact p_pos / p_vel to the owned particles (first n_owned), cell-sorted order kept */
+  RTP_SHARD_PREDICT_FROM = 9 /* predict + cell ids of the owned rows [iter, n_owned) only (arrivals of a migration), no reset */
 } rtp_shard_stage_id;
 
 /* internal buffers a slab exchange touches (device pointers valid until the next RTP_SHARD_SORT) */
@@ -293,7 +294,9 @@ typedef enum rtp_shard_buffer_id
   RTP_SHARD_BUF_LIST_BUILD_POS = 7, /* f4[M] positions the neighbour lists were built from */
   RTP_SHARD_BUF_LIST_INVALID = 8, /* u32[2][16] per-epoch "lists invalid" flags: raised by own particles / by ghosts */
   RTP_SHARD_BUF_POS = 9, /* f4[M] p_pos (unsorted between steps: migration) */
-  RTP_SHARD_BUF_VEL = 10 /* f4[M] p_vel */
+  RTP_SHARD_BUF_VEL = 10, /* f4[M] p_vel */
+  RTP_SHARD_BUF_ROW_BOUNDS = 11 /* u32[4] rtp_shard_set_interior: first interior row, one past the last, rows holding a
+                                   particle, error flag (a launch by row phase was sized too small: results are invalid) */
 } rtp_shard_buffer_id;
 
 /* number of leading (unsorted) particles this rank owns; the rest of nb_particles are ghosts */
@@ -304,7 +307,8 @@ RTP_API int rtp_shard_buffer(rtp_handle* h, int which, void** dptr, size_t* byte
  * caller). All pointers are DEVICE pointers, everything is enqueued on the handle's stream, nothing synchronises.
  *  pack:   d_out[k] = buffer[d_idx[k]], k < n; an index 0xFFFFFFFF ("no particle": fixed-capacity exchanges are padded)
  *          packs a +inf position (f4 rows) or 0 (scalar rows);  unpack: buffer[d_idx[k]] = d_in[k], padding skipped.
- *  clear_rows: p_pos[d_idx[k]] = +inf, p_vel[d_idx[k]] = 0: the row holds no particle any more (it migrated); such rows sort
+ *  clear_rows: p_pos[d_idx[k]] = +inf, p_vel[d_idx[k]] = 0 (and the prediction / cell id RTP_SHARD_PREDICT gives such a row):
+ *          the row holds no particle any more (it migrated); such rows sort
  *          behind every particle, appear in no cell range and are skipped by the sweeps of a sharded handle.
  *  inverse_perm: d_inv[perm[i]] = i for the nb_particles cell-sorted rows (where did unsorted row j go).
  *  check_ghosts: raise the "lists invalid" flag of next_epoch when a ghost row (sorted indices d_sorted_idx) has been moved
@@ -312,6 +316,10 @@ RTP_API int rtp_shard_buffer(rtp_handle* h, int which, void** dptr, size_t* byte
 RTP_API int rtp_shard_pack(rtp_handle* h, int buffer, const uint32_t* d_idx, uint64_t n, void* d_out);
 RTP_API int rtp_shard_unpack(rtp_handle* h, int buffer, const uint32_t* d_idx, uint64_t n, const void* d_in);
 RTP_API int rtp_shard_clear_rows(rtp_handle* h, const uint32_t* d_idx, uint64_t n);
+/* classify: for the first n (unsorted) rows, after RTP_SHARD_PREDICT: d_below[i] = the row holds a particle (finite p_pos)
+ *          whose predicted cell x-layer is < layer_below, d_above[i] = ... >= layer_from (bytes 0 / 1): the leavers of a
+ *          migration, the face layers of a halo; the caller compacts the masks (order-preserving). */
+RTP_API int rtp_shard_classify(rtp_handle* h, uint64_t n, uint32_t layer_below, uint32_t layer_from, uint8_t* d_below, uint8_t* d_above);
 RTP_API int rtp_shard_inverse_perm(rtp_handle* h, uint32_t* d_inv);
 RTP_API int rtp_shard_check_ghosts(rtp_handle* h, const uint32_t* d_sorted_idx, uint64_t n, int next_epoch);
 /* neighbour-list validity: radius^2 a particle may move from its list-build position (see sweep.cuh) */

@@ -81,7 +81,7 @@ EXPORTS = ["rtp_abi_version", "rtp_device_count", "rtp_create", "rtp_destroy", "
            "rtp_set_displayed_quantity", "rtp_reset_ids", "rtp_init_clouds_fields", "rtp_step", "rtp_step_n",
            "rtp_sync", "rtp_get_stream", "rtp_sort_keys", "rtp_sort_keys_host", "rtp_selftest_math", "rtp_enable_profiling", "rtp_get_stage_times",
            "rtp_last_launch_count", "rtp_list_stats", "rtp_shard_set_owned", "rtp_shard_stage", "rtp_shard_buffer", "rtp_shard_list_dmax_sq", "rtp_shard_pack", "rtp_shard_unpack", "rtp_shard_clear_rows", "rtp_shard_inverse_perm", "rtp_shard_check_ghosts",
-           "rtp_shard_set_interior", "rtp_shard_stage_rows", "rtp_shard_exchange_stream", "rtp_shard_exchange_fork", "rtp_shard_exchange_done", "rtp_shard_exchange_join",
+           "rtp_shard_classify", "rtp_shard_set_interior", "rtp_shard_stage_rows", "rtp_shard_exchange_stream", "rtp_shard_exchange_fork", "rtp_shard_exchange_done", "rtp_shard_exchange_join",
            "rtp_gen_box_grid", "rtp_gen_sphere_grid", "rtp_gen_rectangle_grid", "rtp_gen_circle_grid", "rtp_gen_random_box",
            "rtp_baked_constant", "rtp_register_gl", "rtp_unregister_gl", "rtp_target_create", "rtp_target_destroy", "rtp_target_update"]
 
@@ -135,6 +135,7 @@ def lib():
     L.rtp_shard_clear_rows.argtypes = [vp, C.c_void_p, C.c_uint64]
     L.rtp_shard_inverse_perm.argtypes = [vp, C.c_void_p]
     L.rtp_shard_check_ghosts.argtypes = [vp, C.c_void_p, C.c_uint64, C.c_int]
+    L.rtp_shard_classify.argtypes = [vp, C.c_uint64, C.c_uint32, C.c_uint32, C.c_void_p, C.c_void_p]
     L.rtp_shard_set_interior.argtypes = [vp, C.c_uint32, C.c_uint32, C.c_uint64]
     L.rtp_shard_stage_rows.argtypes = [vp, C.c_int, C.c_int, C.c_int, C.c_int]
     L.rtp_shard_exchange_stream.argtypes = [vp, C.POINTER(C.c_void_p)]
@@ -327,6 +328,9 @@ class Handle:
 
     def shard_stage_rows(self, stage, it, last, rows):
         self._check(self.L.rtp_shard_stage_rows(self.h, int(stage), int(it), int(bool(last)), int(rows)), "rtp_shard_stage_rows")
+
+    def shard_classify(self, n, layer_below, layer_from, below_ptr, above_ptr):
+        self._check(self.L.rtp_shard_classify(self.h, int(n), int(layer_below), int(layer_from), below_ptr, above_ptr), "rtp_shard_classify")
 
     def shard_set_interior(self, cell_lo, cell_hi, max_boundary_rows):
         self._check(self.L.rtp_shard_set_interior(self.h, int(cell_lo), int(cell_hi), int(max_boundary_rows)), "rtp_shard_set_interior")

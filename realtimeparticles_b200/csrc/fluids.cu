@@ -80,13 +80,13 @@ __device__ __forceinline__ float4 cloudBoundary(const GridParams& g, float4 np)
 // histogram kernel and one read of the keys; the caller has zeroed the sort control block before the launch)
 template <bool HIST>
 __global__ void __launch_bounds__(EW_THREADS) fluidPredictKernel(DeviceState s, GridParams g, float dt, u32* __restrict__ keys,
-    int passes, PassDesc desc, u32* __restrict__ sortCtrl, u32* __restrict__ sortStatus, size_t statusWords)
+    int passes, PassDesc desc, u32* __restrict__ sortCtrl, u32* __restrict__ sortStatus, size_t statusWords, int resets)
 {
   RTP_PDL_PROLOGUE();
   const u32 i = blockIdx.x * EW_THREADS + threadIdx.x;
-  if (i < g.numCells)
+  if (resets && i < g.numCells)
     s.table[i] = make_uint2(1u, 0u);
-  if (i < NBR_EPOCHS && s.nbrInvalid)
+  if (resets && i < NBR_EPOCHS && s.nbrInvalid)
   {
     s.nbrInvalid[i] = s.nbrInvalid[NBR_EPOCHS + i] = 0u; // (own particles / ghosts of a slab, sweep.cuh)
     s.stragCount[i] = s.stragCount[NBR_EPOCHS + i] = 0u; // (two queue classes, sweep.cuh)
@@ -336,7 +336,7 @@ __global__ void __launch_bounds__(NB_THREADS, NB_MIN_BLOCKS) marginMaskKernel(De
   const u32 i = row0 + threadIdx.x;
   const bool active = i < s.N && !isPassiveRow(s, i, P[i]);
   const float4 pi = active ? P[i] : make_float4(0.f, 0.f, 0.f, 0.f);
-  tileFilterToMask<TRAV>(sm, g, c.nbrRadiusSq, s.table, P, pi, active, s.marginMask, s.buildStats);
+  tileFilterToMask<TRAV>(sm, g, c.nbrRadiusSq, s.table, P, pi, active, row0, s.marginMask, s.buildStats);
 }
 
 template <int TRAV>
@@ -696,15 +696,18 @@ static inline int sweepBlocks(const DeviceState& s) { return s.rowPhase ? (int)s
 
 static_assert(EW_THREADS == SORT_THREADS, "fluidPredictKernel<true> builds the sort histograms with SORT_THREADS threads per block");
 void launchFluidPredict(const DeviceState& s, const GridParams& g, const FluidStepParams& p, u32* keysOut, const SortPlan* fusedSort,
-    u32* sortCtrl, u32* sortStatus, cudaStream_t st)
+    u32* sortCtrl, u32* sortStatus, cudaStream_t st, bool resets)
 {
-  const int blocks = ewBlocks(max(s.N, g.numCells));
+  // resets = false: only the prediction and the cell ids of the rows (slab decomposition: the arrivals of a migration)
+  const int blocks = ewBlocks(resets ? max(s.N, g.numCells) : s.N);
+  if (!blocks)
+    return;
   if (fusedSort && fusedSort->n)
     launchKernel(fluidPredictKernel<true>, blocks, EW_THREADS, st, s, g, p.f.timeStep, keysOut, fusedSort->passes, makePassDesc(*fusedSort),
-        sortCtrl, sortStatus, sortStatusWords(*fusedSort));
+        sortCtrl, sortStatus, sortStatusWords(*fusedSort), resets ? 1 : 0);
   else
     launchKernel(fluidPredictKernel<false>, blocks, EW_THREADS, st, s, g, p.f.timeStep, keysOut, 0, PassDesc {}, (u32*)nullptr, (u32*)nullptr,
-        (size_t)0);
+        (size_t)0, resets ? 1 : 0);
 }
 void launchMarginMask(const DeviceState& s, int model, const GridParams& g, const SphConsts& c, const float4* P, cudaStream_t st)
 {

@@ -249,6 +249,7 @@ __global__ void __launch_bounds__(EW_THREADS) ghostDisplacementKernel(const floa
 // interior rows of a slab (kernels.cuh: rowPhaseBounds) = the sorted rows of the cells [cellLo, cellHi): bounds[0] = first
 // row, bounds[1] = one past the last one; bounds[2] = one past the last row that holds a particle (any cell). Pre-set to
 // 0xFFFFFFFF / 0 / 0 by the launcher (an empty interior, no particle); runs on the table BEFORE adjustEndCell caps the ends.
+// bounds[3] is the sticky error flag of the launches by row phase (sweep.cuh: a grid too small for its rows).
 __global__ void __launch_bounds__(EW_THREADS) rowPhaseBoundsKernel(const uint2* __restrict__ table, u32 numCells, u32 cellLo, u32 cellHi,
     u32* __restrict__ bounds)
 {
@@ -286,8 +287,33 @@ void launchRowPhaseBounds(const DeviceState& s, const GridParams& g, u32 cellLo,
     launchKernel(rowPhaseBoundsKernel, ewBlocks(g.numCells), EW_THREADS, st, (const uint2*)s.table, g.numCells, cellLo, cellHi, bounds);
 }
 
-// rows that hold no particle any more (it migrated): +inf position, zero velocity
-__global__ void __launch_bounds__(EW_THREADS) clearRowsKernel(float4* __restrict__ pos, float4* __restrict__ vel, const u32* __restrict__ idx, u32 n)
+// slab decomposition: which rows hold a particle whose cell x-layer (key / plane, the +x wall index clamped into the last
+// layer) lies below cutLo / at or above cutHi -- the leavers of a migration, the face layers of a halo. One pass over
+// keys and positions; the caller compacts the two byte masks (order-preserving, deterministic).
+__global__ void __launch_bounds__(EW_THREADS) classifyRowsKernel(const u32* __restrict__ keys, const float4* __restrict__ pos, u32 n, u32 plane,
+    u32 lastLayer, u32 cutLo, u32 cutHi, unsigned char* __restrict__ below, unsigned char* __restrict__ above)
+{
+  RTP_PDL_PROLOGUE();
+  const u32 i = blockIdx.x * EW_THREADS + threadIdx.x;
+  if (i >= n)
+    return;
+  const bool alive = isfinite(pos[i].x);
+  const u32 layer = min(keys[i] / plane, lastLayer);
+  below[i] = alive && layer < cutLo;
+  above[i] = alive && layer >= cutHi;
+}
+void launchClassifyRows(const DeviceState& s, const GridParams& g, const u32* keys, u32 n, u32 cutLo, u32 cutHi, unsigned char* below,
+    unsigned char* above, cudaStream_t st)
+{
+  if (n)
+    launchKernel(classifyRowsKernel, ewBlocks(n), EW_THREADS, st, keys, (const float4*)s.posA, n, (u32)(g.res[1] * g.res[2]), (u32)(g.res[0] - 1), cutLo,
+        cutHi, below, above);
+}
+
+// rows that hold no particle any more (it migrated): +inf position, zero velocity -- and the prediction / cell id
+// RTP_SHARD_PREDICT computes for such a row (the leavers are cleared after the prediction that found them)
+__global__ void __launch_bounds__(EW_THREADS) clearRowsKernel(float4* __restrict__ pos, float4* __restrict__ vel, float4* __restrict__ pred,
+    u32* __restrict__ keys, GridParams g, const u32* __restrict__ idx, u32 n)
 {
   RTP_PDL_PROLOGUE();
   const u32 k = blockIdx.x * EW_THREADS + threadIdx.x;
@@ -298,12 +324,14 @@ __global__ void __launch_bounds__(EW_THREADS) clearRowsKernel(float4* __restrict
   {
     pos[j] = make_float4(INFINITY, INFINITY, INFINITY, 0.0f);
     vel[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+    pred[j] = make_float4(INFINITY, INFINITY, INFINITY, 0.0f);
+    keys[j] = cell1D(g, INFINITY, INFINITY, INFINITY);
   }
 }
-void launchClearRows(const DeviceState& s, const u32* idx, u32 n, cudaStream_t st)
+void launchClearRows(const DeviceState& s, const GridParams& g, u32* keys, const u32* idx, u32 n, cudaStream_t st)
 {
   if (n)
-    launchKernel(clearRowsKernel, ewBlocks(n), EW_THREADS, st, s.posA, s.velA, idx, n);
+    launchKernel(clearRowsKernel, ewBlocks(n), EW_THREADS, st, s.posA, s.velA, s.pred0, keys, g, idx, n);
 }
 void launchPackRows(const void* buf, int rowBytes, const u32* idx, u32 n, void* out, cudaStream_t st)
 {

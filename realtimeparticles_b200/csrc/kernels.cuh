@@ -26,7 +26,7 @@ struct DeviceState
   // slab decomposition, overlap of the ghost refresh with the sweeps: sorted rows [rowPhaseBounds[0], rowPhaseBounds[1]) are
   // INTERIOR (two cell layers or more from both slab faces: no ghost among their neighbours, not a ghost of anybody).
   // rowPhase 0 = a launch covers every row, 1 = only the CTAs with a row outside the interior, 2 = only the CTAs inside it.
-  const u32* rowPhaseBounds = nullptr; // { first interior row, one past the last, one past the last row holding a particle }
+  u32* rowPhaseBounds = nullptr; // { first interior row, one past the last, one past the last row holding a particle, error flag }
   int rowPhase = 0;
   int rowPhaseToEnd = 0; // a BOUNDARY launch also visits the "no particle" rows behind the last particle (the sweep that writes the state back)
   u32 rowPhaseBlocks = 0; // grid of a launch by row phase (an upper bound from the caller's capacities; sweep.cuh maps the blocks)
@@ -92,7 +92,9 @@ struct FluidStepParams
 // ---- grid.cu
 void launchSelftestMath(u32 lo, u32 hi, unsigned long long* bad, cudaStream_t st);
 void launchRowPhaseBounds(const DeviceState& s, const GridParams& g, u32 cellLo, u32 cellHi, u32* bounds, cudaStream_t st);
-void launchClearRows(const DeviceState& s, const u32* idx, u32 n, cudaStream_t st);
+void launchClassifyRows(const DeviceState& s, const GridParams& g, const u32* keys, u32 n, u32 cutLo, u32 cutHi, unsigned char* below,
+    unsigned char* above, cudaStream_t st);
+void launchClearRows(const DeviceState& s, const GridParams& g, u32* keys, const u32* idx, u32 n, cudaStream_t st);
 void launchPackRows(const void* buf, int rowBytes, const u32* idx, u32 n, void* out, cudaStream_t st);
 void launchUnpackRows(void* buf, int rowBytes, const u32* idx, u32 n, const void* in, cudaStream_t st);
 void launchInversePerm(const DeviceState& s, u32* inv, cudaStream_t st);
@@ -116,7 +118,7 @@ void launchBoidsRules(const DeviceState& s, const GridParams& g, const SphConsts
 struct SortPlan;
 // fusedSort != nullptr: the kernel also builds that sort's histograms (sort.cuh enqueueSortBegin / enqueueSortPasses around it)
 void launchFluidPredict(const DeviceState& s, const GridParams& g, const FluidStepParams& p, u32* keysOut, const SortPlan* fusedSort,
-    u32* sortCtrl, u32* sortStatus, cudaStream_t st);
+    u32* sortCtrl, u32* sortStatus, cudaStream_t st, bool resets = true);
 // the block-cooperative filter of a list build: writes the margin mask of positions P (tilebuild.cuh)
 void launchMarginMask(const DeviceState& s, int model, const GridParams& g, const SphConsts& c, const float4* P, cudaStream_t st);
 void launchFluidGather(const DeviceState& s, const GridParams& g, cudaStream_t st);

@@ -47,10 +47,17 @@ struct rtp_handle
   float4* shardCur = nullptr; // slab decomposition: prediction buffer the next stage reads
   // ... overlap of a ghost refresh with the sweeps of the interior rows (rtp_shard_set_interior, rtp_shard_exchange_*)
   u32 interiorCellLo = 0, interiorCellHi = 0, maxBoundaryRows = 0;
-  u32* rowBounds = nullptr; // device: sorted rows [rowBounds[0], rowBounds[1]) are interior
+  u32* rowBounds = nullptr; // device: sorted rows [rowBounds[0], rowBounds[1]) are interior, [2] = rows with a particle, [3] = error
+  volatile u32* rowBoundsHost = nullptr; // pinned copy of [0..2], a step or two old (no synchronisation): sizes the grids
   cudaStream_t exchStream = nullptr;
   cudaEvent_t exchFork = nullptr, exchDone = nullptr;
   bool exchActive = false, exchPending = false;
+  // the BOUNDARY launches of the sweeps run on a stream of their own (high priority: the exchange waits for them), so that
+  // the two launches of a stage share the GPU instead of each paying its tail: bndPre = "the compute stream has reached
+  // this stage", bndDone = "the boundary launch of the last stage is through"
+  cudaStream_t bndStream = nullptr;
+  cudaEvent_t bndPre = nullptr, bndDone = nullptr;
+  bool bndPending = false;
   cudaStream_t shardStream() const { return exchActive ? exchStream : stream; } // pack / unpack / check_ghosts
   float nbrMargin = 0.12f; // RTP_NBR_MARGIN (0.10 / 0.12 / 0.15 measured: equal with a cold L2, 4 / 2 / 0 % faster L2-resident)
   bool nbrEnabled = true; // RTP_NBR_LISTS=0 disables the lists (plain 27-cell traversal in every sweep)
@@ -230,7 +237,13 @@ extern "C" void rtp_destroy(rtp_handle* h)
     cudaStreamDestroy(h->exchStream);
     cudaEventDestroy(h->exchFork);
     cudaEventDestroy(h->exchDone);
+    cudaStreamSynchronize(h->bndStream);
+    cudaStreamDestroy(h->bndStream);
+    cudaEventDestroy(h->bndPre);
+    cudaEventDestroy(h->bndDone);
   }
+  if (h->rowBoundsHost)
+    cudaFreeHost((void*)h->rowBoundsHost);
   for (void* p : h->allocs)
     cudaFree(p);
   if (h->stream)
@@ -1127,6 +1140,8 @@ extern "C" int rtp_shard_set_owned(rtp_handle* h, uint64_t n_owned)
 
 extern "C" float rtp_shard_list_dmax_sq(const rtp_handle* h) { return h ? h->c.nbrDmaxSq : 0.0f; }
 
+static int ensureExchangeStream(rtp_handle* h);
+
 extern "C" int rtp_shard_stage(rtp_handle* h, int stage, int iter, int last) { return rtp_shard_stage_rows(h, stage, iter, last, RTP_ROWS_ALL); }
 
 extern "C" int rtp_shard_stage_rows(rtp_handle* h, int stage, int iter, int last, int rows)
@@ -1150,13 +1165,51 @@ extern "C" int rtp_shard_stage_rows(rtp_handle* h, int stage, int iter, int last
       && (stage == RTP_SHARD_XSPH || (stage == RTP_SHARD_CORRECTION && last && !h->fp.f.isVorticityConfEnabled));
   sPhase.rowPhaseBlocks = rows == RTP_ROWS_BOUNDARY && !sPhase.rowPhaseToEnd
       ? min(allBlocks, (h->maxBoundaryRows + SWEEP_BLOCK_ROWS - 1) / SWEEP_BLOCK_ROWS + 3u) : allBlocks;
+  if (rows != RTP_ROWS_ALL && h->rowBoundsHost && !sPhase.rowPhaseToEnd)
+  {
+    // tighter: the bounds of a recent step (copied to the host without synchronisation, a step or two old) plus a margin the
+    // populations cannot outrun in that time; a launch that turns out too small raises rowBounds[3] (sweep.cuh), which the
+    // caller reads with its capacity flags
+    const u32 b0 = h->rowBoundsHost[0], b1 = h->rowBoundsHost[1], nr = h->rowBoundsHost[2];
+    const u32 margin = 64u; // blocks = 8192 rows per side
+    if (nr != 0u && nr <= h->s.N && b0 < b1 && b1 <= nr)
+    {
+      const u32 i0 = (b0 + SWEEP_BLOCK_ROWS - 1) / SWEEP_BLOCK_ROWS, i1 = b1 / SWEEP_BLOCK_ROWS, nb = (nr + SWEEP_BLOCK_ROWS - 1) / SWEEP_BLOCK_ROWS;
+      const u32 want = rows == RTP_ROWS_INTERIOR ? (i1 > i0 ? i1 - i0 : 0u) + margin : i0 + (nb > i1 ? nb - i1 : 0u) + 2u * margin;
+      sPhase.rowPhaseBlocks = min(sPhase.rowPhaseBlocks, want);
+    }
+  }
   sPhase.rowPhaseBounds = rows != RTP_ROWS_ALL ? h->rowBounds : nullptr; // (a step runs all its sweeps one way or the other:
                                                                           //  the straggler queues are split by row class)
   const bool completes = rows != RTP_ROWS_INTERIOR;
   DeviceState& s = stage >= RTP_SHARD_DENSITY_LAMBDA && stage <= RTP_SHARD_XSPH ? sPhase : h->s;
+  cudaStream_t st = h->stream;
+  if (rows == RTP_ROWS_BOUNDARY)
+  {
+    const int rc = ensureExchangeStream(h);
+    if (rc != RTP_OK)
+      return rc;
+    // after everything the compute stream held when this stage began (the INTERIOR call recorded it), beside its interior launch
+    st = h->bndStream;
+    CUDA_TRY(h, cudaStreamWaitEvent(st, h->bndPre, 0));
+  }
+  else
+  {
+    if (h->bndPending) // the previous stage is complete once its boundary launch is
+    {
+      CUDA_TRY(h, cudaStreamWaitEvent(h->stream, h->bndDone, 0));
+      h->bndPending = false;
+    }
+    if (rows == RTP_ROWS_INTERIOR)
+    {
+      const int rc = ensureExchangeStream(h);
+      if (rc != RTP_OK)
+        return rc;
+      CUDA_TRY(h, cudaEventRecord(h->bndPre, h->stream));
+    }
+  }
   const GridParams& g = h->g;
   const SphConsts& c = h->c;
-  cudaStream_t st = h->stream;
   const bool lists = s.nbrList != nullptr && h->jacobi + 1 < NBR_EPOCH_TEMP;
   u32* keysIn = (h->cellPlan.passes % 2 == 0) ? s.cellID : s.keysTmp;
   // iteration it reads shardCur and writes the other prediction buffer
@@ -1167,6 +1220,16 @@ extern "C" int rtp_shard_stage_rows(rtp_handle* h, int stage, int iter, int last
     DeviceState own = s;
     own.N = min(s.nOwned, s.N);
     launchFluidPredict(own, g, h->fp, keysIn, nullptr, nullptr, nullptr, st);
+    break;
+  }
+  case RTP_SHARD_PREDICT_FROM:
+  {
+    // prediction and cell ids of the owned rows [iter, n_owned) only (the arrival slots of a migration), nothing reset
+    const u32 end = min(s.nOwned, s.N), first = min((u32)max(iter, 0), end);
+    DeviceState own = s;
+    own.N = end - first;
+    own.posA = s.posA + first, own.velA = s.velA + first, own.pred0 = s.pred0 + first;
+    launchFluidPredict(own, g, h->fp, keysIn + first, nullptr, nullptr, nullptr, st, false);
     break;
   }
   case RTP_SHARD_GHOST_KEYS:
@@ -1185,7 +1248,10 @@ extern "C" int rtp_shard_stage_rows(rtp_handle* h, int stage, int iter, int last
     enqueueSort(h->cellPlan, s.cellID, s.perm, s.keysTmp, s.permTmp, s.sortCtrl, s.sortStatus, st);
     launchFluidGather(s, g, st);
     if (h->rowBounds)
+    {
       launchRowPhaseBounds(s, g, h->interiorCellLo, h->interiorCellHi, h->rowBounds, st);
+      cudaMemcpyAsync((void*)h->rowBoundsHost, h->rowBounds, 3 * sizeof(u32), cudaMemcpyDeviceToHost, st); // read whenever it has landed
+    }
     launchAdjustEndCell(s, g, st);
     h->shardCur = s.pred1;
     h->predFinal = s.pred1;
@@ -1232,6 +1298,11 @@ extern "C" int rtp_shard_stage_rows(rtp_handle* h, int stage, int iter, int last
   default: return fail(h, RTP_ERR_INVALID, "unknown shard stage");
   }
   CUDA_TRY(h, cudaGetLastError());
+  if (rows == RTP_ROWS_BOUNDARY)
+  {
+    CUDA_TRY(h, cudaEventRecord(h->bndDone, h->bndStream));
+    h->bndPending = true;
+  }
   return RTP_OK;
 }
 
@@ -1255,6 +1326,7 @@ extern "C" int rtp_shard_buffer(rtp_handle* h, int which, void** dptr, size_t* b
   case RTP_SHARD_BUF_POS: p = s.posA; b = 16 * M; break;
   case RTP_SHARD_BUF_VEL: p = s.velA; b = 16 * M; break;
   case RTP_SHARD_BUF_LIST_BUILD_POS: p = s.nbrBuildPos; b = 16 * M; break;
+  case RTP_SHARD_BUF_ROW_BOUNDS: p = h->rowBounds; b = 4 * sizeof(u32); break;
   case RTP_SHARD_BUF_LIST_INVALID: p = s.nbrInvalid; b = 4 * (size_t)2 * NBR_EPOCHS; break;
   default: return fail(h, RTP_ERR_INVALID, "unknown shard buffer");
   }
@@ -1306,12 +1378,23 @@ extern "C" int rtp_shard_unpack(rtp_handle* h, int buffer, const uint32_t* d_idx
   return RTP_OK;
 }
 
+extern "C" int rtp_shard_classify(rtp_handle* h, uint64_t n, uint32_t layer_below, uint32_t layer_from, uint8_t* d_below, uint8_t* d_above)
+{
+  if (!h || n > h->s.M || (n && (!d_below || !d_above)))
+    return RTP_ERR_INVALID;
+  CUDA_TRY(h, cudaSetDevice(h->cfg.device));
+  const u32* keysIn = (h->cellPlan.passes % 2 == 0) ? h->s.cellID : h->s.keysTmp; // RTP_SHARD_BUF_KEYS_IN
+  launchClassifyRows(h->s, h->g, keysIn, (u32)n, layer_below, layer_from, d_below, d_above, h->stream);
+  CUDA_TRY(h, cudaGetLastError());
+  return RTP_OK;
+}
+
 extern "C" int rtp_shard_clear_rows(rtp_handle* h, const uint32_t* d_idx, uint64_t n)
 {
   if (!h || (n && !d_idx) || n > h->s.M)
     return RTP_ERR_INVALID;
   CUDA_TRY(h, cudaSetDevice(h->cfg.device));
-  launchClearRows(h->s, d_idx, (u32)n, h->stream);
+  launchClearRows(h->s, h->g, (h->cellPlan.passes % 2 == 0) ? h->s.cellID : h->s.keysTmp, d_idx, (u32)n, h->stream);
   CUDA_TRY(h, cudaGetLastError());
   return RTP_OK;
 }
@@ -1347,7 +1430,14 @@ extern "C" int rtp_shard_set_interior(rtp_handle* h, uint32_t cell_lo, uint32_t 
   CUDA_TRY(h, cudaSetDevice(h->cfg.device));
   if (!h->rowBounds)
   {
-    const int rc = devAlloc(h, &h->rowBounds, (size_t)3);
+    const int rc = devAlloc(h, &h->rowBounds, (size_t)4);
+    if (rc == RTP_OK)
+    {
+      void* hp = nullptr;
+      CUDA_TRY(h, cudaHostAlloc(&hp, 4 * sizeof(u32), cudaHostAllocDefault));
+      memset(hp, 0, 4 * sizeof(u32));
+      h->rowBoundsHost = (volatile u32*)hp;
+    }
     if (rc != RTP_OK)
       return rc;
   }
@@ -1365,6 +1455,9 @@ static int ensureExchangeStream(rtp_handle* h)
   CUDA_TRY(h, cudaStreamCreateWithPriority(&h->exchStream, cudaStreamNonBlocking, hi)); // small kernels: ahead of the sweeps' CTAs
   CUDA_TRY(h, cudaEventCreateWithFlags(&h->exchFork, cudaEventDisableTiming));
   CUDA_TRY(h, cudaEventCreateWithFlags(&h->exchDone, cudaEventDisableTiming));
+  CUDA_TRY(h, cudaStreamCreateWithPriority(&h->bndStream, cudaStreamNonBlocking, hi));
+  CUDA_TRY(h, cudaEventCreateWithFlags(&h->bndPre, cudaEventDisableTiming));
+  CUDA_TRY(h, cudaEventCreateWithFlags(&h->bndDone, cudaEventDisableTiming));
   return RTP_OK;
 }
 
@@ -1388,7 +1481,8 @@ extern "C" int rtp_shard_exchange_fork(rtp_handle* h)
     return rc;
   if (h->exchActive)
     return fail(h, RTP_ERR_STATE, "an exchange is already open");
-  CUDA_TRY(h, cudaEventRecord(h->exchFork, h->stream));
+  // the rows that travel are boundary rows: produced by the boundary launch of the stage when the sweeps run by row phase
+  CUDA_TRY(h, cudaEventRecord(h->exchFork, h->bndPending ? h->bndStream : h->stream));
   CUDA_TRY(h, cudaStreamWaitEvent(h->exchStream, h->exchFork, 0));
   h->exchActive = true;
   return RTP_OK;
@@ -1416,7 +1510,8 @@ extern "C" int rtp_shard_exchange_join(rtp_handle* h)
   if (!h->exchPending)
     return RTP_OK;
   CUDA_TRY(h, cudaSetDevice(h->cfg.device));
-  CUDA_TRY(h, cudaStreamWaitEvent(h->stream, h->exchDone, 0));
+  // (only the boundary rows read ghosts: with sweeps by row phase, their stream waits)
+  CUDA_TRY(h, cudaStreamWaitEvent(h->rowBounds ? h->bndStream : h->stream, h->exchDone, 0));
   h->exchPending = false;
   return RTP_OK;
 }

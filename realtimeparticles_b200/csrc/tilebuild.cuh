@@ -223,11 +223,11 @@ constexpr u32 MASK_FALLBACK = 0xFFFFFFFFu;
 typedef MarginMaskBuffers MarginMask; // kernels.cuh
 
 // Filter the candidates of the CTA's 128 particles (positions P, particle of this thread: pi) against sqrt(radiusSq) and
-// write the margin mask. Every thread of the CTA must call (inactive threads: active = false). stats: optional counters
+// write the margin mask; row0 = first row of the CTA. Every thread of the CTA must call (inactive threads: active = false). stats: optional counters
 // { irregular warps, warps over the word capacity, CTAs over the tile capacity }.
 template <int TRAV>
 __device__ __forceinline__ void tileFilterToMask(TileSmem& sm, const GridParams& g, const float radiusSq, const uint2* __restrict__ table,
-    const float4* __restrict__ P, const float4 pi, const bool active, const MarginMask& mm, u32* __restrict__ stats)
+    const float4* __restrict__ P, const float4 pi, const bool active, const u32 row0, const MarginMask& mm, u32* __restrict__ stats)
 {
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int3 ci = cell3D(g, pi.x, pi.y, pi.z);
@@ -392,7 +392,7 @@ __device__ __forceinline__ void tileFilterToMask(TileSmem& sm, const GridParams&
   const bool useTiles = sm.overflow == 0u;
   if (!useTiles && tid == 0 && stats)
     atomicAdd(stats + 2, 1u);
-  const u32 gwarp = blockIdx.x * TB_WARPS + warp;
+  const u32 gwarp = row0 / 32u + warp; // (by rows, not by blockIdx: launches by row phase map their blocks, sweep.cuh)
   if (!useTiles)
   {
     if (lane == 0)

@@ -59,9 +59,10 @@ class _CudaArray:
 class CudaSlabEngine:
     """Local engine: one rtp handle (fluids model, GLOBAL box/grid) + torch views of the buffers the exchanges touch."""
 
-    ST = dict(PREDICT=0, GHOST_KEYS=1, SORT=2, DENSITY_LAMBDA=3, CORRECTION=4, VORTICITY=5, CONFINEMENT=6, XSPH=7, DROP_GHOSTS=8)
+    ST = dict(PREDICT=0, GHOST_KEYS=1, SORT=2, DENSITY_LAMBDA=3, CORRECTION=4, VORTICITY=5, CONFINEMENT=6, XSPH=7, DROP_GHOSTS=8,
+              PREDICT_FROM=9)
     BUF = dict(KEYS_IN=0, PRED_IN=1, PRED_CUR=2, LAMBDA=3, VEL_SORTED=4, VORT_NORM=5, VEL_CONFINED=6, LIST_BUILD_POS=7,
-               LIST_INVALID=8, POS=9, VEL=10)
+               LIST_INVALID=8, POS=9, VEL=10, ROW_BOUNDS=11)
     ROW = dict(PRED_IN=4, PRED_CUR=4, LAMBDA=1, VEL_SORTED=4, VORT_NORM=1, VEL_CONFINED=4, POS=4, VEL=4)
 
     def __init__(self, capacity, box, grid, device, fluid_params=None, jacobi=3):
@@ -86,7 +87,7 @@ class CudaSlabEngine:
 
     def buf(self, name):
         p, n = self.h.shard_buffer(self.BUF[name])
-        return self._view(p, n, f4=self.ROW.get(name) == 4, u32=name in ("KEYS_IN", "LIST_INVALID"))
+        return self._view(p, n, f4=self.ROW.get(name) == 4, u32=name in ("KEYS_IN", "LIST_INVALID", "ROW_BOUNDS"))
 
     def field(self, name, f4=False, u32=False):
         p = self.h.device_ptr(name)
@@ -163,6 +164,11 @@ class CudaSlabEngine:
 
     static_layout = True  # the sweeps of a sharded handle skip "no particle" rows (+inf position): see SlabDecomposition
 
+    def classify(self, n, layer_below, layer_from, below, above):
+        """below[i] / above[i] (bool tensors): row i < n holds a particle whose predicted cell x-layer is < layer_below /
+        >= layer_from (one kernel over the cell ids and p_pos)"""
+        self.h.shard_classify(n, layer_below, layer_from, below.data_ptr(), above.data_ptr())
+
     def clear_rows(self, idx):
         """the rows idx (int32, -1 = padding) hold no particle any more"""
         self.h.shard_clear_rows(idx.data_ptr(), idx.numel())
@@ -231,6 +237,8 @@ class SlabDecomposition:
                 if self.A0 <= 0:
                     raise ValueError("slab capacity too small for the ghost regions and arrival slots")
                 self._err = torch.zeros(1, dtype=torch.int64, device=e.device)
+                self._mask_l = torch.zeros(self.S, dtype=torch.bool, device=e.device)
+                self._mask_r = torch.zeros(self.S, dtype=torch.bool, device=e.device)
                 self._migrated = torch.zeros(1, dtype=torch.int64, device=e.device)
                 self._inf_rows = torch.zeros((max(self.ghost_cap, self.migrate_cap), 4), device=e.device)
                 self._inf_rows[:, :3] = float("inf")
@@ -375,6 +383,17 @@ class SlabDecomposition:
                 ph[name] = ph.get(name, 0.0) + a.elapsed_time(b)
             self.stats["phases"] = {k: round(v, 3) for k, v in ph.items()}
 
+    def _face_masks(self, layer_below, layer_from):
+        """static layout: {"l": rows of the own region holding a particle whose predicted x-layer is < layer_below,
+        "r": ... >= layer_from}"""
+        e, S = self.e, self.S
+        if hasattr(e, "classify"):
+            e.classify(S, layer_below, layer_from, self._mask_l, self._mask_r)
+            return {"l": self._mask_l, "r": self._mask_r}
+        layer = self.slab_of(e.keys_in()[:S])
+        alive = torch.isfinite(e.pos()[:S, 0])
+        return {"l": alive & (layer < layer_below), "r": alive & (layer >= layer_from)}
+
     def _compact(self, mask, cap):
         """indices of the set entries of `mask`, padded with -1 to `cap` rows (no host synchronisation), and their number"""
         return torch.nonzero_static(mask, size=cap, fill_value=-1).flatten().to(torch.int32), mask.sum()
@@ -518,12 +537,10 @@ class SlabDecomposition:
         #    them in its arrival slots
         e.set_counts(S, S)
         e.stage("PREDICT")
-        keys = e.keys_in()[:S]
-        layer = self.slab_of(keys)
-        alive = torch.isfinite(pos[:S, 0])
+        masks = self._face_masks(self.xlo, self.xhi)
         self._err += torch.isfinite(pos[A0:S, 0]).any().to(torch.int64)  # the arrival slots must be free
         for s, _ in sides:
-            idx, cnt = self._compact(alive & ((layer < self.xlo) if s == "l" else (layer >= self.xhi)), Mc)
+            idx, cnt = self._compact(masks[s], Mc)
             self._cnt_s[s].copy_(cnt.reshape(1))
             self._migrated += cnt
             self._err += (cnt > Mc).to(torch.int64) * 2
@@ -536,16 +553,17 @@ class SlabDecomposition:
             if (self.left if s == "l" else self.right) is not None:
                 pos[a:a + Mc] = self._mig_r[s][0]  # (the message is padded with "no particle" rows)
                 vel[a:a + Mc] = self._mig_r[s][1]
-        e.stage("PREDICT")  # (again: the arrivals need their prediction and cell id; same arithmetic, same bits for the rest)
+        if hasattr(e, "ST") and "PREDICT_FROM" in e.ST:
+            e.stage("PREDICT_FROM", A0)  # the arrivals need their prediction and cell id
+        else:
+            e.stage("PREDICT")  # (everything again: same arithmetic, same bits for the rest)
         self._mark("predict+migrate")
 
         # 2. halo of predicted positions into the ghost regions, sort everything by cell
-        layer = self.slab_of(e.keys_in()[:S])
-        alive = torch.isfinite(pos[:S, 0])
+        masks = self._face_masks(self.xlo + GHOST_LAYERS, self.xhi - GHOST_LAYERS)
         src, off = {}, {"l": S, "r": S + G}
         for s, _ in sides:
-            m = alive & ((layer < self.xlo + GHOST_LAYERS) if s == "l" else (layer >= self.xhi - GHOST_LAYERS))
-            src[s], c = self._compact(m, G)
+            src[s], c = self._compact(masks[s], G)
             self._err += (c > G).to(torch.int64) * 4
             e.pack("PRED_IN", src[s], self._row_s[4][s])
         yield _Exchange(*[[(self._row_s[4][s], self._row_r[4][s])] if p is not None else None for s, p in (("l", self.left), ("r", self.right))])
@@ -631,7 +649,11 @@ class SlabDecomposition:
         if not self.static:
             return
         with self.e.stream_context():
-            vals = torch.cat([self._err, self._migrated, torch.isfinite(self.e.pos()[:self.S, 0]).sum().reshape(1)]).cpu().tolist()
+            rows_err = self.e.buf("ROW_BOUNDS")[3:4].to(torch.int64) if self.overlap else torch.zeros_like(self._err)
+            vals = torch.cat([self._err, self._migrated, torch.isfinite(self.e.pos()[:self.S, 0]).sum().reshape(1), rows_err]).cpu().tolist()
+        if vals[3]:
+            raise RuntimeError("a sweep launched by row phase was sized too small for its rows (the row bounds of a step ago "
+                               "were outrun): results since the last check are invalid")
         if vals[0]:
             raise RuntimeError("slab capacity exceeded on the device (flags %d: 1 = arrival slots in use, 2 = migration message, "
                                "4 = ghost region)" % vals[0])
