@@ -568,10 +568,11 @@ def run_ours(args):
                 "whole_step": {"algorithmic_bytes_per_particle": PBF_BYTES_PER_PARTICLE_STEP,
                                "achieved": round(value / world * PBF_BYTES_PER_PARTICLE_STEP / 1e9, 1),
                                "frac": round(value / world * PBF_BYTES_PER_PARTICLE_STEP / 1e9 / peak, 4)},
-                "note": "neighbour sweeps do ~460 pair evaluations per particle on 16-64 B of compulsory traffic: instruction-"
-                        "issue bound (64-68% of peak issue slots, math-pipe throttled), far below the HBM line by construction "
-                        "(SURVEY 8d); traffic = ncu dram bytes per launch, dominated by the neighbour lists the sweep writes "
-                        "once and later sweeps read instead of re-testing 460 candidates (DESIGN.md section 5)"}
+                "note": "neighbour sweeps test ~460 candidate pairs per particle on 16-64 B of compulsory traffic: instruction-"
+                        "issue bound (ncu: 65-71% of the issue slots busy, profiles/r02_ncu_pbf130k_step.txt), far below the HBM line "
+                        "by construction (SURVEY 8d); traffic = ncu dram bytes per launch with a cold L2, dominated by the "
+                        "neighbour lists a step writes once (tile filter + build) and its seven later sweeps walk instead of "
+                        "re-testing the candidates (DESIGN.md section 5)"}
     try:
         with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
             tj = json.load(f)

@@ -337,6 +337,9 @@ RTP_API float rtp_shard_list_dmax_sq(const rtp_handle* h);
  * A step runs ALL its sweeps by row phase or none (the straggler queues of the sweeps are split by row class).
  * max_boundary_rows bounds the rows outside the interior (ghost rows + the owned rows of the face layers: the caller's
  * exchange capacities): it sizes the BOUNDARY launches; "no particle" rows are not visited by launches by row phase. */
+/* ghost layers per slab face the interior range of rtp_shard_set_interior is understood with (sharded.py: GHOST_LAYERS) */
+#define RTP_SHARD_GHOST_LAYERS 2
+
 typedef enum rtp_rows_id
 {
   RTP_ROWS_ALL = 0,

@@ -250,13 +250,13 @@ __global__ void __launch_bounds__(EW_THREADS) ghostDisplacementKernel(const floa
 // row, bounds[1] = one past the last one; bounds[2] = one past the last row that holds a particle (any cell). Pre-set to
 // 0xFFFFFFFF / 0 / 0 by the launcher (an empty interior, no particle); runs on the table BEFORE adjustEndCell caps the ends.
 // bounds[3] is the sticky error flag of the launches by row phase (sweep.cuh: a grid too small for its rows).
-__global__ void __launch_bounds__(EW_THREADS) rowPhaseBoundsKernel(const uint2* __restrict__ table, u32 numCells, u32 cellLo, u32 cellHi,
+__global__ void __launch_bounds__(EW_THREADS) rowPhaseBoundsKernel(const uint2* __restrict__ table, u32 scanLo, u32 scanHi, u32 cellLo, u32 cellHi,
     u32* __restrict__ bounds)
 {
   RTP_PDL_PROLOGUE();
-  const u32 c = blockIdx.x * EW_THREADS + threadIdx.x;
+  const u32 c = scanLo + blockIdx.x * EW_THREADS + threadIdx.x;
   u32 lo = 0xFFFFFFFFu, hi = 0u, last = 0u;
-  if (c < numCells)
+  if (c < scanHi)
   {
     const uint2 se = table[c];
     if (se.y >= se.x) // (start, LAST index) of a cell that holds particles
@@ -279,12 +279,13 @@ __global__ void __launch_bounds__(EW_THREADS) rowPhaseBoundsKernel(const uint2* 
     atomicMax(bounds + 2, last);
   }
 }
-void launchRowPhaseBounds(const DeviceState& s, const GridParams& g, u32 cellLo, u32 cellHi, u32* bounds, cudaStream_t st)
+// scanLo / scanHi: the cells that can hold a row of this handle at all (the slab's layers and its ghost layers)
+void launchRowPhaseBounds(const DeviceState& s, u32 scanLo, u32 scanHi, u32 cellLo, u32 cellHi, u32* bounds, cudaStream_t st)
 {
   cudaMemsetAsync(bounds, 0xFF, sizeof(u32), st);
   cudaMemsetAsync(bounds + 1, 0, 2 * sizeof(u32), st);
-  if (cellHi > cellLo)
-    launchKernel(rowPhaseBoundsKernel, ewBlocks(g.numCells), EW_THREADS, st, (const uint2*)s.table, g.numCells, cellLo, cellHi, bounds);
+  if (cellHi > cellLo && scanHi > scanLo)
+    launchKernel(rowPhaseBoundsKernel, ewBlocks(scanHi - scanLo), EW_THREADS, st, (const uint2*)s.table, scanLo, scanHi, cellLo, cellHi, bounds);
 }
 
 // slab decomposition: which rows hold a particle whose cell x-layer (key / plane, the +x wall index clamped into the last
@@ -367,9 +368,12 @@ void launchResetIds(const DeviceState& s, u32 numCells, cudaStream_t st)
 {
   launchKernel(resetIdsKernel, ewBlocks(s.M), EW_THREADS, st, s.cellID, s.cameraDist, s.perm, s.cameraPerm, s.M, numCells);
 }
-void launchAdjustEndCell(const DeviceState& s, const GridParams& g, cudaStream_t st)
+void launchAdjustEndCell(const DeviceState& s, const GridParams& g, cudaStream_t st, u32 cellLo, u32 cellHi)
 {
-  launchKernel(adjustEndCellKernel, ewBlocks(g.numCells), EW_THREADS, st, s.table, g.numCells, g.maxPartsInCell);
+  // (a slab only looks at the cells that can hold one of its rows)
+  cellHi = min(cellHi, g.numCells);
+  if (cellHi > cellLo)
+    launchKernel(adjustEndCellKernel, ewBlocks(cellHi - cellLo), EW_THREADS, st, s.table + cellLo, cellHi - cellLo, g.maxPartsInCell);
 }
 void launchFillCameraDist(const DeviceState& s, const float cam[3], u32* keysOut, cudaStream_t st)
 {

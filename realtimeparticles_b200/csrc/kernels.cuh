@@ -91,7 +91,7 @@ struct FluidStepParams
 
 // ---- grid.cu
 void launchSelftestMath(u32 lo, u32 hi, unsigned long long* bad, cudaStream_t st);
-void launchRowPhaseBounds(const DeviceState& s, const GridParams& g, u32 cellLo, u32 cellHi, u32* bounds, cudaStream_t st);
+void launchRowPhaseBounds(const DeviceState& s, u32 scanLo, u32 scanHi, u32 cellLo, u32 cellHi, u32* bounds, cudaStream_t st);
 void launchClassifyRows(const DeviceState& s, const GridParams& g, const u32* keys, u32 n, u32 cutLo, u32 cutHi, unsigned char* below,
     unsigned char* above, cudaStream_t st);
 void launchClearRows(const DeviceState& s, const GridParams& g, u32* keys, const u32* idx, u32 n, cudaStream_t st);
@@ -102,7 +102,7 @@ void launchGhostDisplacement(const DeviceState& s, const float4* pred, const u32
 void launchGhostFlags(const DeviceState& s, u32* keysOut, cudaStream_t st);
 void launchCompactGather(const DeviceState& s, const u32* order, u32 n, cudaStream_t st);
 void launchResetIds(const DeviceState& s, u32 numCells, cudaStream_t st);
-void launchAdjustEndCell(const DeviceState& s, const GridParams& g, cudaStream_t st);
+void launchAdjustEndCell(const DeviceState& s, const GridParams& g, cudaStream_t st, u32 cellLo = 0, u32 cellHi = 0xFFFFFFFFu);
 void launchFillCameraDist(const DeviceState& s, const float cam[3], u32* keysOut, cudaStream_t st);
 void launchCameraGather(const DeviceState& s, int model, const float4* pred, float4* predOut, cudaStream_t st);
 void launchGridDetector(const DeviceState& s, const GridParams& g, cudaStream_t st); // reset + fill (2 launches)

@@ -1165,7 +1165,7 @@ extern "C" int rtp_shard_stage_rows(rtp_handle* h, int stage, int iter, int last
       && (stage == RTP_SHARD_XSPH || (stage == RTP_SHARD_CORRECTION && last && !h->fp.f.isVorticityConfEnabled));
   sPhase.rowPhaseBlocks = rows == RTP_ROWS_BOUNDARY && !sPhase.rowPhaseToEnd
       ? min(allBlocks, (h->maxBoundaryRows + SWEEP_BLOCK_ROWS - 1) / SWEEP_BLOCK_ROWS + 3u) : allBlocks;
-  if (rows != RTP_ROWS_ALL && h->rowBoundsHost && !sPhase.rowPhaseToEnd)
+  if (rows != RTP_ROWS_ALL && h->rowBoundsHost)
   {
     // tighter: the bounds of a recent step (copied to the host without synchronisation, a step or two old) plus a margin the
     // populations cannot outrun in that time; a launch that turns out too small raises rowBounds[3] (sweep.cuh), which the
@@ -1175,7 +1175,8 @@ extern "C" int rtp_shard_stage_rows(rtp_handle* h, int stage, int iter, int last
     if (nr != 0u && nr <= h->s.N && b0 < b1 && b1 <= nr)
     {
       const u32 i0 = (b0 + SWEEP_BLOCK_ROWS - 1) / SWEEP_BLOCK_ROWS, i1 = b1 / SWEEP_BLOCK_ROWS, nb = (nr + SWEEP_BLOCK_ROWS - 1) / SWEEP_BLOCK_ROWS;
-      const u32 want = rows == RTP_ROWS_INTERIOR ? (i1 > i0 ? i1 - i0 : 0u) + margin : i0 + (nb > i1 ? nb - i1 : 0u) + 2u * margin;
+      const u32 end = sPhase.rowPhaseToEnd ? allBlocks : nb; // (to the end: the rows without a particle too)
+      const u32 want = rows == RTP_ROWS_INTERIOR ? (i1 > i0 ? i1 - i0 : 0u) + margin : i0 + (end > i1 ? end - i1 : 0u) + 2u * margin;
       sPhase.rowPhaseBlocks = min(sPhase.rowPhaseBlocks, want);
     }
   }
@@ -1249,10 +1250,15 @@ extern "C" int rtp_shard_stage_rows(rtp_handle* h, int stage, int iter, int last
     launchFluidGather(s, g, st);
     if (h->rowBounds)
     {
-      launchRowPhaseBounds(s, g, h->interiorCellLo, h->interiorCellHi, h->rowBounds, st);
+      // the slab's rows live in the interior layers, two face layers and two ghost layers per side
+      const u32 plane = (u32)(g.res[1] * g.res[2]), reach = 2u * RTP_SHARD_GHOST_LAYERS * plane;
+      const u32 scanLo = h->interiorCellLo > reach ? h->interiorCellLo - reach : 0u, scanHi = min(g.numCells, h->interiorCellHi + reach);
+      launchRowPhaseBounds(s, scanLo, scanHi, h->interiorCellLo, h->interiorCellHi, h->rowBounds, st);
       cudaMemcpyAsync((void*)h->rowBoundsHost, h->rowBounds, 3 * sizeof(u32), cudaMemcpyDeviceToHost, st); // read whenever it has landed
+      launchAdjustEndCell(s, g, st, scanLo, scanHi);
     }
-    launchAdjustEndCell(s, g, st);
+    else
+      launchAdjustEndCell(s, g, st);
     h->shardCur = s.pred1;
     h->predFinal = s.pred1;
     break;
@@ -1442,7 +1448,7 @@ extern "C" int rtp_shard_set_interior(rtp_handle* h, uint32_t cell_lo, uint32_t 
       return rc;
   }
   h->interiorCellLo = cell_lo, h->interiorCellHi = cell_hi;
-  launchRowPhaseBounds(h->s, h->g, 0, 0, h->rowBounds, h->stream); // empty interior, no rows until the next RTP_SHARD_SORT
+  launchRowPhaseBounds(h->s, 0, 0, 0, 0, h->rowBounds, h->stream); // empty interior, no rows until the next RTP_SHARD_SORT
   return RTP_OK;
 }
 
