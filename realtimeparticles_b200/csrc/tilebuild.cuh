@@ -15,8 +15,10 @@
 //   shared memory with 1-D TMA bulk copies (cp.async.bulk, one per segment, completion on an mbarrier). The resident
 //   CTAs of an SM are in different phases, so the copies of one run under the filter of the others.
 //  FILTER. Every lane tests ALL candidates of its warp's window in lock step: the candidate is one broadcast LDS.128 for
-//   the whole warp, the test the squared distance against the list radius (3 FADD, FMUL, 2 FFMA, FSETP), the result one
-//   bit of a 32-candidate mask word. No divergence, no per-lane addresses. Candidates of the window outside the lane's
+//   the whole warp, the test three FFMAs and an FSETP: a stage's positions are rewritten in place, right after the copy, as
+//   (c - origin, |c - origin|^2) with origin = the CTA's first particle, and |c'|^2 - 2 p'.c' is compared with a per-lane
+//   threshold r^2 - |p'|^2 raised by four times the rounding bound (a superset of the exact test; the walk that follows
+//   applies the exact support test anyway). The result is one bit of a 32-candidate mask word. No divergence, no per-lane addresses. Candidates of the window outside the lane's
 //   own run (another lane's cell) are removed per word with a range mask, so a lane keeps exactly the reference's
 //   candidate set; words no lane needs (a hole between two families of runs) are skipped.
 //  MASKS. The words go straight to global memory (one coalesced 128-byte row per word and warp) as the MARGIN MASK of the
@@ -62,6 +64,7 @@ struct __align__(16) TileSmem
   u32 nStages;
   u32 stageHasData;
   u32 overflow;
+  float4 origin; // the filter works in coordinates relative to the CTA's first particle (see FILTER)
   unsigned long long bar;
 };
 
@@ -238,6 +241,8 @@ __device__ __forceinline__ void tileFilterToMask(TileSmem& sm, const GridParams&
   if (tid == 0)
   {
     sm.overflow = 0u;
+    const float4 o = P[row0];
+    sm.origin = (isfinite(o.x) && isfinite(o.y) && isfinite(o.z)) ? o : make_float4(0.f, 0.f, 0.f, 0.f);
     mbarInit(&sm.bar, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -426,7 +431,11 @@ __device__ __forceinline__ void tileFilterToMask(TileSmem& sm, const GridParams&
 
   // (clouds: the filter uses the shifted centre pi - shift, one rounding away from the canonical (pi - pj) - shift; the
   //  list radius has 12 % of slack and the caller applies the exact support test)
-  const float filterSq = radiusSq;
+  // The test runs on |c'|^2 - 2 p'.c' < r^2 - |p'|^2 (p', c' relative to the CTA's first particle): its rounding error is
+  // bounded by a few ulp of D^2, D = |p'| + 6 r >= the distance of the lane's own candidates from the origin, and the
+  // threshold is raised by 2e-6 D^2 (four times that bound): the mask is a superset of the canonical sq < radiusSq.
+  const float4 org = sm.origin;
+  const float filterSq = radiusSq, sixR = 6.0f * sqrtf(radiusSq);
 
   u32 wordsOut = 0u;
   const size_t wordBase = (size_t)gwarp * mm.wordCap;
@@ -444,6 +453,21 @@ __device__ __forceinline__ void tileFilterToMask(TileSmem& sm, const GridParams&
         continue;
       mbarWait(&sm.bar, phase);
       phase ^= 1u;
+      {
+        // staged positions -> (c - origin, |c - origin|^2): the filter's squared distance becomes three FFMAs per candidate
+        const u32 lastCol = sm.stageFirst[stage + 1] - 1u;
+        const u32 staged = sm.colOff[lastCol] + sm.colLen[lastCol];
+        for (u32 j = (u32)tid; j < staged; j += (u32)TB_THREADS)
+        {
+          float4 q = sm.tile[j];
+          q.x -= org.x;
+          q.y -= org.y;
+          q.z -= org.z;
+          q.w = fmaf(q.z, q.z, fmaf(q.y, q.y, q.x * q.x));
+          sm.tile[j] = q;
+        }
+        __syncthreads();
+      }
       if (!warpRegular)
         continue;
       const float4* tileBuf = sm.tile;
@@ -469,6 +493,10 @@ __device__ __forceinline__ void tileFilterToMask(TileSmem& sm, const GridParams&
           const u32 e0 = !in ? 0u : (kind == 0 ? re[0] : (kind == 1 ? re[1] : re[2]));
           const u32 tileBase = tileIndex(col, wl.x);
           const u32 nW = ((wl.y - wl.x) >> 5) + 1u;
+          const float ppx = px - org.x, ppy = py - org.y, ppz = pz - org.z;
+          const float n2 = fmaf(ppz, ppz, fmaf(ppy, ppy, ppx * ppx)), D = sqrtf(n2) + sixR;
+          const float thr = (filterSq + 2e-6f * D * D) - n2;
+          const float ax = -2.0f * ppx, ay = -2.0f * ppy, az = -2.0f * ppz;
 #pragma unroll 1
           for (u32 w = 0; w < nW; ++w)
           {
@@ -488,9 +516,7 @@ __device__ __forceinline__ void tileFilterToMask(TileSmem& sm, const GridParams&
             for (int k = 0; k < 32; ++k)
             {
               const float4 q = tp[k];
-              const float dx = px - q.x, dy = py - q.y, dz = pz - q.z;
-              const float sq = dot3c(dx, dy, dz, dx, dy, dz);
-              if (sq < filterSq)
+              if (fmaf(ax, q.x, fmaf(ay, q.y, fmaf(az, q.z, q.w))) < thr)
                 m |= 1u << k;
             }
             if (wordsOut < mm.wordCap)
