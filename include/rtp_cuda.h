@@ -353,6 +353,36 @@ RTP_API int rtp_shard_exchange_fork(rtp_handle* h);
 RTP_API int rtp_shard_exchange_done(rtp_handle* h);
 RTP_API int rtp_shard_exchange_join(rtp_handle* h);
 
+/* ---- the slab decomposition driven from inside the library (csrc/slab_group.cu) ----
+ * One host thread, `nslabs` slabs of the GLOBAL box along x, slab r on CUDA device dev_ids[r] (ids may repeat: several
+ * slabs on one GPU -- how the 1-GPU tests run it). Each slab is an rtp handle of `slab_capacity` rows in the static row
+ * layout described above rtp_shard_stage_id / in realtimeparticles_b200/sharded.py: own region, arrival slots, one ghost
+ * region of ghost_cap rows per face (0: slab_capacity / 8; migrate_cap 0: ghost_cap / 4). A step is the same sequence
+ * sharded.py runs -- predict, migrate, halo, joint sort, 2I+3 ghost refreshes, compaction -- and the transport is a PULL over
+ * peer memory: the receiving slab copies its neighbour's packed rows with cudaMemcpyAsync (NVLink between GPUs), ordered
+ * by events between the slabs' streams. overlap != 0: the refreshes travel on the slabs' exchange streams while the next
+ * sweep runs its interior rows (rtp_shard_stage_rows). rtp_slab_group_step only ENQUEUES; nothing synchronises with the
+ * host until rtp_slab_group_sync / _check / _download. Bit-identical to the Python orchestration (tests/test_sharded.py). */
+typedef struct rtp_slab_group rtp_slab_group;
+RTP_API int rtp_slab_group_create(rtp_slab_group** out, int nslabs, const int* dev_ids, uint64_t slab_capacity, const uint32_t box[3],
+    const uint32_t grid[3], uint64_t ghost_cap, uint64_t migrate_cap, int overlap);
+RTP_API void rtp_slab_group_destroy(rtp_slab_group* g);
+RTP_API const char* rtp_slab_group_last_error(const rtp_slab_group* g); /* g may be NULL: error of the last failed create */
+RTP_API int rtp_slab_group_size(const rtp_slab_group* g);
+/* the rtp handle of one slab (fields in cell-sorted order incl. ghosts: diagnostics, rtp_download of p_density ...) */
+RTP_API int rtp_slab_group_handle(rtp_slab_group* g, int slab, rtp_handle** h);
+RTP_API int rtp_slab_group_set_fluid_params(rtp_slab_group* g, const rtp_fluid_params* fluid, int nb_jacobi_iters);
+/* the full initial state (host, float4 rows); every slab keeps the particles whose cell x-layer it owns */
+RTP_API int rtp_slab_group_upload(rtp_slab_group* g, const float* pos_xyzw, const float* vel_xyzw, uint64_t n);
+RTP_API int rtp_slab_group_step(rtp_slab_group* g, int nsteps);
+RTP_API int rtp_slab_group_sync(rtp_slab_group* g);
+/* synchronises and reads the device-side capacity flags: RTP_ERR_COMM when a ghost region, a migration message or the
+ * arrival slots overflowed since the last check (results are then invalid); migrated_total: particles that changed slab */
+RTP_API int rtp_slab_group_check(rtp_slab_group* g, uint64_t* migrated_total);
+/* all particles, slab by slab (inside a slab: cell-sorted); returns their number or a negative rtp_status;
+ * per_slab (optional): nslabs counts */
+RTP_API int64_t rtp_slab_group_download(rtp_slab_group* g, float* pos_xyzw, float* vel_xyzw, uint64_t capacity_rows, uint64_t* per_slab);
+
 #ifdef __cplusplus
 }
 #endif

@@ -11,7 +11,7 @@ import numpy as np
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("RTP_CUDA_LIB") or os.path.join(_HERE, "lib", "librtp_cuda.so")  # override: A/B builds
 
-RTP_OK = 0
+RTP_OK, RTP_ERR_INVALID, RTP_ERR_CUDA, RTP_ERR_STATE, RTP_ERR_COMM = 0, -1, -2, -3, -4
 
 # rtp_model
 BOIDS, FLUIDS, CLOUDS = 0, 1, 2
@@ -83,7 +83,10 @@ EXPORTS = ["rtp_abi_version", "rtp_device_count", "rtp_create", "rtp_destroy", "
            "rtp_last_launch_count", "rtp_list_stats", "rtp_shard_set_owned", "rtp_shard_stage", "rtp_shard_buffer", "rtp_shard_list_dmax_sq", "rtp_shard_pack", "rtp_shard_unpack", "rtp_shard_clear_rows", "rtp_shard_inverse_perm", "rtp_shard_check_ghosts",
            "rtp_shard_classify", "rtp_shard_set_interior", "rtp_shard_stage_rows", "rtp_shard_exchange_stream", "rtp_shard_exchange_fork", "rtp_shard_exchange_done", "rtp_shard_exchange_join",
            "rtp_gen_box_grid", "rtp_gen_sphere_grid", "rtp_gen_rectangle_grid", "rtp_gen_circle_grid", "rtp_gen_random_box",
-           "rtp_baked_constant", "rtp_register_gl", "rtp_unregister_gl", "rtp_target_create", "rtp_target_destroy", "rtp_target_update"]
+           "rtp_baked_constant", "rtp_register_gl", "rtp_unregister_gl", "rtp_target_create", "rtp_target_destroy", "rtp_target_update",
+           "rtp_slab_group_create", "rtp_slab_group_destroy", "rtp_slab_group_last_error", "rtp_slab_group_size", "rtp_slab_group_handle",
+           "rtp_slab_group_set_fluid_params", "rtp_slab_group_upload", "rtp_slab_group_step", "rtp_slab_group_sync", "rtp_slab_group_check",
+           "rtp_slab_group_download"]
 
 _lib = None
 
@@ -157,6 +160,20 @@ def lib():
     L.rtp_gen_random_box.restype = C.c_int64
     L.rtp_baked_constant.argtypes = [C.c_float]
     L.rtp_baked_constant.restype = C.c_float
+    L.rtp_slab_group_create.argtypes = [C.POINTER(vp), C.c_int, C.POINTER(C.c_int), C.c_uint64, u32p, u32p, C.c_uint64, C.c_uint64, C.c_int]
+    L.rtp_slab_group_destroy.argtypes = [vp]
+    L.rtp_slab_group_destroy.restype = None
+    L.rtp_slab_group_last_error.argtypes = [vp]
+    L.rtp_slab_group_last_error.restype = C.c_char_p
+    L.rtp_slab_group_size.argtypes = [vp]
+    L.rtp_slab_group_handle.argtypes = [vp, C.c_int, C.POINTER(vp)]
+    L.rtp_slab_group_set_fluid_params.argtypes = [vp, C.POINTER(FluidParams), C.c_int]
+    L.rtp_slab_group_upload.argtypes = [vp, vp, vp, C.c_uint64]
+    L.rtp_slab_group_step.argtypes = [vp, C.c_int]
+    L.rtp_slab_group_sync.argtypes = [vp]
+    L.rtp_slab_group_check.argtypes = [vp, C.POINTER(C.c_uint64)]
+    L.rtp_slab_group_download.argtypes = [vp, vp, vp, C.c_uint64, C.POINTER(C.c_uint64)]
+    L.rtp_slab_group_download.restype = C.c_int64
     _lib = L
     return L
 
@@ -452,3 +469,61 @@ def gen_random_box(n, start, end, seed=1):
 
 def baked_constant(v):
     return float(lib().rtp_baked_constant(float(v)))
+
+
+class SlabGroup:
+    """rtp_slab_group: the x-slab decomposition of the PBF step driven from inside the library by ONE host thread
+    (csrc/slab_group.cu); slab r lives on CUDA device devices[r] (ids may repeat). Same step, same bits as
+    realtimeparticles_b200.sharded.SlabDecomposition over its transports."""
+
+    def __init__(self, devices, slab_capacity, box, grid, ghost_cap=0, migrate_cap=0, overlap=True, fluid_params=None, jacobi=3):
+        self.L = lib()
+        g = C.c_void_p()
+        devs = (C.c_int * len(devices))(*[int(d) for d in devices])
+        rc = self.L.rtp_slab_group_create(C.byref(g), len(devices), devs, int(slab_capacity), (C.c_uint32 * 3)(*box), (C.c_uint32 * 3)(*grid),
+                                          int(ghost_cap), int(migrate_cap), int(bool(overlap)))
+        if rc != RTP_OK:
+            raise RtpError("rtp_slab_group_create failed (%d): %s" % (rc, (self.L.rtp_slab_group_last_error(None) or b"").decode()))
+        self.g = g
+        self.n_slabs = len(devices)
+        fp = fluid_params or FluidParams(450.0, 600.0, 0.010, 3, 1, 0.006, 0.001, 4, 1, 0.0004, 0.0001)
+        self._check(self.L.rtp_slab_group_set_fluid_params(self.g, C.byref(fp), int(jacobi)), "rtp_slab_group_set_fluid_params")
+
+    def close(self):
+        if getattr(self, "g", None):
+            self.L.rtp_slab_group_destroy(self.g)
+            self.g = None
+
+    def __del__(self):
+        self.close()
+
+    def _check(self, rc, what):
+        if rc < 0:
+            raise RtpError("%s failed (%d): %s" % (what, rc, (self.L.rtp_slab_group_last_error(self.g) or b"").decode()))
+        return rc
+
+    def upload(self, pos, vel):
+        pos = np.ascontiguousarray(pos, np.float32)
+        vel = np.ascontiguousarray(vel, np.float32)
+        assert pos.shape == vel.shape and pos.shape[1] == 4
+        self._n = len(pos)
+        self._check(self.L.rtp_slab_group_upload(self.g, pos.ctypes.data, vel.ctypes.data, len(pos)), "rtp_slab_group_upload")
+
+    def step(self, n=1):
+        self._check(self.L.rtp_slab_group_step(self.g, int(n)), "rtp_slab_group_step")
+
+    def sync(self):
+        self._check(self.L.rtp_slab_group_sync(self.g), "rtp_slab_group_sync")
+
+    def check(self):
+        m = C.c_uint64(0)
+        self._check(self.L.rtp_slab_group_check(self.g, C.byref(m)), "rtp_slab_group_check")
+        return int(m.value)
+
+    def download(self):
+        """(pos, vel, particles per slab): all particles, slab by slab"""
+        pos = np.empty((self._n, 4), np.float32)
+        vel = np.empty((self._n, 4), np.float32)
+        per = (C.c_uint64 * self.n_slabs)()
+        n = self._check(self.L.rtp_slab_group_download(self.g, pos.ctypes.data, vel.ctypes.data, self._n, per), "rtp_slab_group_download")
+        return pos[:n], vel[:n], [int(x) for x in per]

@@ -127,6 +127,67 @@ def test_slab_decomposition_on_one_device_matches_single_handle(world):
 
 
 @pytest.mark.gpu
+@pytest.mark.parametrize("world,overlap", [(3, True), (2, False)])
+def test_library_slab_group_same_bits_as_python_orchestration(world, overlap):
+    # rtp_slab_group (csrc/slab_group.cu: one host thread, slabs pulling their neighbours' rows over peer memory, ordered by
+    # events) against SlabDecomposition over LocalSlabGroup (the step bench.py runs over NCCL): the same launches on the same
+    # rows in the same order -- bit-identical particles, slab by slab. All slabs on device 0: runs on a 1-GPU lease.
+    from realtimeparticles_b200 import sharded
+    pos0 = _dam((48, 32, 32), end=(3.0, 0.0, 0.0))
+    vel0 = _drift(pos0)
+    steps, jacobi, n = 8, 3, len(pos0)
+    grp, sds = _local_group(lambda: sharded.CudaSlabEngine(n, BOX, GRID, 0, jacobi=jacobi), world, pos0, vel0,
+                            lambda a: torch.from_numpy(a).cuda(), overlap=overlap)
+    for _ in range(steps):
+        grp.step()
+    ref = [tuple(t.cpu().numpy() for t in sd.owned_state()) for sd in sds]
+    ref_migrated = sum(sd.stats.get("migrated_out_total", 0) for sd in sds)
+    sg = _abi.SlabGroup([0] * world, n, BOX, GRID, overlap=overlap, jacobi=jacobi)
+    sg.upload(pos0, vel0)
+    sg.step(steps)
+    migrated = sg.check()
+    pos, vel, per = sg.download()
+    assert per == [len(p) for p, _ in ref] and sum(per) == n and migrated == ref_migrated and migrated > 0
+    o = 0
+    for (p, v), k in zip(ref, per):
+        assert np.array_equal(pos[o:o + k], p) and np.array_equal(vel[o:o + k], v)
+        o += k
+
+
+@pytest.mark.gpu
+def test_library_slab_group_one_slab_equals_rtp_step():
+    pos0 = _dam((32, 32, 16))
+    n = len(pos0)
+    sg = _abi.SlabGroup([0], n + 4096, BOX, GRID, jacobi=3)  # (rows behind the particles hold no particle)
+    sg.upload(pos0, np.zeros((n, 4), np.float32))
+    sg.step(4)
+    pos, vel, per = sg.download()
+    h = _abi.Handle(_abi.FLUIDS, n, n, BOX, GRID)
+    h.set_fluid_params(_abi.FluidParams(450.0, 600.0, 0.010, 3, 1, 0.006, 0.001, 4, 1, 0.0004, 0.0001), 3)
+    h.upload("p_pos", pos0)
+    h.upload("p_vel", np.zeros((n, 4), np.float32))
+    h.reset_ids()
+    h.step_n(4, _abi.STEP_PHYSICS)
+    h.sync()
+    assert per == [n] and np.array_equal(pos, h.download("p_pos")) and np.array_equal(vel, h.download("p_vel"))
+
+
+def test_library_slab_group_fails_loudly_without_a_device_or_with_bad_arguments():
+    L = _abi.lib()
+    import ctypes as C
+    g = C.c_void_p()
+    box, grid = (C.c_uint32 * 3)(*BOX), (C.c_uint32 * 3)(*GRID)
+    assert L.rtp_slab_group_create(C.byref(g), 0, (C.c_int * 1)(0), 1000, box, grid, 0, 0, 1) == _abi.RTP_ERR_INVALID
+    # 16 slabs over 30 x-layers: thinner than two ghost layers per face
+    rc = L.rtp_slab_group_create(C.byref(g), 16, (C.c_int * 16)(*([0] * 16)), 100000, box, grid, 0, 0, 1)
+    assert rc in (_abi.RTP_ERR_INVALID, _abi.RTP_ERR_CUDA) and not g.value  # (no device: the first rtp_create fails)
+    assert L.rtp_slab_group_last_error(None)
+    if L.rtp_device_count() == 0:
+        with pytest.raises(_abi.RtpError):
+            _abi.SlabGroup([0, 0], 100000, BOX, GRID)
+
+
+@pytest.mark.gpu
 def test_refresh_overlapped_with_interior_sweeps_same_bits():
     # the ghost refresh of a stage travelling on the exchange stream while the next stage sweeps its interior rows
     # (rtp_shard_stage_rows INTERIOR / BOUNDARY, split straggler queues) is a re-ordering of launches only: same bits as
