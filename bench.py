@@ -442,6 +442,23 @@ def run_slab_16m(args, torch, abi, rank, local_rank, world, steps=10, warmup=8):
     return out
 
 
+def run_slab_group_library(world, one_gpu):
+    """`rtp_headless slabs <world>`: the 16.7M-particle dam on `world` slabs / GPUs driven by rtp_slab_group (C ABI, one host
+    thread, no Python, no NCCL), same step window (steps 10-19); ms_per_step is HOST wall clock (enqueue + drain)."""
+    import subprocess
+    exe = os.path.join(ROOT, "realtimeparticles_b200", "lib", "rtp_headless")
+    try:
+        r = subprocess.run([exe, "slabs", str(world), "10", "9"], capture_output=True, text=True, timeout=240)
+        d = json.loads(r.stdout.strip().splitlines()[-1])
+    except Exception as e:
+        return {"error": repr(e)[:300]}
+    if one_gpu:
+        d["strong_scaling_efficiency"] = round(one_gpu["ms_per_step"] / (world * d["ms_per_step"]), 4)
+        ke = one_gpu["invariants"]["kinetic_energy"]
+        d["kinetic_energy_vs_one_gpu"] = abs(d["kinetic_energy"] - ke) / ke
+    return d
+
+
 def run_ours(args):
     import numpy as np
     import torch
@@ -525,8 +542,17 @@ def run_ours(args):
                 slab["one_gpu_same_window"] = {k: one[k] for k in ("ms_per_step", "value", "invariants")}
                 slab["strong_scaling_efficiency"] = round(one["ms_per_step"] / (world * slab["ms_per_step"]), 4)
             dist.barrier()
+            # the same decomposition driven from inside the library by ONE host thread (rtp_slab_group, csrc/slab_group.cu:
+            # slabs pull their neighbours' rows over peer memory) through the C++ headless harness, on all GPUs of the box;
+            # the other ranks wait on a CPU-side (gloo) barrier so that no NCCL kernel spins on their GPUs meanwhile
+            torch.cuda.empty_cache()
+            cpu_group = dist.new_group(backend="gloo")
+            dist.barrier(group=cpu_group)
+            if rank == 0:
+                slab["library_driver"] = run_slab_group_library(world, slab.get("one_gpu_same_window"))
+            dist.barrier(group=cpu_group)
         except Exception as e:  # keep the headline line even if the large config cannot run here
-            slab = {"error": repr(e)[:300]}
+            slab = dict(slab or {}, error=repr(e)[:300])
         flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
         h, pos0 = make_pbf(abi, local_rank)
         stream = torch.cuda.ExternalStream(h.stream(), device=dev)
@@ -686,6 +712,7 @@ def run_ours(args):
         "roofline": roofline, "kernels": kernels, "kernels_window": kernels_window, "cpu_baseline": cpu, "clocks": sampler.result(),
         "other_workloads": others, "slab_16m": slab,
         "slab_16m_strong_scaling_efficiency": (slab or {}).get("strong_scaling_efficiency"),
+        "slab_16m_library_driver_strong_scaling_efficiency": ((slab or {}).get("library_driver") or {}).get("strong_scaling_efficiency"),
         "wall_s_timed_region": round(t_wall, 3),
     }
     print(json.dumps(out), flush=True)
