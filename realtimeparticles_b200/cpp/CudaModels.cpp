@@ -1,5 +1,7 @@
-// CudaModels.cpp -- host orchestration of the CUDA models; mirrors physics/ocl/{Boids,Fluids,Clouds}.cpp with every
-// Context:: call replaced by one C-ABI call. Presets and JSON handling follow the reference line by line (cited).
+// CudaModels.cpp -- host orchestration of the CUDA models: the reference-side binding of librtp_cuda.so. It has to
+// reproduce what physics/ocl/{Boids,Fluids,Clouds}.cpp do around their kernels -- JSON keys and parsing rules, the POD
+// parameter blocks, the initial states of every preset -- so those values are the reference's (cited); every Context::
+// call becomes one C-ABI call, and the presets are data tables (Preset / Lattice / Region below) instead of switch blocks.
 #include "CudaModels.hpp"
 
 #include "Geometry.hpp"
@@ -128,19 +130,131 @@ void Boids::transferKernelInputsToGPU()
       isTargetActivated() ? 1 : 0);
 }
 
+// ---- initial states as data: a lattice is a particle count, a shape and a region given per axis as (num * box) / den --
+// the reference spells its regions as box fractions (Boids.cpp:277-321, Fluids.cpp:273-398, Clouds.cpp:401-501); keeping the
+// operation (one multiplication by a small integer, one division) keeps the corner coordinates bit-identical.
+namespace
+{
+struct Frac
+{
+  float num, den;
+  float of(float box) const { return num * box / den; }
+};
+constexpr Frac ZERO { 0.0f, 1.0f };
+struct Region
+{
+  Frac lo[3], hi[3];
+  Math::float3 start(const Geometry::BoxSize3D& b) const { return { lo[0].of((float)b.x), lo[1].of((float)b.y), lo[2].of((float)b.z) }; }
+  Math::float3 end(const Geometry::BoxSize3D& b) const { return { hi[0].of((float)b.x), hi[1].of((float)b.y), hi[2].of((float)b.z) }; }
+};
+enum LatticeShape
+{
+  LATTICE_BOX, // 3D box / 2D rectangle
+  LATTICE_ROUND // 3D sphere / 2D circle
+};
+struct Lattice
+{
+  int count; // Utils::NbParticles, 0 = no such lattice; the subdivision follows from it unless res is given
+  LatticeShape shape;
+  Region region;
+  int res[3]; // explicit subdivision (2D: res[0], res[1]) or { 0, 0, 0 }
+};
+struct Preset
+{
+  Utils::PhysicsCase pcase;
+  Lattice main, extra; // extra: a second lattice appended to the first (the pool under the drop)
+};
+
+std::vector<Math::float3> generate(const Lattice& l, bool dim2D, const Geometry::BoxSize3D& box,
+    Geometry::Distribution dist = Geometry::Distribution::Uniform)
+{
+  const Math::float3 a = l.region.start(box), b = l.region.end(box);
+  if (dim2D)
+  {
+    Math::int2 res = { l.res[0], l.res[1] };
+    if (!l.res[0])
+    {
+      const auto& sub = Utils::GetNbParticlesSubdiv2D((Utils::NbParticles)l.count);
+      res = { sub[0], sub[1] };
+    }
+    return Geometry::Generate2DGrid(l.shape == LATTICE_ROUND ? Geometry::Shape2D::Circle : Geometry::Shape2D::Rectangle, Geometry::Plane::YZ, res, a, b, dist);
+  }
+  Math::int3 res = { l.res[0], l.res[1], l.res[2] };
+  if (!l.res[0])
+  {
+    const auto& sub = Utils::GetNbParticlesSubdiv3D((Utils::NbParticles)l.count);
+    res = { sub[0], sub[1], sub[2] };
+  }
+  return Geometry::Generate3DGrid(l.shape == LATTICE_ROUND ? Geometry::Shape3D::Sphere : Geometry::Shape3D::Box, res, a, b, dist);
+}
+
+// particles of a preset (main lattice + optional extra one); nb = their nominal number
+std::vector<Math::float3> generate(const Preset& p, bool dim2D, const Geometry::BoxSize3D& box, size_t& nb,
+    Geometry::Distribution dist = Geometry::Distribution::Uniform)
+{
+  std::vector<Math::float3> verts = generate(p.main, dim2D, box, dist);
+  nb = (size_t)p.main.count;
+  if (p.extra.count)
+  {
+    const auto more = generate(p.extra, dim2D, box, dist);
+    verts.insert(verts.end(), more.begin(), more.end());
+    nb += (size_t)p.extra.count;
+  }
+  return verts;
+}
+
+template <size_t N>
+const Preset* findPreset(const Preset (&table)[N], Utils::PhysicsCase pcase)
+{
+  for (const Preset& p : table)
+    if (p.pcase == pcase)
+      return &p;
+  return nullptr;
+}
+
+constexpr Lattice NONE { 0, LATTICE_BOX, { { ZERO, ZERO, ZERO }, { ZERO, ZERO, ZERO } }, { 0, 0, 0 } };
+using NP = Utils::NbParticles;
+using PC = Utils::PhysicsCase;
+
+// boids: a ball (3D) / disc (2D, YZ plane) of a third of the box around the centre; the case only sets the count
+constexpr Region BOIDS_3D { { { 1, -6 }, { 1, -6 }, { 1, -6 } }, { { 1, 6 }, { 1, 6 }, { 1, 6 } } };
+constexpr Region BOIDS_2D { { ZERO, { 1, -6 }, { 1, -6 } }, { ZERO, { 1, 6 }, { 1, 6 } } };
+constexpr struct { PC pcase; int count; } BOIDS_COUNTS[] = { { PC::BOIDS_SMALL, NP::P512 }, { PC::BOIDS_MEDIUM, NP::P16K },
+  { PC::BOIDS_LARGE, NP::P65K }, { PC::BOIDS_XLARGE, NP::P130K } };
+
+// fluids: dam (the -x half of the lower half), bomb (a ball in the centre), drop (a block above a pool)
+constexpr Preset FLUIDS_3D[] = {
+  { PC::FLUIDS_DAM, { NP::P130K, LATTICE_BOX, { { { 1, -2 }, { 1, -2 }, { 1, -2 } }, { { 1, 2 }, ZERO, ZERO } }, { 0, 0, 0 } }, NONE },
+  { PC::FLUIDS_BOMB, { NP::P65K, LATTICE_ROUND, BOIDS_3D, { 0, 0, 0 } }, NONE },
+  { PC::FLUIDS_DROP, { NP::P4K, LATTICE_BOX, { { { 1, -10 }, { 2, 10 }, { 1, -10 } }, { { 1, 10 }, { 4, 10 }, { 1, 10 } } }, { 0, 0, 0 } },
+      { NP::P65K, LATTICE_BOX, { { { 1, -2 }, { 1, -2 }, { 1, -2 } }, { { 1, 2 }, { 1, -2.55f }, { 1, 2 } } }, { 64, 16, 64 } } },
+};
+constexpr Preset FLUIDS_2D[] = {
+  { PC::FLUIDS_DAM, { NP::P4K, LATTICE_BOX, { { ZERO, { 1, -2 }, { 1, -2 } }, { ZERO, ZERO, ZERO } }, { 0, 0, 0 } }, NONE },
+  { PC::FLUIDS_BOMB, { NP::P4K, LATTICE_BOX, BOIDS_2D, { 0, 0, 0 } }, NONE },
+  { PC::FLUIDS_DROP, { NP::P512, LATTICE_BOX, { { ZERO, { 2, 10 }, { 1, -10 } }, { ZERO, { 4, 10 }, { 1, 10 } } }, { 0, 0, 0 } },
+      { NP::P4K, LATTICE_BOX, { { ZERO, { 1, -2 }, { 1, -2 } }, { ZERO, ZERO, { 1, 2 } } }, { 64, 128, 0 } } },
+};
+
+// clouds: randomly filled slab at the bottom (cumulus) or the whole box (homogeneous)
+constexpr Preset CLOUDS_3D[] = {
+  { PC::CLOUDS_CUMULUS, { NP::P65K, LATTICE_BOX, { { { 1, -2 }, { 1, -2 }, { 1, -2 } }, { { 1, 2 }, { 1, -4 }, { 1, 2 } } }, { 0, 0, 0 } }, NONE },
+  { PC::CLOUDS_HOMOGENEOUS, { NP::P65K, LATTICE_BOX, { { { 1, -2 }, { 1, -2 }, { 1, -2 } }, { { 1, 2 }, { 1, 2 }, { 1, 2 } } }, { 0, 0, 0 } }, NONE },
+};
+constexpr Preset CLOUDS_2D[] = {
+  { PC::CLOUDS_CUMULUS, { NP::P8K, LATTICE_BOX, { { ZERO, { 1, -2 }, { 1, -2 } }, { ZERO, ZERO, { 1, 2 } } }, { 0, 0, 0 } }, NONE },
+  { PC::CLOUDS_HOMOGENEOUS, { NP::P8K, LATTICE_BOX, { { ZERO, { 1, -2 }, { 1, -2 } }, { ZERO, { 1, 2 }, { 1, 2 } } }, { 0, 0, 0 } }, NONE },
+};
+} // namespace
+
 void Boids::reset()
 {
   if (!m_init)
     return;
   resetInputJson(boidsJson());
-  switch (m_case)
-  { // Boids.cpp:235-257
-  case Utils::PhysicsCase::BOIDS_SMALL: m_currNbParticles = Utils::NbParticles::P512; break;
-  case Utils::PhysicsCase::BOIDS_MEDIUM: m_currNbParticles = Utils::NbParticles::P16K; break;
-  case Utils::PhysicsCase::BOIDS_LARGE: m_currNbParticles = Utils::NbParticles::P65K; break;
-  case Utils::PhysicsCase::BOIDS_XLARGE: m_currNbParticles = Utils::NbParticles::P130K; break;
-  default: break;
-  }
+  for (const auto& c : BOIDS_COUNTS) // the case only chooses the flock's size (Boids.cpp:235-257)
+    if (c.pcase == m_case)
+      m_currNbParticles = (size_t)c.count;
   rtp_set_nb_particles(m_handle, m_currNbParticles);
   rtp_set_dimension(m_handle, m_dimension == Geometry::Dimension::dim2D ? 2 : 3);
   json js = getInputJson();
@@ -156,23 +270,9 @@ void Boids::initBoidsParticles()
     LOG_ERROR("Cannot init boids, current number of particles is higher than max limit");
     return;
   }
-  std::vector<Math::float3> gridVerts;
-  if (m_dimension == Geometry::Dimension::dim2D)
-  {
-    const auto& subdiv2D = Utils::GetNbParticlesSubdiv2D((Utils::NbParticles)m_currNbParticles);
-    Math::int2 grid2DRes = { subdiv2D[0], subdiv2D[1] };
-    Math::float3 start2D = { 0.0f, m_boxSize.y / -6.0f, m_boxSize.z / -6.0f };
-    Math::float3 end2D = { 0.0f, m_boxSize.y / 6.0f, m_boxSize.z / 6.0f };
-    gridVerts = Geometry::Generate2DGrid(Geometry::Shape2D::Circle, Geometry::Plane::YZ, grid2DRes, start2D, end2D);
-  }
-  else
-  {
-    const auto& subdiv3D = Utils::GetNbParticlesSubdiv3D((Utils::NbParticles)m_currNbParticles);
-    Math::int3 grid3DRes = { subdiv3D[0], subdiv3D[1], subdiv3D[2] };
-    Math::float3 start3D = { m_boxSize.x / -6.0f, m_boxSize.y / -6.0f, m_boxSize.z / -6.0f };
-    Math::float3 end3D = { m_boxSize.x / 6.0f, m_boxSize.y / 6.0f, m_boxSize.z / 6.0f };
-    gridVerts = Geometry::Generate3DGrid(Geometry::Shape3D::Sphere, grid3DRes, start3D, end3D);
-  }
+  const bool dim2D = m_dimension == Geometry::Dimension::dim2D;
+  const Lattice flock { (int)m_currNbParticles, LATTICE_ROUND, dim2D ? BOIDS_2D : BOIDS_3D, { 0, 0, 0 } };
+  const std::vector<Math::float3> gridVerts = generate(flock, dim2D, m_boxSize);
   const float colour[4] = { 1.0f, 0.02f, 0.02f, 0.5f }; // bd_fillBoidsColor boids.cl:38-41
   uploadParticles(gridVerts, true /* "Using same buffer to initialize vel", Boids.cpp:316-318 */, colour);
 }
@@ -238,79 +338,18 @@ void Fluids::reset()
 
 void Fluids::initFluidsParticles()
 { // Fluids.cpp:273-398
+  const bool dim2D = m_dimension == Geometry::Dimension::dim2D;
+  const Preset* preset = dim2D ? findPreset(FLUIDS_2D, m_case) : findPreset(FLUIDS_3D, m_case);
   std::vector<Math::float3> gridVerts;
-  Math::float3 startFluidPos = { 0.0f, 0.0f, 0.0f };
-  Math::float3 endFluidPos = { 0.0f, 0.0f, 0.0f };
-  if (m_dimension == Geometry::Dimension::dim2D)
+  if (!preset)
   {
-    switch (m_case)
-    {
-    case Utils::PhysicsCase::FLUIDS_DAM:
-      m_currNbParticles = Utils::NbParticles::P4K;
-      startFluidPos = { 0.0f, m_boxSize.y / -2.0f, m_boxSize.z / -2.0f };
-      endFluidPos = { 0.0f, 0.0f, 0.0f };
-      break;
-    case Utils::PhysicsCase::FLUIDS_BOMB:
-      m_currNbParticles = Utils::NbParticles::P4K;
-      startFluidPos = { 0.0f, m_boxSize.y / -6.0f, m_boxSize.z / -6.0f };
-      endFluidPos = { 0.0f, m_boxSize.y / 6.0f, m_boxSize.z / 6.0f };
-      break;
-    case Utils::PhysicsCase::FLUIDS_DROP:
-      m_currNbParticles = Utils::NbParticles::P512;
-      startFluidPos = { 0.0f, 2.0f * m_boxSize.y / 10.0f, m_boxSize.z / -10.0f };
-      endFluidPos = { 0.0f, 4.0f * m_boxSize.y / 10.0f, m_boxSize.z / 10.0f };
-      break;
-    default: LOG_ERROR("Unkown case type"); break;
-    }
-    const auto& subdiv2D = Utils::GetNbParticlesSubdiv2D((Utils::NbParticles)m_currNbParticles);
-    Math::int2 grid2DRes = { subdiv2D[0], subdiv2D[1] };
-    gridVerts = Geometry::Generate2DGrid(Geometry::Shape2D::Rectangle, Geometry::Plane::YZ, grid2DRes, startFluidPos, endFluidPos);
-    if (m_case == Utils::PhysicsCase::FLUIDS_DROP)
-    {
-      m_currNbParticles += Utils::NbParticles::P4K;
-      Math::int2 res2 = { 64, 128 };
-      startFluidPos = { 0.0f, m_boxSize.y / -2.0f, m_boxSize.z / -2.0f };
-      endFluidPos = { 0.0f, 0.0f, m_boxSize.z / 2.0f };
-      auto bottom = Geometry::Generate2DGrid(Geometry::Shape2D::Rectangle, Geometry::Plane::YZ, res2, startFluidPos, endFluidPos);
-      gridVerts.insert(gridVerts.end(), bottom.begin(), bottom.end());
-    }
+    LOG_ERROR("Unkown case type");
+    // (the reference falls through with an empty region: every particle of the current count at the origin)
+    const Lattice origin { (int)m_currNbParticles, LATTICE_BOX, NONE.region, { 0, 0, 0 } };
+    gridVerts = generate(origin, dim2D, m_boxSize);
   }
   else
-  {
-    Geometry::Shape3D shape = Geometry::Shape3D::Box;
-    switch (m_case)
-    {
-    case Utils::PhysicsCase::FLUIDS_DAM:
-      m_currNbParticles = Utils::NbParticles::P130K;
-      startFluidPos = { m_boxSize.x / -2.0f, m_boxSize.y / -2.0f, m_boxSize.z / -2.0f };
-      endFluidPos = { m_boxSize.x / 2.0f, 0.0f, 0.0f };
-      break;
-    case Utils::PhysicsCase::FLUIDS_BOMB:
-      m_currNbParticles = Utils::NbParticles::P65K;
-      shape = Geometry::Shape3D::Sphere;
-      startFluidPos = { m_boxSize.x / -6.0f, m_boxSize.y / -6.0f, m_boxSize.z / -6.0f };
-      endFluidPos = { m_boxSize.x / 6.0f, m_boxSize.y / 6.0f, m_boxSize.z / 6.0f };
-      break;
-    case Utils::PhysicsCase::FLUIDS_DROP:
-      m_currNbParticles = Utils::NbParticles::P4K;
-      startFluidPos = { m_boxSize.x / -10.0f, 2.0f * m_boxSize.y / 10.0f, m_boxSize.z / -10.0f };
-      endFluidPos = { m_boxSize.x / 10.0f, 4.0f * m_boxSize.y / 10.0f, m_boxSize.z / 10.0f };
-      break;
-    default: LOG_ERROR("Unkown case type"); break;
-    }
-    const auto& subdiv3D = Utils::GetNbParticlesSubdiv3D((Utils::NbParticles)m_currNbParticles);
-    Math::int3 grid3DRes = { subdiv3D[0], subdiv3D[1], subdiv3D[2] };
-    gridVerts = Geometry::Generate3DGrid(shape, grid3DRes, startFluidPos, endFluidPos);
-    if (m_case == Utils::PhysicsCase::FLUIDS_DROP)
-    {
-      m_currNbParticles += Utils::NbParticles::P65K;
-      Math::int3 res3 = { 64, 16, 64 };
-      startFluidPos = { m_boxSize.x / -2.0f, m_boxSize.y / -2.0f, m_boxSize.z / -2.0f };
-      endFluidPos = { m_boxSize.x / 2.0f, m_boxSize.y / -2.55f, m_boxSize.z / 2.0f };
-      auto bottom = Geometry::Generate3DGrid(Geometry::Shape3D::Box, res3, startFluidPos, endFluidPos);
-      gridVerts.insert(gridVerts.end(), bottom.begin(), bottom.end());
-    }
-  }
+    gridVerts = generate(*preset, dim2D, m_boxSize, m_currNbParticles);
   if (m_currNbParticles > m_maxNbParticles)
     m_currNbParticles = m_maxNbParticles;
   rtp_set_nb_particles(m_handle, m_currNbParticles);
@@ -408,31 +447,14 @@ void Clouds::reset()
 
 void Clouds::initCloudsParticles()
 { // Clouds.cpp:401-501
-  std::vector<Math::float3> gridVerts;
-  Math::float3 startFluidPos = { 0.0f, 0.0f, 0.0f };
-  Math::float3 endFluidPos = { 0.0f, 0.0f, 0.0f };
-  const Geometry::Distribution distribution = Geometry::Distribution::Random;
-  const bool cumulus = m_case == Utils::PhysicsCase::CLOUDS_CUMULUS;
-  if (m_case != Utils::PhysicsCase::CLOUDS_CUMULUS && m_case != Utils::PhysicsCase::CLOUDS_HOMOGENEOUS)
+  const bool dim2D = m_dimension == Geometry::Dimension::dim2D;
+  const Preset* preset = dim2D ? findPreset(CLOUDS_2D, m_case) : findPreset(CLOUDS_3D, m_case);
+  if (!preset)
+  {
     LOG_ERROR("Unkown case type");
-  if (m_dimension == Geometry::Dimension::dim2D)
-  {
-    m_currNbParticles = Utils::NbParticles::P8K;
-    startFluidPos = { 0.0f, m_boxSize.y / -2.0f, m_boxSize.z / -2.0f };
-    endFluidPos = { 0.0f, cumulus ? 0.0f : m_boxSize.y / 2.0f, m_boxSize.z / 2.0f };
-    const auto& subdiv2D = Utils::GetNbParticlesSubdiv2D((Utils::NbParticles)m_currNbParticles);
-    Math::int2 grid2DRes = { subdiv2D[0], subdiv2D[1] };
-    gridVerts = Geometry::Generate2DGrid(Geometry::Shape2D::Rectangle, Geometry::Plane::YZ, grid2DRes, startFluidPos, endFluidPos, distribution);
+    preset = dim2D ? &CLOUDS_2D[1] : &CLOUDS_3D[1]; // (the reference treats every other case like the homogeneous one)
   }
-  else
-  {
-    m_currNbParticles = Utils::NbParticles::P65K;
-    startFluidPos = { m_boxSize.x / -2.0f, m_boxSize.y / -2.0f, m_boxSize.z / -2.0f };
-    endFluidPos = { m_boxSize.x / 2.0f, cumulus ? m_boxSize.y / -4.0f : m_boxSize.y / 2.0f, m_boxSize.z / 2.0f };
-    const auto& subdiv3D = Utils::GetNbParticlesSubdiv3D((Utils::NbParticles)m_currNbParticles);
-    Math::int3 grid3DRes = { subdiv3D[0], subdiv3D[1], subdiv3D[2] };
-    gridVerts = Geometry::Generate3DGrid(Geometry::Shape3D::Box, grid3DRes, startFluidPos, endFluidPos, distribution);
-  }
+  const std::vector<Math::float3> gridVerts = generate(*preset, dim2D, m_boxSize, m_currNbParticles, Geometry::Distribution::Random);
   if (m_currNbParticles > m_maxNbParticles)
     m_currNbParticles = m_maxNbParticles;
   rtp_set_nb_particles(m_handle, m_currNbParticles);
