@@ -784,7 +784,8 @@ extern "C" int rtp_slab_group_check(rtp_slab_group* g, uint64_t* migrated_total)
 {
   if (!g)
     return RTP_ERR_INVALID;
-  u64 migrated = 0;
+  u64 migrated = 0, capFlags = 0;
+  int capSlab = -1, rowSlab = -1;
   for (Slab& sl : g->slabs)
   {
     SG_CUDA(g, cudaSetDevice(sl.dev));
@@ -800,20 +801,24 @@ extern "C" int rtp_slab_group_check(rtp_slab_group* g, uint64_t* migrated_total)
         return rc;
       SG_CUDA(g, cudaMemcpy(&rowErr, rb + 3, sizeof rowErr, cudaMemcpyDeviceToHost));
     }
-    if (rowErr)
-    {
-      g->err = "a sweep launched by row phase was sized too small for its rows: results since the last check are invalid";
-      return RTP_ERR_COMM;
-    }
-    if (f[0])
-    {
-      char buf[160];
-      snprintf(buf, sizeof buf, "slab %d: capacity exceeded on the device (flags %llu: 1 = arrival slots in use, 2 = migration message, 4 = ghost region)",
-          sl.rank, f[0]);
-      g->err = buf;
-      return RTP_ERR_COMM;
-    }
+    if (f[0] && capSlab < 0)
+      capSlab = sl.rank, capFlags = f[0];
+    if (rowErr && rowSlab < 0)
+      rowSlab = sl.rank;
     migrated += f[1];
+  }
+  if (capSlab >= 0) // (the cause: an overflowing ghost region also outruns the launches sized from it)
+  {
+    char buf[200];
+    snprintf(buf, sizeof buf, "slab %d: capacity exceeded on the device (flags %llu: 1 = arrival slots in use, 2 = migration message, 4 = ghost region)",
+        capSlab, capFlags);
+    g->err = buf;
+    return RTP_ERR_COMM;
+  }
+  if (rowSlab >= 0)
+  {
+    g->err = "slab " + std::to_string(rowSlab) + ": a sweep launched by row phase was sized too small for its rows: results since the last check are invalid";
+    return RTP_ERR_COMM;
   }
   if (migrated_total)
     *migrated_total = migrated;

@@ -172,6 +172,21 @@ def test_library_slab_group_one_slab_equals_rtp_step():
     assert per == [n] and np.array_equal(pos, h.download("p_pos")) and np.array_equal(vel, h.download("p_vel"))
 
 
+@pytest.mark.gpu
+def test_library_slab_group_reports_capacity_overflow():
+    # a ghost region far too small for the two face layers: the halo does not fit, the device-side flag is raised and
+    # rtp_slab_group_check / _download refuse the results (RTP_ERR_COMM) instead of returning a wrong state
+    pos0 = _dam((48, 32, 32), end=(3.0, 0.0, 0.0))
+    n = len(pos0)
+    sg = _abi.SlabGroup([0, 0], n, BOX, GRID, ghost_cap=256, migrate_cap=64, jacobi=2)
+    sg.upload(pos0, _drift(pos0))
+    sg.step(2)
+    with pytest.raises(_abi.RtpError, match="capacity exceeded"):
+        sg.check()
+    with pytest.raises(_abi.RtpError):
+        sg.download()
+
+
 def test_library_slab_group_fails_loudly_without_a_device_or_with_bad_arguments():
     L = _abi.lib()
     import ctypes as C
