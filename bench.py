@@ -595,7 +595,7 @@ def run_ours(args):
                                "achieved": round(value / world * PBF_BYTES_PER_PARTICLE_STEP / 1e9, 1),
                                "frac": round(value / world * PBF_BYTES_PER_PARTICLE_STEP / 1e9 / peak, 4)},
                 "note": "neighbour sweeps test ~460 candidate pairs per particle on 16-64 B of compulsory traffic: instruction-"
-                        "issue bound (ncu: 65-71% of the issue slots busy, profiles/r02_ncu_pbf130k_step.txt), far below the HBM line "
+                        "issue bound (ncu: 65-71% of the issue slots busy, profiles/r02b_ncu_pbf130k_step.txt), far below the HBM line "
                         "by construction (SURVEY 8d); traffic = ncu dram bytes per launch with a cold L2, dominated by the "
                         "neighbour lists a step writes once (tile filter + build) and its seven later sweeps walk instead of "
                         "re-testing the candidates (DESIGN.md section 5)"}
@@ -665,6 +665,28 @@ def run_ours(args):
                    "what": "rtp_step(PHYSICS | RENDER_AUX | CAMERA_SORT): the whole Fluids::update() of the app, L2 flushed per step"}
     hf.close()
 
+    # ---- the same step SUSTAINED: the driver's short window (steps W+1 .. W+K) covers the start of the dam break, when the
+    # lattice is barely disturbed and the lists are at their shortest; this is the figure over 2000 more steps of the collapse
+    sustained = None
+    if K < 1000:
+        hs, _ = make_pbf(abi, local_rank)
+        ss = torch.cuda.ExternalStream(hs.stream(), device=dev)
+        with torch.cuda.stream(ss):
+            hs.step_n(50, flags)
+        hs.sync()
+        evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(2000)]
+        with torch.cuda.stream(ss):
+            for a, b in evs:
+                flush.zero_()
+                a.record(ss)
+                hs.step_n(1, flags)
+                b.record(ss)
+        hs.sync()
+        sus_ms = sum(a.elapsed_time(b) for a, b in evs)
+        sustained = {"steps": len(evs), "window": "steps 51-2050 of the dam break, L2 flushed before every step", "ms_per_step": round(sus_ms / len(evs), 4),
+                     "steps_per_s": round(len(evs) / (sus_ms * 1e-3), 1), "value": N130K * len(evs) / (sus_ms * 1e-3), "unit": "particle-updates/s"}
+        hs.close()
+
     # ---- CPU baseline on this box's host cores, bounded sample: the reference's own kernels compiled for the CPU
     # (oracle/_ref) when that library travelled here, and the oracle port beside it
     cpu = None
@@ -710,7 +732,7 @@ def run_ours(args):
                         "note": "same K steps replayed back to back from one CUDA graph, no flush"},
         "e2e": e2e, "full_update": full_update, "gpu_launches": launches_per_step * K * world, "launches_per_step": launches_per_step,
         "roofline": roofline, "kernels": kernels, "kernels_window": kernels_window, "cpu_baseline": cpu, "clocks": sampler.result(),
-        "other_workloads": others, "slab_16m": slab,
+        "sustained": sustained, "other_workloads": others, "slab_16m": slab,
         "slab_16m_strong_scaling_efficiency": (slab or {}).get("strong_scaling_efficiency"),
         "slab_16m_library_driver_strong_scaling_efficiency": ((slab or {}).get("library_driver") or {}).get("strong_scaling_efficiency"),
         "wall_s_timed_region": round(t_wall, 3),

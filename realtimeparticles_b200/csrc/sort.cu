@@ -70,8 +70,10 @@ __global__ void __launch_bounds__(SORT_THREADS) sortHistogramKernel(const u32* _
       atomicAdd(&ctrl[i], sHist[i]);
 }
 
+// Large tiles (ITEMS = 16) fetch their values only when the tile is reordered (after the look-back): sixteen registers less
+// per thread through the ranking and the look-back, four resident CTAs per SM instead of three.
 template <int ITEMS>
-__global__ void __launch_bounds__(SORT_THREADS) onesweepPassKernel(const u32* __restrict__ kin, const u32* __restrict__ vin,
+__global__ void __launch_bounds__(SORT_THREADS, ITEMS > 4 ? 4 : 1) onesweepPassKernel(const u32* __restrict__ kin, const u32* __restrict__ vin,
     u32* __restrict__ kout, u32* __restrict__ vout, u32 n, int shift, u32 mask, const u32* __restrict__ ghist,
     u32* __restrict__ status, u32* __restrict__ ticket)
 {
@@ -95,7 +97,8 @@ __global__ void __launch_bounds__(SORT_THREADS) onesweepPassKernel(const u32* __
   const u32 tileBase = tile * TILE;
 
   // warp-striped load: warp w owns [tileBase + w*32*ITEMS, +32*ITEMS), item r of lane l = base + r*32 + l
-  u32 key[ITEMS], val[ITEMS], rank[ITEMS];
+  constexpr bool LATE_VALS = ITEMS > 4;
+  u32 key[ITEMS], val[LATE_VALS ? 1 : ITEMS], rank[ITEMS];
   const u32 warpBase = tileBase + warp * 32 * ITEMS;
 #pragma unroll
   for (int r = 0; r < ITEMS; ++r)
@@ -103,7 +106,8 @@ __global__ void __launch_bounds__(SORT_THREADS) onesweepPassKernel(const u32* __
     const u32 idx = warpBase + r * 32 + lane;
     const bool valid = idx < n;
     key[r] = valid ? __ldg(kin + idx) : 0xFFFFFFFFu;
-    val[r] = valid ? (vin ? __ldg(vin + idx) : idx) : 0u;
+    if (!LATE_VALS)
+      val[r] = valid ? (vin ? __ldg(vin + idx) : idx) : 0u;
   }
 
   // stable ranking inside the warp: (round, lane) order == memory order
@@ -161,15 +165,39 @@ __global__ void __launch_bounds__(SORT_THREADS) onesweepPassKernel(const u32* __
   sLBase[d] = lscan;
   __syncthreads();
 
-#pragma unroll
-  for (int r = 0; r < ITEMS; ++r)
+  if (LATE_VALS)
   {
-    if ((warpBase + r * 32 + lane) < n)
+    u32 v[ITEMS];
+#pragma unroll
+    for (int r = 0; r < ITEMS; ++r)
     {
-      const u32 dd = (key[r] >> shift) & mask;
-      const u32 lp = sLBase[dd] + sWarpHist[warp][dd] + rank[r];
-      sKeys[lp] = key[r];
-      sVals[lp] = val[r];
+      const u32 idx = warpBase + r * 32 + lane;
+      v[r] = (vin && idx < n) ? __ldg(vin + idx) : idx;
+    }
+#pragma unroll
+    for (int r = 0; r < ITEMS; ++r)
+    {
+      if ((warpBase + r * 32 + lane) < n)
+      {
+        const u32 dd = (key[r] >> shift) & mask;
+        const u32 lp = sLBase[dd] + sWarpHist[warp][dd] + rank[r];
+        sKeys[lp] = key[r];
+        sVals[lp] = v[r];
+      }
+    }
+  }
+  else
+  {
+#pragma unroll
+    for (int r = 0; r < ITEMS; ++r)
+    {
+      if ((warpBase + r * 32 + lane) < n)
+      {
+        const u32 dd = (key[r] >> shift) & mask;
+        const u32 lp = sLBase[dd] + sWarpHist[warp][dd] + rank[r];
+        sKeys[lp] = key[r];
+        sVals[lp] = val[LATE_VALS ? 0 : r];
+      }
     }
   }
   __syncthreads();
