@@ -88,23 +88,56 @@ __global__ void __launch_bounds__(BD_THREADS) boidsRulesKernel(DeviceState s, Gr
   float avx = 0.f, avy = 0.f, avz = 0.f; // averageBoidsVel
   float rpx = 0.f, rpy = 0.f, rpz = 0.f; // repulseHeading
 
+  // One candidate: the reference's test and its nine ordered sums (boids.cl:96-110). nv / r are fetched and computed
+  // BEFORE the test by the caller: no load and no reciprocal sits behind the (divergent) hit branch.
+  auto accumulate = [&](const float4 pj, const float4 nv, float dx, float dy, float dz, float r)
+  {
+    apx = fadd(apx, pj.x); apy = fadd(apy, pj.y); apz = fadd(apz, pj.z);
+    avx = fadd(avx, nv.x); avy = fadd(avy, nv.y); avz = fadd(avz, nv.z);
+    rpx = ffma(dx, r, rpx); rpy = ffma(dy, r, rpy); rpz = ffma(dz, r, rpz); // vec / squaredDist == vec * (1 / squaredDist), one fused op per component
+    ++count;
+  };
+  // The flock collapses into a few cells holding thousands of boids each: the step is the ~10 warps per SM that sweep them,
+  // far too few to hide a load behind every hit. Candidates are therefore taken four at a time: positions AND pre-normalised
+  // velocities of all four are in flight together, the four tests and reciprocals are independent, and only the short,
+  // load-free sums run in order.
   auto visit = [&](u32 start, u32 end, float, float)
   {
-    forRangeLoad4(P, start, end,
-        [&](u32 e, const float4 pj)
-        {
-          const float dx = pi.x - pj.x, dy = pi.y - pj.y, dz = pi.z - pj.z;
-          const float sq = dot3c(dx, dy, dz, dx, dy, dz);
-          if (sq < c.effectRadiusSq && sq > RTP_FLOAT_EPS)
-          {
-            const float4 nv = ld4(NV, e);
-            apx = fadd(apx, pj.x); apy = fadd(apy, pj.y); apz = fadd(apz, pj.z);
-            avx = fadd(avx, nv.x); avy = fadd(avy, nv.y); avz = fadd(avz, nv.z);
-            const float r = frcp(sq); // vec / squaredDist == vec * (1 / squaredDist), one fused op per component
-            rpx = ffma(dx, r, rpx); rpy = ffma(dy, r, rpy); rpz = ffma(dz, r, rpz);
-            ++count;
-          }
-        });
+    u32 e = start;
+#pragma unroll 1
+    for (; e + 3u <= end; e += 4u)
+    {
+      float4 a[4], v[4];
+#pragma unroll
+      for (int k = 0; k < 4; ++k)
+      {
+        a[k] = __ldg(P + e + k);
+        v[k] = __ldg(NV + e + k);
+      }
+      float dx[4], dy[4], dz[4], r[4];
+      bool hit[4];
+#pragma unroll
+      for (int k = 0; k < 4; ++k)
+      {
+        dx[k] = pi.x - a[k].x, dy[k] = pi.y - a[k].y, dz[k] = pi.z - a[k].z;
+        const float sq = dot3c(dx[k], dy[k], dz[k], dx[k], dy[k], dz[k]);
+        hit[k] = sq < c.effectRadiusSq && sq > RTP_FLOAT_EPS;
+        r[k] = frcp(hit[k] ? sq : 1.0f);
+      }
+#pragma unroll
+      for (int k = 0; k < 4; ++k)
+        if (hit[k])
+          accumulate(a[k], v[k], dx[k], dy[k], dz[k], r[k]);
+    }
+#pragma unroll 1
+    for (; e <= end; ++e)
+    {
+      const float4 pj = __ldg(P + e), nv = __ldg(NV + e);
+      const float dx = pi.x - pj.x, dy = pi.y - pj.y, dz = pi.z - pj.z;
+      const float sq = dot3c(dx, dy, dz, dx, dy, dz);
+      if (sq < c.effectRadiusSq && sq > RTP_FLOAT_EPS)
+        accumulate(pj, nv, dx, dy, dz, frcp(sq));
+    }
   };
 
   if (!DIM2)
