@@ -15,6 +15,10 @@
 namespace rtp
 {
 constexpr int BD_THREADS = 128;
+#ifndef RTP_BD_GROUP
+#define RTP_BD_GROUP 8
+#endif
+constexpr int BD_GROUP = RTP_BD_GROUP; // candidates in flight per thread in the rules sweep
 
 // fast_normalize(v) = v * (1 / sqrt(dot(v, v))), and a zero vector is returned unchanged (OpenCL 1.2 s6.12.5; the test is
 // dot == 0, as in the oracle)
@@ -98,26 +102,26 @@ __global__ void __launch_bounds__(BD_THREADS) boidsRulesKernel(DeviceState s, Gr
     ++count;
   };
   // The flock collapses into a few cells holding thousands of boids each: the step is the ~10 warps per SM that sweep them,
-  // far too few to hide a load behind every hit. Candidates are therefore taken four at a time: positions AND pre-normalised
+  // far too few to hide a load behind every hit. Candidates are therefore taken BD_GROUP at a time: positions AND pre-normalised
   // velocities of all four are in flight together, the four tests and reciprocals are independent, and only the short,
   // load-free sums run in order.
   auto visit = [&](u32 start, u32 end, float, float)
   {
     u32 e = start;
 #pragma unroll 1
-    for (; e + 3u <= end; e += 4u)
+    for (; e + (u32)(BD_GROUP - 1) <= end; e += (u32)BD_GROUP)
     {
-      float4 a[4], v[4];
+      float4 a[BD_GROUP], v[BD_GROUP];
 #pragma unroll
-      for (int k = 0; k < 4; ++k)
+      for (int k = 0; k < BD_GROUP; ++k)
       {
         a[k] = __ldg(P + e + k);
         v[k] = __ldg(NV + e + k);
       }
-      float dx[4], dy[4], dz[4], r[4];
-      bool hit[4];
+      float dx[BD_GROUP], dy[BD_GROUP], dz[BD_GROUP], r[BD_GROUP];
+      bool hit[BD_GROUP];
 #pragma unroll
-      for (int k = 0; k < 4; ++k)
+      for (int k = 0; k < BD_GROUP; ++k)
       {
         dx[k] = pi.x - a[k].x, dy[k] = pi.y - a[k].y, dz[k] = pi.z - a[k].z;
         const float sq = dot3c(dx[k], dy[k], dz[k], dx[k], dy[k], dz[k]);
@@ -125,7 +129,7 @@ __global__ void __launch_bounds__(BD_THREADS) boidsRulesKernel(DeviceState s, Gr
         r[k] = frcp(hit[k] ? sq : 1.0f);
       }
 #pragma unroll
-      for (int k = 0; k < 4; ++k)
+      for (int k = 0; k < BD_GROUP; ++k)
         if (hit[k])
           accumulate(a[k], v[k], dx[k], dy[k], dz[k], r[k]);
     }
