@@ -14,7 +14,10 @@
 
 namespace rtp
 {
-constexpr int BD_THREADS = 128;
+#ifndef RTP_BD_THREADS
+#define RTP_BD_THREADS 128
+#endif
+constexpr int BD_THREADS = RTP_BD_THREADS;
 #ifndef RTP_BD_GROUP
 #define RTP_BD_GROUP 8
 #endif
