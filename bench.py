@@ -206,6 +206,14 @@ def time_cpu_world(w, warmup, steps, budget_s):
     return done, time.perf_counter() - t0
 
 
+def headline_config(world):
+    """`config` of the JSON line: the same dict for both arms (the reference arm runs on OUR arm's config: the l2 /
+    parallelism entries describe how the GPU arm is timed)."""
+    return {"workload": "pbf_dam_130k_I3_vorticity_xsph", "particles": N130K, "jacobi_iterations": JACOBI,
+            "grid": [30, 30, 30], "box": [10, 10, 10], "l2": "flushed before every timed step (256 MiB memset, untimed)",
+            "parallelism": "replicas" if world > 1 else "single"}
+
+
 def run_reference(args):
     """The reference's CPU implementation of the path. The OpenCL runtime it needs does not exist here, so its kernel
     sources (physics/ocl/kernels/*.cl, unmodified) are compiled for the CPU through oracle/ref/ocl_shim.hpp into
@@ -223,7 +231,7 @@ def run_reference(args):
         cw = cpu_world(pos, kind)
     w, cores = cw
     budget = 150.0
-    wu = min(args.warmup, 2)
+    wu = min(args.warmup, 5)  # (a CPU step takes 0.3 s: the driver's W = 5 is honoured)
     done, dt = time_cpu_world(w, wu, args.steps, budget)
     value = N130K * done / dt
     sample = "%d of %d requested steps of the full 131072-particle PBF step (time-bounded to %ds)" % (done, args.steps, int(budget))
@@ -231,8 +239,7 @@ def run_reference(args):
         "impl": "reference", "metric": "particle-updates/sec", "value": value, "unit": "particle-updates/s",
         "n_gpus": args.gpus, "steps": done, "warmup": wu, "ms_per_step": 1e3 * dt / max(done, 1),
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": "pbf_dam_130k_I3_vorticity_xsph", "particles": N130K, "jacobi_iterations": JACOBI,
-                   "grid": [30, 30, 30], "box": [10, 10, 10]},
+        "config": headline_config(max(args.gpus, 1)),
         "cpu_baseline": {"value": value, "unit": "particle-updates/s", "cores": cores, "kind": kind, "sample": sample},
         "e2e": {"value": value, "unit": "particle-updates/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -724,9 +731,7 @@ def run_ours(args):
         "metric": "particle-updates/sec", "value": value, "unit": "particle-updates/s", "n_gpus": world, "steps": K, "warmup": W,
         "ms_per_step": ms_total / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
         "data": "synthetic",
-        "config": {"workload": "pbf_dam_130k_I3_vorticity_xsph", "particles": N130K, "jacobi_iterations": JACOBI,
-                   "grid": [30, 30, 30], "box": [10, 10, 10], "l2": "flushed before every timed step (256 MiB memset, untimed)",
-                   "parallelism": "replicas" if world > 1 else "single"},
+        "config": headline_config(world),
         "steps_per_s": K / (ms_total * 1e-3),
         "l2_resident": {"value": N130K * K / (warm_ms * 1e-3), "steps_per_s": K / (warm_ms * 1e-3),
                         "note": "same K steps replayed back to back from one CUDA graph, no flush"},
