@@ -627,15 +627,18 @@ def run_ours(args):
     hpos = torch.from_numpy(pos0.copy()).pin_memory()
     hvel = torch.zeros((N130K, 4), dtype=torch.float32).pin_memory()
     ke = max(20, min(K, 500))
+    hpos_np, hvel_np = hpos.numpy(), hvel.numpy()
 
     def e2e_step():
         # the state lives on the HOST between steps: what step k downloads is what step k + 1 uploads, so the simulation
         # advances (the dam collapses over the timed window like in the device-resident run)
-        m.upload("p_pos", hpos.numpy())
-        m.upload("p_vel", hvel.numpy())
+        # (page-locked buffers: the four copies are stream-ordered around the step, one synchronisation per frame)
+        m.upload("p_pos", hpos_np, blocking=False)
+        m.upload("p_vel", hvel_np, blocking=False)
         m.update()
-        m._h.download("p_pos", out=hpos.numpy())
-        m._h.download("p_vel", out=hvel.numpy())
+        m.download("p_pos", out=hpos_np, blocking=False)
+        m.download("p_vel", out=hvel_np, blocking=False)
+        m.sync()
     for _ in range(3):
         e2e_step()
     torch.cuda.synchronize()
@@ -648,8 +651,9 @@ def run_ours(args):
     e2e = {"value": N130K * ke / e2e_dt, "unit": "particle-updates/s", "h2d_bytes_per_step": 2 * N130K * 16,
            "d2h_bytes_per_step": 2 * N130K * 16, "steps": ke, "ms_per_step": round(1e3 * e2e_dt / ke, 4),
            "max_displacement_over_run": round(e2e_moved, 4),
-           "api": "realtimeparticles_b200.models.Fluids: upload(p_pos,p_vel) + update() + download(p_pos,p_vel), pinned host "
-                  "buffers; the downloaded state is the next step's upload"}
+           "api": "realtimeparticles_b200.models.Fluids: upload(p_pos,p_vel) + update() + download(p_pos,p_vel) + sync(), pinned host "
+                  "buffers, stream-ordered copies (rtp_upload_async / rtp_download_async), one synchronisation per frame; the "
+                  "downloaded state is the next step's upload"}
 
     # ---- what Model::update() costs in the app: physics + render-side kernels + camera sort (Fluids.cpp:400-471)
     hf, _ = make_pbf(abi, local_rank)

@@ -177,6 +177,12 @@ RTP_API const char* rtp_last_error(const rtp_handle* h); /* h may be NULL: error
 RTP_API int rtp_field_bytes(const rtp_handle* h, int field, size_t* bytes);
 RTP_API int rtp_upload(rtp_handle* h, int field, const void* host, size_t bytes);
 RTP_API int rtp_download(rtp_handle* h, int field, void* host, size_t bytes);
+/* Stream-ordered variants for PAGE-LOCKED host buffers (a frame loop that streams its state through the host): the copy is
+ * enqueued on the handle's stream, in order with the steps around it, and the call returns; the device data is in place
+ * for the next rtp_step by stream order, the host buffer is complete / reusable after rtp_sync (or any blocking call).
+ * With pageable memory they behave like the blocking calls for the host buffer's lifetime (the runtime stages it). */
+RTP_API int rtp_upload_async(rtp_handle* h, int field, const void* host, size_t bytes);
+RTP_API int rtp_download_async(rtp_handle* h, int field, void* host, size_t bytes);
 /* device pointer of a field for zero-copy consumers (torch, CUDA-GL interop); valid until the next rtp_step */
 RTP_API int rtp_device_ptr(rtp_handle* h, int field, void** dptr);
 

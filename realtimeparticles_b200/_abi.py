@@ -76,7 +76,7 @@ assert C.sizeof(FluidParams) == 44 and C.sizeof(CloudParams) == 52
 
 # every symbol include/rtp_cuda.h declares
 EXPORTS = ["rtp_abi_version", "rtp_device_count", "rtp_create", "rtp_destroy", "rtp_last_error", "rtp_field_bytes",
-           "rtp_upload", "rtp_download", "rtp_device_ptr", "rtp_set_boids_params", "rtp_set_fluid_params",
+           "rtp_upload", "rtp_download", "rtp_upload_async", "rtp_download_async", "rtp_device_ptr", "rtp_set_boids_params", "rtp_set_fluid_params",
            "rtp_set_cloud_params", "rtp_set_boundary", "rtp_set_nb_particles", "rtp_set_dimension",
            "rtp_set_displayed_quantity", "rtp_reset_ids", "rtp_init_clouds_fields", "rtp_step", "rtp_step_n",
            "rtp_sync", "rtp_get_stream", "rtp_sort_keys", "rtp_sort_keys_host", "rtp_selftest_math", "rtp_enable_profiling", "rtp_get_stage_times",
@@ -112,6 +112,8 @@ def lib():
     L.rtp_field_bytes.argtypes = [vp, C.c_int, C.POINTER(C.c_size_t)]
     L.rtp_upload.argtypes = [vp, C.c_int, vp, C.c_size_t]
     L.rtp_download.argtypes = [vp, C.c_int, vp, C.c_size_t]
+    L.rtp_upload_async.argtypes = [vp, C.c_int, vp, C.c_size_t]
+    L.rtp_download_async.argtypes = [vp, C.c_int, vp, C.c_size_t]
     L.rtp_device_ptr.argtypes = [vp, C.c_int, C.POINTER(vp)]
     L.rtp_set_boids_params.argtypes = [vp, C.POINTER(BoidsParams), C.POINTER(TargetParams), fp, C.c_int]
     L.rtp_set_fluid_params.argtypes = [vp, C.POINTER(FluidParams), C.c_int]
@@ -237,20 +239,29 @@ class Handle:
         self._check(self.L.rtp_field_bytes(self.h, field_id(f), C.byref(n)), "rtp_field_bytes")
         return n.value
 
-    def upload(self, f, arr):
+    def upload(self, f, arr, blocking=True):
+        """blocking=False (rtp_upload_async): `arr` must be a page-locked, contiguous array of the field's layout that stays
+        untouched until the next sync()"""
         fid = field_id(f)
         n = self.field_bytes(fid)
         dt, shape = _np_layout(fid, n)
         a = np.ascontiguousarray(np.asarray(arr, dtype=dt).reshape(shape))
-        self._check(self.L.rtp_upload(self.h, fid, a.ctypes.data, a.nbytes), "rtp_upload")
+        if blocking:
+            self._check(self.L.rtp_upload(self.h, fid, a.ctypes.data, a.nbytes), "rtp_upload")
+        else:
+            self._check(self.L.rtp_upload_async(self.h, fid, a.ctypes.data, a.nbytes), "rtp_upload_async")
 
-    def download(self, f, out=None):
+    def download(self, f, out=None, blocking=True):
+        """blocking=False (rtp_download_async): `out` (page-locked) is complete after the next sync()"""
         fid = field_id(f)
         n = self.field_bytes(fid)
         dt, shape = _np_layout(fid, n)
         if out is None:
             out = np.empty(shape, dt)
-        self._check(self.L.rtp_download(self.h, fid, out.ctypes.data, out.nbytes), "rtp_download")
+        if blocking:
+            self._check(self.L.rtp_download(self.h, fid, out.ctypes.data, out.nbytes), "rtp_download")
+        else:
+            self._check(self.L.rtp_download_async(self.h, fid, out.ctypes.data, out.nbytes), "rtp_download_async")
         return out
 
     def device_ptr(self, f):

@@ -555,7 +555,7 @@ extern "C" int rtp_field_bytes(const rtp_handle* h, int field, size_t* bytes)
   return fieldInfo(const_cast<rtp_handle*>(h), field, &p, bytes);
 }
 
-extern "C" int rtp_upload(rtp_handle* h, int field, const void* host, size_t bytes)
+static int uploadField(rtp_handle* h, int field, const void* host, size_t bytes, bool blocking)
 {
   if (!h || !host)
     return RTP_ERR_INVALID;
@@ -582,11 +582,15 @@ extern "C" int rtp_upload(rtp_handle* h, int field, const void* host, size_t byt
     if (urc != RTP_OK)
       return urc;
   }
-  CUDA_TRY(h, cudaStreamSynchronize(h->stream)); // blocking, like the reference's CL_TRUE writes (Context.cpp:368)
+  if (blocking)
+    CUDA_TRY(h, cudaStreamSynchronize(h->stream)); // blocking, like the reference's CL_TRUE writes (Context.cpp:368)
   return RTP_OK;
 }
 
-extern "C" int rtp_download(rtp_handle* h, int field, void* host, size_t bytes)
+extern "C" int rtp_upload(rtp_handle* h, int field, const void* host, size_t bytes) { return uploadField(h, field, host, bytes, true); }
+extern "C" int rtp_upload_async(rtp_handle* h, int field, const void* host, size_t bytes) { return uploadField(h, field, host, bytes, false); }
+
+static int downloadField(rtp_handle* h, int field, void* host, size_t bytes, bool blocking)
 {
   if (!h || !host)
     return RTP_ERR_INVALID;
@@ -613,9 +617,13 @@ extern "C" int rtp_download(rtp_handle* h, int field, void* host, size_t bytes)
     if (urc != RTP_OK)
       return urc;
   }
-  CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+  if (blocking)
+    CUDA_TRY(h, cudaStreamSynchronize(h->stream));
   return RTP_OK;
 }
+
+extern "C" int rtp_download(rtp_handle* h, int field, void* host, size_t bytes) { return downloadField(h, field, host, bytes, true); }
+extern "C" int rtp_download_async(rtp_handle* h, int field, void* host, size_t bytes) { return downloadField(h, field, host, bytes, false); }
 
 extern "C" int rtp_device_ptr(rtp_handle* h, int field, void** dptr)
 {

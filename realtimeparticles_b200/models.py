@@ -219,11 +219,13 @@ class Model:
         """Which parts of update() run: physics, render-side kernels, camera sort (default: all, like the app)."""
         self.m_stepFlags = flags
 
-    def upload(self, name, arr):
-        self._h.upload(name, arr)
+    def upload(self, name, arr, blocking=True):
+        """loadBufferFromHost (Context.cpp:355-377); blocking=False: stream-ordered copy from a page-locked array"""
+        self._h.upload(name, arr, blocking)
 
-    def download(self, name):
-        return self._h.download(name)
+    def download(self, name, out=None, blocking=True):
+        """unloadBufferFromDevice (Context.cpp:379-400); blocking=False: `out` (page-locked) is complete after sync()"""
+        return self._h.download(name, out, blocking)
 
     def sync(self):
         self._h.sync()
@@ -240,10 +242,13 @@ class Model:
             flags &= ~_abi.STEP_PHYSICS
         return flags
 
-    def update(self):
+    def update(self, replay_graph=True):
         if not self.m_init:
             return
-        self._h.step(self._flags(), self.m_cameraPos)
+        if self.isProfilingEnabled() or not replay_graph:
+            self._h.step(self._flags(), self.m_cameraPos)  # plain launches (with events between the stages when profiling)
+        else:
+            self._h.step_n(1, self._flags(), self.m_cameraPos)  # the step's cached CUDA graph: one launch, same result
 
     def updateN(self, n):
         """n consecutive update() calls replayed from one CUDA graph (headless runs)."""
@@ -255,7 +260,8 @@ class Model:
         M = self.m_maxNbParticles
         pos = np.full((M, 4), np.inf, np.float32)
         pos[:, 3] = 0.0
-        pos[:len(verts)] = verts
+        k = min(len(verts), M)  # a preset larger than maxNbParticles is cut, like CudaModel::uploadParticles
+        pos[:k] = verts[:k]
         self._h.upload("p_pos", pos)
         v = np.zeros((M, 4), np.float32) if vel is None else vel
         self._h.upload("p_vel", v)
@@ -343,6 +349,8 @@ class Boids(Model):
         if not self.m_pause and self.m_targetActive:
             self.m_targetPos = self.m_target.update(3 if self.m_dimension == Dimension.dim3D else 2, self.m_rules.velocityScale)
             self.transferKernelInputsToGPU()
+            super().update(replay_graph=False)  # (the target moves every frame: new kernel parameters, nothing to replay)
+            return
         super().update()
 
     def transferJsonInputsToModel(self, inputJson):  # Boids.cpp:177-210
@@ -403,7 +411,8 @@ class Boids(Model):
         M = self.m_maxNbParticles
         pos = np.full((M, 4), np.inf, np.float32)
         pos[:, 3] = 0.0
-        pos[:len(verts)] = verts
+        k = min(len(verts), M)  # a preset larger than maxNbParticles is cut, like CudaModel::uploadParticles
+        pos[:k] = verts[:k]
         self._h.upload("p_pos", pos)
         self._h.upload("p_vel", pos)  # "Using same buffer to initialize vel", Boids.cpp:316-318
 

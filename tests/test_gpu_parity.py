@@ -494,3 +494,37 @@ def test_cpp_model_equals_python_model(kind):
         assert np.array_equal(a, b, equal_nan=True), f
     h.h = None
     L.rtpm_destroy(m)
+
+
+@pytest.mark.gpu
+def test_stream_ordered_copies_equal_blocking_copies():
+    # rtp_upload_async / rtp_download_async from page-locked buffers around the cached-graph update() (the e2e loop of
+    # bench.py: one synchronisation per frame) against the blocking calls around plain rtp_step launches: same bits
+    import torch
+    from realtimeparticles_b200 import models
+    n = 131072
+    params = models.ModelParams(currNbParticles=n, maxNbParticles=n, boxSize=(10, 10, 10), gridRes=(30, 30, 30),
+                                pCase=models.PhysicsCase.FLUIDS_DROP)  # 4k-particle block falling into a 65k-particle pool
+    out = []
+    for streamed in (False, True):
+        m = models.CreateModel(models.ModelType.FLUIDS, params)
+        m.setStepFlags(_abi.STEP_PHYSICS)
+        pos = torch.from_numpy(m.download("p_pos")).pin_memory().numpy()
+        vel = torch.from_numpy(m.download("p_vel")).pin_memory().numpy()
+        for _ in range(6):
+            if streamed:
+                m.upload("p_pos", pos, blocking=False)
+                m.upload("p_vel", vel, blocking=False)
+                m.update()
+                m.download("p_pos", out=pos, blocking=False)
+                m.download("p_vel", out=vel, blocking=False)
+                m.sync()
+            else:
+                m.upload("p_pos", pos)
+                m.upload("p_vel", vel)
+                m.update(replay_graph=False)
+                m.download("p_pos", out=pos)
+                m.download("p_vel", out=vel)
+        out.append((pos.copy(), vel.copy()))
+    assert np.array_equal(out[0][0], out[1][0], equal_nan=True) and np.array_equal(out[0][1], out[1][1], equal_nan=True)
+    assert np.isfinite(out[0][0][:m.nbParticles()]).all() and np.abs(out[0][1]).max() > 0
