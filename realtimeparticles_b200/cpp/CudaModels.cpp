@@ -282,12 +282,13 @@ void Boids::update()
   if (!m_init)
     return;
   rtp_set_boundary(m_handle, m_boundary == Boundary::CyclicWall ? RTP_BOUNDARY_CYCLIC_WALL : RTP_BOUNDARY_BOUNCING_WALL);
-  if (!m_pause && isTargetActivated())
+  const bool movingTarget = !m_pause && isTargetActivated();
+  if (movingTarget)
   {
     m_target->updatePos(m_dimension, getKernelInput<BoidsRuleKernelInputs>(0).velocityScale);
     transferKernelInputsToGPU();
   }
-  stepDevice();
+  stepDevice(!movingTarget);
 }
 
 // ------------------------------------------------------------------ Fluids (physics/ocl/Fluids.cpp)

@@ -107,12 +107,18 @@ class CudaModel : public Model
   void setStepFlags(unsigned flags) { m_stepFlags = flags; }
 
   protected:
-  void stepDevice()
+  // replayGraph: the frame is the cached CUDA graph of the step (one launch, same result; the library falls back to plain
+  // launches while OpenGL buffers are registered). Not when profiling (events between the stages) or when the kernel
+  // parameters change every frame (the moving boids target).
+  void stepDevice(bool replayGraph = true)
   {
     unsigned flags = m_stepFlags;
     if (m_pause)
       flags &= ~RTP_STEP_PHYSICS; // Fluids.cpp:409: on pause only the camera sort (and clouds colouring) run
-    rtp_step(m_handle, flags, m_camera);
+    if (replayGraph && !m_profiling)
+      rtp_step_n(m_handle, flags, m_camera, 1);
+    else
+      rtp_step(m_handle, flags, m_camera);
   }
   void uploadParticles(const std::vector<Math::float3>& verts, bool velocityIsPosition, const float* colour);
 
