@@ -28,8 +28,8 @@ static int runSlabs(int nslabs, int steps, int warmup)
     return 2;
   }
   std::vector<int> devs(nslabs);
-  for (int r = 0; r < nslabs; ++r)
-    devs[r] = (int)((long long)r * ndev / nslabs) % ndev; // contiguous slabs share a GPU when there are more slabs than GPUs
+  for (int r = 0; r < nslabs; ++r) // GPUs 0 .. nslabs-1; with more slabs than GPUs, contiguous slabs share one
+    devs[r] = nslabs <= ndev ? r : (int)((long long)r * ndev / nslabs) % ndev;
   // capacities of bench.py's run_slab_16m: ghost regions of 2 x-layers with room for 8 particles per cell, 32k-row migration messages
   const uint64_t ghostCap = nslabs > 1 ? 2ull * 120 * 120 * 8 : 0, migrateCap = nslabs > 1 ? (1ull << 15) : 1;
   const uint64_t capacity = (uint64_t)((double)(total / nslabs) * 1.10) + 2 * migrateCap + 2 * ghostCap;
