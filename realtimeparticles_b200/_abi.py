@@ -497,6 +497,7 @@ class SlabGroup:
             raise RtpError("rtp_slab_group_create failed (%d): %s" % (rc, (self.L.rtp_slab_group_last_error(None) or b"").decode()))
         self.g = g
         self.n_slabs = len(devices)
+        self._n = 0  # particles uploaded (sizes the download buffers)
         fp = fluid_params or FluidParams(450.0, 600.0, 0.010, 3, 1, 0.006, 0.001, 4, 1, 0.0004, 0.0001)
         self._check(self.L.rtp_slab_group_set_fluid_params(self.g, C.byref(fp), int(jacobi)), "rtp_slab_group_set_fluid_params")
 
