@@ -723,11 +723,11 @@ void launchFluidGather(const DeviceState& s, const GridParams& g, cudaStream_t s
   if (s.N)
     launchKernel(fluidGatherKernel, ewBlocks(s.N), EW_THREADS, st, s, g);
 }
-void launchDensityLambda(const DeviceState& s, int model, const GridParams& g, const SphConsts& c, const FluidStepParams& p,
+int launchDensityLambda(const DeviceState& s, int model, const GridParams& g, const SphConsts& c, const FluidStepParams& p,
     const float4* pred, int nbrMode, int epoch, cudaStream_t st)
 {
   if (!s.N)
-    return;
+    return 0;
   static_assert(NB_THREADS == TB_THREADS && NB_THREADS == SWEEP_BLOCK_ROWS, "tilebuild.cuh is written for the neighbour kernels' block size");
   if (nbrMode == NBR_BUILD && s.tiledBuild)
   {
@@ -736,12 +736,13 @@ void launchDensityLambda(const DeviceState& s, int model, const GridParams& g, c
       launchKernel(densityLambdaBuildKernel<TRAV_CLOUDS>, sweepBlocks(s), NB_THREADS, st, s, g, c, p.f.restDensity, p.f.relaxCFM, pred, epoch);
     else
       launchKernel(densityLambdaBuildKernel<TRAV_FLUIDS>, sweepBlocks(s), NB_THREADS, st, s, g, c, p.f.restDensity, p.f.relaxCFM, pred, epoch);
-    return;
+    return 2; // filter + build walk
   }
   if (model == RTP_MODEL_CLOUDS)
     launchKernel(densityLambdaKernel<TRAV_CLOUDS>, sweepBlocks(s), NB_THREADS, st, s, g, c, p.f.restDensity, p.f.relaxCFM, pred, nbrMode, epoch);
   else
     launchKernel(densityLambdaKernel<TRAV_FLUIDS>, sweepBlocks(s), NB_THREADS, st, s, g, c, p.f.restDensity, p.f.relaxCFM, pred, nbrMode, epoch);
+  return 1;
 }
 template <int TRAV, bool LAST>
 static void launchCorrectionArt(const DeviceState& s, const GridParams& g, const SphConsts& c, const FluidStepParams& p, const float4* pred,
@@ -819,15 +820,17 @@ void launchCloudsGather(const DeviceState& s, const GridParams& g, cudaStream_t 
   if (s.N)
     launchKernel(cloudsGatherKernel, ewBlocks(s.N), EW_THREADS, st, s, g);
 }
-void launchCloudsLaplacianTemp(const DeviceState& s, const GridParams& g, const SphConsts& c, const rtp_cloud_params& cloud, int nbrMode, cudaStream_t st)
+int launchCloudsLaplacianTemp(const DeviceState& s, const GridParams& g, const SphConsts& c, const rtp_cloud_params& cloud, int nbrMode, cudaStream_t st)
 {
   if (s.N && nbrMode == NBR_BUILD && s.tiledBuild)
   {
     launchMarginMask(s, RTP_MODEL_CLOUDS, g, c, s.posB, st);
     launchKernel(laplacianTempBuildKernel, nbBlocks(s.N), NB_THREADS, st, s, g, c, cloud.restDensity);
+    return 2; // filter + build walk
   }
-  else if (s.N)
+  if (s.N)
     launchKernel(laplacianTempKernel, nbBlocks(s.N), NB_THREADS, st, s, g, c, cloud.restDensity, nbrMode);
+  return s.N ? 1 : 0;
 }
 void launchCloudsLambdaTemp(const DeviceState& s, const GridParams& g, const SphConsts& c, const rtp_cloud_params& cloud, int nbrMode, cudaStream_t st)
 {

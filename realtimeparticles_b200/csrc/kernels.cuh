@@ -122,7 +122,8 @@ void launchFluidPredict(const DeviceState& s, const GridParams& g, const FluidSt
 // the block-cooperative filter of a list build: writes the margin mask of positions P (tilebuild.cuh)
 void launchMarginMask(const DeviceState& s, int model, const GridParams& g, const SphConsts& c, const float4* P, cudaStream_t st);
 void launchFluidGather(const DeviceState& s, const GridParams& g, cudaStream_t st);
-void launchDensityLambda(const DeviceState& s, int model, const GridParams& g, const SphConsts& c, const FluidStepParams& p,
+// (returns the number of kernels launched: the list build of a step is a filter + a walk)
+int launchDensityLambda(const DeviceState& s, int model, const GridParams& g, const SphConsts& c, const FluidStepParams& p,
     const float4* pred, int nbrMode, int epoch, cudaStream_t st);
 // last: also integrates velocity (updateVel) and, without vorticity, copies the position (updatePosition)
 void launchCorrection(const DeviceState& s, int model, const GridParams& g, const SphConsts& c, const FluidStepParams& p,
@@ -137,7 +138,7 @@ void launchXsph(const DeviceState& s, int model, const GridParams& g, const SphC
 void launchCloudsInitFields(const DeviceState& s, const GridParams& g, const rtp_cloud_params& cloud, cudaStream_t st);
 void launchCloudsThermoPredict(const DeviceState& s, const GridParams& g, const rtp_cloud_params& cloud, u32* keysOut, cudaStream_t st);
 void launchCloudsGather(const DeviceState& s, const GridParams& g, cudaStream_t st);
-void launchCloudsLaplacianTemp(const DeviceState& s, const GridParams& g, const SphConsts& c, const rtp_cloud_params& cloud, int nbrMode, cudaStream_t st);
+int launchCloudsLaplacianTemp(const DeviceState& s, const GridParams& g, const SphConsts& c, const rtp_cloud_params& cloud, int nbrMode, cudaStream_t st);
 void launchCloudsLambdaTemp(const DeviceState& s, const GridParams& g, const SphConsts& c, const rtp_cloud_params& cloud, int nbrMode, cudaStream_t st);
 void launchCloudsCorrectTemp(const DeviceState& s, const GridParams& g, const SphConsts& c, const rtp_cloud_params& cloud, int nbrMode, cudaStream_t st);
 void launchCloudsFinish(const DeviceState& s, const GridParams& g, const rtp_cloud_params& cloud, const float4* pred, bool smoothing, cudaStream_t st);

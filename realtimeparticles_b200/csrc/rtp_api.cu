@@ -958,24 +958,24 @@ static int enqueueStep(rtp_handle* h, unsigned flags, const float cam[3], bool p
       rec.mark("adjustEndCell");
       if (clouds && h->cp.isTempSmoothingEnabled)
       {
-        launchCloudsLaplacianTemp(s, g, c, h->cp, lists ? NBR_BUILD : NBR_OFF, st);
+        launches += launchCloudsLaplacianTemp(s, g, c, h->cp, lists ? NBR_BUILD : NBR_OFF, st);
         rec.mark("laplacianTemp");
         launchCloudsLambdaTemp(s, g, c, h->cp, lists ? NBR_USE : NBR_OFF, st);
         rec.mark("lambdaTemp");
         launchCloudsCorrectTemp(s, g, c, h->cp, lists ? NBR_USE : NBR_OFF, st);
         rec.mark("correctTemp");
-        launches += 3;
+        launches += 2;
       }
       float4* cur = s.pred1;
       float4* nxt = s.pred0;
       for (int it = 0; it < h->jacobi; ++it)
       {
         const bool last = it == h->jacobi - 1;
-        launchDensityLambda(s, model, g, c, h->fp, cur, !lists ? NBR_OFF : (it == 0 ? NBR_BUILD : NBR_BUILD_IF_INVALID), it, st);
+        launches += launchDensityLambda(s, model, g, c, h->fp, cur, !lists ? NBR_OFF : (it == 0 ? NBR_BUILD : NBR_BUILD_IF_INVALID), it, st);
         rec.mark("densityLambda");
         launchCorrection(s, model, g, c, h->fp, h->cp, cur, nxt, last, debug, lists ? NBR_USE : NBR_OFF, it, st);
         rec.mark("correction");
-        launches += 2;
+        launches += 1;
         float4* t = cur;
         cur = nxt;
         nxt = t;
