@@ -1,3 +1,4 @@
+# ncu --set full of every kernel of one settled boids step and one clouds step (through gpurun); summarised into profiles/ by scripts/ncu_summary.py.
 mkdir -p gpurun_out
 timeout 300 python -m pytest tests/test_sharded.py -m gpu -q -x -k "library" 2>&1 | tail -2
 # boids: the 7 launches of step 320 (graph replays are not profiled: only the last, plain step is)

@@ -1,3 +1,4 @@
+# Round-end validation on a GPU box (through gpurun): the -m gpu tests, smoke(), the default bench line, the C++ headless harness.
 mkdir -p gpurun_out
 (time timeout 400 python -m pytest tests -m gpu -x -q) > gpurun_out/final_gputests.log 2>&1; tail -5 gpurun_out/final_gputests.log
 python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -1
