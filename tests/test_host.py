@@ -204,3 +204,25 @@ def test_target_trajectory_matches_reference():
     from oracle import ref_py as R
     if R.available():
         assert np.array_equal(R.target_trajectory(10, 3, 0.5, 50), gold["dim3_v05"][:50])
+
+
+def test_bench_reference_arm_contract():
+    # `bench.py --impl reference`: one JSON line with the GPU arm's metric / unit / config, impl = "reference", a cpu_baseline
+    # describing this run and an e2e object without transfers; under torchrun only rank 0 prints
+    import json
+    import subprocess
+    import sys
+    sys.path.insert(0, ROOT)
+    import bench
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "0"],
+                       capture_output=True, text=True, timeout=600, cwd=ROOT)
+    assert r.returncode == 0, r.stderr[-500:]
+    d = json.loads(r.stdout.strip().splitlines()[-1])
+    assert d["impl"] == "reference" and d["unit"] == "particle-updates/s" and d["higher_is_better"] is True
+    assert d["config"] == bench.headline_config(1) and d["config"]["workload"] == "pbf_dam_130k_I3_vorticity_xsph"
+    assert d["cpu_baseline"]["kind"] in ("reference", "port") and d["cpu_baseline"]["cores"] >= 1 and d["cpu_baseline"]["value"] == d["value"] > 0
+    assert d["e2e"] == {"value": d["value"], "unit": d["unit"], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+    env = dict(os.environ, RANK="1", LOCAL_RANK="1", WORLD_SIZE="2")
+    r1 = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--gpus", "2", "--steps", "1", "--warmup", "0"],
+                        capture_output=True, text=True, timeout=120, cwd=ROOT, env=env)
+    assert r1.returncode == 0 and r1.stdout.strip() == ""  # the other ranks exit 0 without work
